@@ -172,4 +172,4 @@ def energy_forces(fn, pos_np, *args, **kw):
     pos = torch.tensor(np.asarray(pos_np, dtype=np.float64), requires_grad=True)
     e = fn(pos, *args, **kw)
     (g,) = torch.autograd.grad(e, pos)
-    return float(e), -g.numpy()
+    return float(e.detach()), -g.numpy()

@@ -1,0 +1,773 @@
+// PaiNN ensemble: forward + hand-written backward (forces) for a batch of structures x models.
+// Replaces NFF Painn.forward + autograd energy_grad (reference call site
+// mcmc/calculators/calculators.py:484 via EnsembleNFF.calculate); algorithm restated in
+// oracle/painn.py, dataflow prototyped and checked against autograd in oracle/painn_manual.py.
+//
+// Dataflow (per conv layer, all models x all atoms at once; activations stay in HBM/L2):
+//   F1 h1  = s_in W1^T + b1                      GEMM  [A,128]x[128,128]
+//   F2 phi = swish(h1) W2^T + b2                 GEMM  [A,128]x[128,384]   (swish on the A load)
+//   F3 message: thread f of receiver i walks i's CSR row serially (deterministic), builds the
+//      filter w(d) = Wd.(rbf*env) + bd*env in registers, gathers phi_j / v_j      -> s_mid, v_mid
+//   F4 [Uv|Vv] = v_mid [U^T|V^T]                 GEMM  [3A,128]x[128,256]
+//   F5 nrm = ||Vv||  -> cat = [s_mid | nrm]
+//   F6 h3 = cat W3^T + b3 ; F7 a = swish(h3) W4^T + b4
+//   F8 s_out = s_mid + <Uv,Vv> a_sv + a_ss ; v_out = v_mid + Uv a_vv
+// Backward mirrors it; the message backward is a GATHER over the receiver's own row in which
+// edge i<-j is handled together with its reverse j<-i (same d, unit negated), so sender-side
+// gradients and the position gradient of atom i are produced by atom i's CTA: no atomics.
+//
+// Vector features are stored [A,3,128] (Cartesian-major) so U/V act as plain row GEMMs.
+#include <math.h>
+
+#include "common.cuh"
+#include "painn_layout.h"
+
+namespace {
+using namespace painn;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
+__device__ __forceinline__ float dswishf_(float x) {
+  float s = sigmoidf_(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
+// ------------------------------------------------------------------------------------------
+// SGEMM (fp32 FMA):  C[M,N] (op)= T(A)[M,K] . B[K,N],  batched over models on blockIdx.z.
+//   AMODE 0: A as is; 1: swish(A); 2: dswish(A) * avec[k]
+//   EPI   0: C = acc; 1: C = acc + bias[n]; 2: C = acc * dswish(aux[m,n]); 3: C += acc
+// Tile 128 x BN x 16, 256 threads, 8 x (BN/16) outputs per thread, register-prefetch pipeline.
+// ------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A; int lda; long long sA;
+  const float* B; int ldb; long long sB;
+  const float* bias; long long sBias;
+  const float* aux; int ldaux; long long sAux;
+  const float* avec; long long sAvec;
+  float* C; int ldc; long long sC;
+  int M, N, K;
+};
+
+template <int BN, int AMODE, int EPI>
+__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
+  constexpr int BM = 128, BK = 16, TN = BN / 16, NB4 = (BK * BN / 4) / 256;  // float4 B loads per thread
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int model = blockIdx.z;
+  const float* __restrict__ A = g.A + (long long)model * g.sA;
+  const float* __restrict__ B = g.B + (long long)model * g.sB;
+  float* __restrict__ C = g.C + (long long)model * g.sC;
+  const float* __restrict__ avec = AMODE == 2 ? g.avec + (long long)model * g.sAvec : nullptr;
+
+  const int a_row = tid >> 2, a_k = (tid & 3) * 4;  // rows a_row, a_row+64 ; k offset a_k
+  float4 ra[2], rb[NB4 > 0 ? NB4 : 1];
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = m0 + a_row + 64 * h;
+      if (r < g.M) {
+        ra[h] = *reinterpret_cast<const float4*>(A + (long long)r * g.lda + k0 + a_k);
+        if (AMODE == 1) {
+          ra[h].x = swishf_(ra[h].x); ra[h].y = swishf_(ra[h].y); ra[h].z = swishf_(ra[h].z); ra[h].w = swishf_(ra[h].w);
+        } else if (AMODE == 2) {
+          const float4 av = *reinterpret_cast<const float4*>(avec + k0 + a_k);
+          ra[h].x = dswishf_(ra[h].x) * av.x; ra[h].y = dswishf_(ra[h].y) * av.y;
+          ra[h].z = dswishf_(ra[h].z) * av.z; ra[h].w = dswishf_(ra[h].w) * av.w;
+        }
+      } else {
+        ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NB4; ++q) {
+      const int idx = tid + q * 256;
+      const int r = idx / (BN / 4), c4 = idx % (BN / 4);
+      rb[q] = *reinterpret_cast<const float4*>(B + (long long)(k0 + r) * g.ldb + n0 + c4 * 4);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = a_row + 64 * h;
+      As[buf][a_k + 0][r] = ra[h].x; As[buf][a_k + 1][r] = ra[h].y;
+      As[buf][a_k + 2][r] = ra[h].z; As[buf][a_k + 3][r] = ra[h].w;
+    }
+#pragma unroll
+    for (int q = 0; q < NB4; ++q) {
+      const int idx = tid + q * 256;
+      const int r = idx / (BN / 4), c4 = idx % (BN / 4);
+      *reinterpret_cast<float4*>(&Bs[buf][r][c4 * 4]) = rb[q];
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  const int nk = g.K / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[8], b[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      if (TN == 8) {
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][(BN / 2) + tx * 4]);
+        b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+  const float* __restrict__ bias = EPI == 1 ? g.bias + (long long)model * g.sBias : nullptr;
+  const float* __restrict__ aux = EPI == 2 ? g.aux + (long long)model * g.sAux : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (r >= g.M) continue;
+#pragma unroll
+    for (int h = 0; h < TN / 4; ++h) {
+      const int c = n0 + (h == 0 ? tx * 4 : (BN / 2) + tx * 4);
+      float4 v = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+      if (EPI == 1) {
+        const float4 bb = *reinterpret_cast<const float4*>(bias + c);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+      } else if (EPI == 2) {
+        const float4 x = *reinterpret_cast<const float4*>(aux + (long long)r * g.ldaux + c);
+        v.x *= dswishf_(x.x); v.y *= dswishf_(x.y); v.z *= dswishf_(x.z); v.w *= dswishf_(x.w);
+      } else if (EPI == 3) {
+        const float4 o = *reinterpret_cast<const float4*>(C + (long long)r * g.ldc + c);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *reinterpret_cast<float4*>(C + (long long)r * g.ldc + c) = v;
+    }
+  }
+}
+
+template <int BN, int AMODE, int EPI>
+int launch_gemm(const GemmArgs& g, int n_models, cudaStream_t st) {
+  dim3 grid(ceil_div(g.M, 128), g.N / BN, n_models);
+  gemm_kernel<BN, AMODE, EPI><<<grid, 256, 0, st>>>(g);
+  VSSR_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Edge geometry (shared by all models and layers) + excluded volume.
+// One warp per receiver atom; lanes over the row.  Record per edge:
+//   eg  float4 (ux,uy,uz,d)   d < 0  <=> edge outside the model cutoff for this evaluation
+//   re  [24]  = rbf_n*env (n=1..20), env, denv, 0, 0
+//   dre [20]  = d(rbf_n*env)/dd
+// grad0[a] = excluded-volume gradient (same for every model); evex[a] its energy.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) edge_geometry_kernel(
+    const float* __restrict__ pos, const int32_t* __restrict__ atom_ptr, const float* __restrict__ cell, int n_struct,
+    int n_atoms, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    const int8_t* __restrict__ shift, long long e_cap, float cutoff, float4* __restrict__ eg, float* __restrict__ re,
+    float* __restrict__ dre, float* __restrict__ evex, float* __restrict__ grad0) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n_atoms) return;
+  const int b = struct_of_atom(atom_ptr, n_struct, i);
+  float c[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c[k] = __ldg(cell + 9 * b + k);
+  const float xi = __ldg(pos + 3 * i), yi = __ldg(pos + 3 * i + 1), zi = __ldg(pos + 3 * i + 2);
+  long long e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
+  if (e1 > e_cap) e1 = e_cap;
+  const float pi_over_rc = 3.14159265358979323846f / cutoff;
+  float ev = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+  for (long long e = e0 + lane; e < e1; e += 32) {
+    const int j = __ldg(col + e);
+    const char4 s = reinterpret_cast<const char4*>(shift)[e];
+    const float f0 = (float)s.x, f1 = (float)s.y, f2 = (float)s.z;
+    // same fp32 offset arithmetic as the neighbour list
+    const float ox = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[0]), __fmul_rn(f1, c[3])), __fmul_rn(f2, c[6]));
+    const float oy = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[1]), __fmul_rn(f1, c[4])), __fmul_rn(f2, c[7]));
+    const float oz = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[2]), __fmul_rn(f1, c[5])), __fmul_rn(f2, c[8]));
+    const float rx = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j), xi), ox);
+    const float ry = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j + 1), yi), oy);
+    const float rz = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j + 2), zi), oz);
+    const float d2p = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+    const float dp = sqrtf(d2p);
+    float* rrow = re + e * 24;
+    float* drow = dre + e * 20;
+    if (!(dp <= cutoff)) {
+      eg[e] = make_float4(0.f, 0.f, 0.f, -1.f);
+      continue;
+    }
+    const float d = sqrtf((rx * rx + 1e-10f) + (ry * ry + 1e-10f) + (rz * rz + 1e-10f));
+    const float inv_d = 1.0f / d;
+    const float ux = rx * inv_d, uy = ry * inv_d, uz = rz * inv_d;
+    eg[e] = make_float4(ux, uy, uz, d);
+    float env = 0.f, denv = 0.f;
+    const bool inside = d < cutoff;
+    if (inside) {
+      float sn, cs;
+      sincosf(pi_over_rc * d, &sn, &cs);
+      env = 0.5f * (cs + 1.0f);
+      denv = -0.5f * pi_over_rc * sn;
+    }
+#pragma unroll
+    for (int n = 0; n < NRBF; ++n) {
+      float r = 0.f, dr = 0.f;
+      if (inside) {
+        const float coef = (float)(n + 1) * pi_over_rc;
+        float sn, cs;
+        sincosf(coef * d, &sn, &cs);
+        r = sn * inv_d;
+        dr = (coef * cs - r) * inv_d;
+      }
+      rrow[n] = r * env;
+      drow[n] = dr * env + r * denv;
+    }
+    rrow[20] = env; rrow[21] = denv; rrow[22] = 0.f; rrow[23] = 0.f;
+    // excluded volume (sigma/d)^12 on the plain distance
+    const float q = 1.5f / dp;
+    const float q2 = q * q, q4 = q2 * q2;
+    const float vex = q4 * q4 * q4;
+    ev += vex;
+    const float dv = -12.0f * vex / dp;     // dvex/dd
+    const float gg = -2.0f * dv;            // edge A and its reverse B
+    gx += gg * ux; gy += gg * uy; gz += gg * uz;
+  }
+  ev = warp_sum(ev); gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
+  if (lane == 0) {
+    evex[i] = ev;
+    grad0[3 * i] = gx; grad0[3 * i + 1] = gy; grad0[3 * i + 2] = gz;
+  }
+}
+
+// s0[m][a][:] = embed_m[z[a]][:]
+__global__ void embed_kernel(const float* __restrict__ weights, const int32_t* __restrict__ z, int n_atoms,
+                             float* __restrict__ s0) {
+  const int m = blockIdx.y;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  if (idx >= (long long)n_atoms * (F / 4)) return;
+  const int a = (int)(idx / (F / 4)), f4 = (int)(idx % (F / 4));
+  int zz = __ldg(z + a);
+  zz = zz < 0 ? 0 : (zz >= NEMB ? NEMB - 1 : zz);
+  const float4* emb = reinterpret_cast<const float4*>(weights + (long long)m * W_TOTAL + W_EMBED);
+  reinterpret_cast<float4*>(s0 + (long long)m * n_atoms * F)[idx] = emb[zz * (F / 4) + f4];
+}
+
+// ------------------------------------------------------------------------------------------
+// F3: message passing, forward.  grid (ceil(A/APB), M), 128 threads (thread = feature f).
+// ------------------------------------------------------------------------------------------
+constexpr int MSG_APB = 4;
+
+template <bool FIRST>
+__global__ void __launch_bounds__(128) message_fwd_kernel(
+    const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ col, long long e_cap, const float4* __restrict__ eg, const float* __restrict__ re,
+    const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
+    float* __restrict__ cat, float* __restrict__ v_mid) {
+  const int m = blockIdx.y, f = threadIdx.x;
+  const float* __restrict__ wl = weights + (long long)m * W_TOTAL + W_LAYER0 + (long long)layer * L_SIZE;
+  float wd0[NRBF], wd1[NRBF], wd2[NRBF];
+#pragma unroll
+  for (int n = 0; n < NRBF; ++n) {
+    wd0[n] = __ldg(wl + L_WDT + n * F3 + f);
+    wd1[n] = __ldg(wl + L_WDT + n * F3 + F + f);
+    wd2[n] = __ldg(wl + L_WDT + n * F3 + 2 * F + f);
+  }
+  const float bd0 = __ldg(wl + L_BD + f), bd1 = __ldg(wl + L_BD + F + f), bd2 = __ldg(wl + L_BD + 2 * F + f);
+  const long long mA = (long long)m * n_atoms;
+  phi += mA * F3; s_in += mA * F; cat += mA * 2 * F; v_mid += mA * 3 * F;
+  if (!FIRST) v_in += mA * 3 * F;
+
+  const int i_end = min(n_atoms, (int)(blockIdx.x + 1) * MSG_APB);
+  for (int i = blockIdx.x * MSG_APB; i < i_end; ++i) {
+    long long e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
+    if (e1 > e_cap) e1 = e_cap;
+    float ds = 0.f, dvx = 0.f, dvy = 0.f, dvz = 0.f;
+    for (long long e = e0; e < e1; ++e) {
+      const float4 g = __ldg(eg + e);
+      if (g.w < 0.f) continue;
+      const int j = __ldg(col + e);
+      const float p0 = __ldg(phi + (long long)j * F3 + f);
+      const float p1 = __ldg(phi + (long long)j * F3 + F + f);
+      const float p2 = __ldg(phi + (long long)j * F3 + 2 * F + f);
+      float vjx = 0.f, vjy = 0.f, vjz = 0.f;
+      if (!FIRST) {
+        vjx = __ldg(v_in + (long long)j * 3 * F + f);
+        vjy = __ldg(v_in + (long long)j * 3 * F + F + f);
+        vjz = __ldg(v_in + (long long)j * 3 * F + 2 * F + f);
+      }
+      const float4* r4 = reinterpret_cast<const float4*>(re + e * 24);
+      float rr[24];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float4 t = __ldg(r4 + q);
+        rr[4 * q] = t.x; rr[4 * q + 1] = t.y; rr[4 * q + 2] = t.z; rr[4 * q + 3] = t.w;
+      }
+      const float env = rr[20];
+      float w0 = bd0 * env, w1 = bd1 * env, w2 = bd2 * env;
+#pragma unroll
+      for (int n = 0; n < NRBF; ++n) {
+        w0 = fmaf(wd0[n], rr[n], w0);
+        w1 = fmaf(wd1[n], rr[n], w1);
+        w2 = fmaf(wd2[n], rr[n], w2);
+      }
+      const float x0 = p0 * w0, x1 = p1 * w1, x2 = p2 * w2;
+      ds += x1;
+      dvx += x2 * g.x; dvy += x2 * g.y; dvz += x2 * g.z;
+      if (!FIRST) { dvx = fmaf(x0, vjx, dvx); dvy = fmaf(x0, vjy, dvy); dvz = fmaf(x0, vjz, dvz); }
+    }
+    const float s0 = __ldg(s_in + (long long)i * F + f);
+    cat[(long long)i * 2 * F + f] = s0 + ds;
+    float vx = dvx, vy = dvy, vz = dvz;
+    if (!FIRST) {
+      vx += __ldg(v_in + (long long)i * 3 * F + f);
+      vy += __ldg(v_in + (long long)i * 3 * F + F + f);
+      vz += __ldg(v_in + (long long)i * 3 * F + 2 * F + f);
+    }
+    v_mid[(long long)i * 3 * F + f] = vx;
+    v_mid[(long long)i * 3 * F + F + f] = vy;
+    v_mid[(long long)i * 3 * F + 2 * F + f] = vz;
+  }
+}
+
+// F5: cat[a][128+f] = sqrt(sum_c (Vv[c][f]^2 + 1e-15))
+__global__ void nrm_kernel(const float* __restrict__ UV, int n_atoms, float* __restrict__ cat) {
+  const int m = blockIdx.y;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_atoms * F) return;
+  const long long a = idx / F;
+  const int f = (int)(idx % F);
+  const float* uv = UV + ((long long)m * n_atoms + a) * 3 * 2 * F;
+  const float x = uv[F + f], y = uv[2 * F + F + f], zz = uv[4 * F + F + f];
+  cat[((long long)m * n_atoms + a) * 2 * F + F + f] = sqrtf((x * x + 1e-15f) + (y * y + 1e-15f) + (zz * zz + 1e-15f));
+}
+
+// F8: s_out = s_mid + <Uv,Vv> a_sv + a_ss ; v_out = v_mid + Uv a_vv
+__global__ void update_fwd_kernel(const float* __restrict__ UV, const float* __restrict__ a, const float* __restrict__ cat,
+                                  const float* __restrict__ v_mid, int n_atoms, float* __restrict__ s_out,
+                                  float* __restrict__ v_out) {
+  const int m = blockIdx.y;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_atoms * F) return;
+  const long long am = (long long)m * n_atoms + idx / F;
+  const int f = (int)(idx % F);
+  const float* uv = UV + am * 6 * F;
+  const float* aa = a + am * F3;
+  const float ux = uv[f], uy = uv[2 * F + f], uz = uv[4 * F + f];
+  const float vx = uv[F + f], vy = uv[3 * F + f], vz = uv[5 * F + f];
+  const float inner = ux * vx + uy * vy + uz * vz;
+  const float avv = aa[f], asv = aa[F + f], ass = aa[2 * F + f];
+  s_out[am * F + f] = cat[am * 2 * F + f] + inner * asv + ass;
+  const float* vm = v_mid + am * 3 * F;
+  float* vo = v_out + am * 3 * F;
+  vo[f] = vm[f] + ux * avv;
+  vo[F + f] = vm[F + f] + uy * avv;
+  vo[2 * F + f] = vm[2 * F + f] + uz * avv;
+}
+
+// readout energy: e_atom[m][a] = swish(h5).w6 + b6 + evex[a]; one warp per (m, a)
+__global__ void __launch_bounds__(128) readout_energy_kernel(const float* __restrict__ weights, const float* __restrict__ h5,
+                                                             const float* __restrict__ evex, int n_atoms,
+                                                             float* __restrict__ e_atom) {
+  const int m = blockIdx.y;
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (a >= n_atoms) return;
+  const float* w = weights + (long long)m * W_TOTAL;
+  const float* h = h5 + ((long long)m * n_atoms + a) * FH;
+  float acc = swishf_(h[lane]) * __ldg(w + R_W6 + lane) + swishf_(h[lane + 32]) * __ldg(w + R_W6 + lane + 32);
+  acc = warp_sum(acc);
+  if (lane == 0) e_atom[(long long)m * n_atoms + a] = acc + __ldg(w + R_B6) + evex[a];
+}
+
+// per-structure energy sum in fp64, one warp per (m, structure), fixed order
+__global__ void __launch_bounds__(128) energy_reduce_kernel(const float* __restrict__ e_atom, const int32_t* __restrict__ atom_ptr,
+                                                            int n_struct, int n_atoms, double* __restrict__ energy) {
+  const int m = blockIdx.y;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= n_struct) return;
+  const int a0 = atom_ptr[b], a1 = atom_ptr[b + 1];
+  double acc = 0.0;
+  for (int a = a0 + lane; a < a1; a += 32) acc += (double)e_atom[(long long)m * n_atoms + a];
+  acc = warp_sum(acc);
+  if (lane == 0) energy[(long long)m * n_struct + b] = acc;
+}
+
+// grad[m][a][c] = grad0[a][c]  (excluded-volume part, identical for all models)
+__global__ void grad_init_kernel(const float* __restrict__ grad0, int n3, float* __restrict__ grad) {
+  const int m = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n3) grad[(long long)m * n3 + idx] = grad0[idx];
+}
+
+// B8: update elementwise backward.  in: ds, dv, UV, a.  out: da[A,384], dUV[A,3,256]
+__global__ void update_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ dv, const float* __restrict__ UV,
+                                  const float* __restrict__ a, int n_atoms, float* __restrict__ da,
+                                  float* __restrict__ dUV) {
+  const int m = blockIdx.y;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_atoms * F) return;
+  const long long am = (long long)m * n_atoms + idx / F;
+  const int f = (int)(idx % F);
+  const float* uv = UV + am * 6 * F;
+  const float* aa = a + am * F3;
+  const float ux = uv[f], uy = uv[2 * F + f], uz = uv[4 * F + f];
+  const float vx = uv[F + f], vy = uv[3 * F + f], vz = uv[5 * F + f];
+  const float gs = ds[am * F + f];
+  const float* gv = dv + am * 3 * F;
+  const float gvx = gv[f], gvy = gv[F + f], gvz = gv[2 * F + f];
+  const float avv = aa[f], asv = aa[F + f];
+  const float inner = ux * vx + uy * vy + uz * vz;
+  float* d = da + am * F3;
+  d[f] = gvx * ux + gvy * uy + gvz * uz;
+  d[F + f] = gs * inner;
+  d[2 * F + f] = gs;
+  const float t = gs * asv;
+  float* du = dUV + am * 6 * F;
+  du[f] = gvx * avv + t * vx;       du[F + f] = t * ux;
+  du[2 * F + f] = gvy * avv + t * vy; du[3 * F + f] = t * uy;
+  du[4 * F + f] = gvz * avv + t * vz; du[5 * F + f] = t * uz;
+}
+
+// B5: ds += dcat[:128] ; dVv[c][f] += dcat[128+f]/nrm[f] * Vv[c][f]
+__global__ void nrm_bwd_kernel(const float* __restrict__ dcat, const float* __restrict__ cat, const float* __restrict__ UV,
+                               int n_atoms, float* __restrict__ ds, float* __restrict__ dUV) {
+  const int m = blockIdx.y;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_atoms * F) return;
+  const long long am = (long long)m * n_atoms + idx / F;
+  const int f = (int)(idx % F);
+  ds[am * F + f] += dcat[am * 2 * F + f];
+  const float t = dcat[am * 2 * F + F + f] / cat[am * 2 * F + F + f];
+  const float* uv = UV + am * 6 * F;
+  float* du = dUV + am * 6 * F;
+  du[F + f] += t * uv[F + f];
+  du[3 * F + f] += t * uv[3 * F + f];
+  du[5 * F + f] += t * uv[5 * F + f];
+}
+
+// ------------------------------------------------------------------------------------------
+// B3: message passing, backward (gather over receiver row; edge A = i<-j, edge B = j<-i).
+// Outputs: dphi[i] (skipped for the first layer), dv_in[i] = dv_mid[i] + sender terms (skipped
+// for the first layer), grad[m][i] += position gradient.
+// ------------------------------------------------------------------------------------------
+template <bool FIRST>
+__global__ void __launch_bounds__(128) message_bwd_kernel(
+    const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ col, long long e_cap, const float4* __restrict__ eg, const float* __restrict__ re,
+    const float* __restrict__ dre, const float* __restrict__ phi, const float* __restrict__ v_in,
+    const float* __restrict__ ds, const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in,
+    float* __restrict__ grad) {
+  __shared__ float red[4][3];
+  const int m = blockIdx.y, f = threadIdx.x, lane = f & 31, wid = f >> 5;
+  const float* __restrict__ wl = weights + (long long)m * W_TOTAL + W_LAYER0 + (long long)layer * L_SIZE;
+  float wd0[NRBF], wd1[NRBF], wd2[NRBF];
+#pragma unroll
+  for (int n = 0; n < NRBF; ++n) {
+    wd0[n] = __ldg(wl + L_WDT + n * F3 + f);
+    wd1[n] = __ldg(wl + L_WDT + n * F3 + F + f);
+    wd2[n] = __ldg(wl + L_WDT + n * F3 + 2 * F + f);
+  }
+  const float bd0 = __ldg(wl + L_BD + f), bd1 = __ldg(wl + L_BD + F + f), bd2 = __ldg(wl + L_BD + 2 * F + f);
+  const long long mA = (long long)m * n_atoms;
+  phi += mA * F3; ds += mA * F; dv += mA * 3 * F; grad += mA * 3;
+  if (!FIRST) { v_in += mA * 3 * F; dphi += mA * F3; dv_in += mA * 3 * F; }
+
+  const int i_end = min(n_atoms, (int)(blockIdx.x + 1) * MSG_APB);
+  for (int i = blockIdx.x * MSG_APB; i < i_end; ++i) {
+    long long e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
+    if (e1 > e_cap) e1 = e_cap;
+    const float gsi = __ldg(ds + (long long)i * F + f);
+    const float gvix = __ldg(dv + (long long)i * 3 * F + f);
+    const float gviy = __ldg(dv + (long long)i * 3 * F + F + f);
+    const float gviz = __ldg(dv + (long long)i * 3 * F + 2 * F + f);
+    const float pi0 = __ldg(phi + (long long)i * F3 + f);
+    const float pi1 = __ldg(phi + (long long)i * F3 + F + f);
+    const float pi2 = __ldg(phi + (long long)i * F3 + 2 * F + f);
+    float vix = 0.f, viy = 0.f, viz = 0.f;
+    if (!FIRST) {
+      vix = __ldg(v_in + (long long)i * 3 * F + f);
+      viy = __ldg(v_in + (long long)i * 3 * F + F + f);
+      viz = __ldg(v_in + (long long)i * 3 * F + 2 * F + f);
+    }
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;        // dphi_i
+    float dvx = 0.f, dvy = 0.f, dvz = 0.f;        // sender-side dv_in
+    float gx = 0.f, gy = 0.f, gz = 0.f;           // per-feature partial of dE/dx_i
+    for (long long e = e0; e < e1; ++e) {
+      const float4 g = __ldg(eg + e);
+      if (g.w < 0.f) continue;
+      const int j = __ldg(col + e);
+      const float pj0 = __ldg(phi + (long long)j * F3 + f);
+      const float pj1 = __ldg(phi + (long long)j * F3 + F + f);
+      const float pj2 = __ldg(phi + (long long)j * F3 + 2 * F + f);
+      const float gsj = __ldg(ds + (long long)j * F + f);
+      const float gvjx = __ldg(dv + (long long)j * 3 * F + f);
+      const float gvjy = __ldg(dv + (long long)j * 3 * F + F + f);
+      const float gvjz = __ldg(dv + (long long)j * 3 * F + 2 * F + f);
+      float vjx = 0.f, vjy = 0.f, vjz = 0.f;
+      if (!FIRST) {
+        vjx = __ldg(v_in + (long long)j * 3 * F + f);
+        vjy = __ldg(v_in + (long long)j * 3 * F + F + f);
+        vjz = __ldg(v_in + (long long)j * 3 * F + 2 * F + f);
+      }
+      const float4* r4 = reinterpret_cast<const float4*>(re + e * 24);
+      const float4* d4 = reinterpret_cast<const float4*>(dre + e * 20);
+      float rr[24], dr[20];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float4 t = __ldg(r4 + q);
+        rr[4 * q] = t.x; rr[4 * q + 1] = t.y; rr[4 * q + 2] = t.z; rr[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float4 t = __ldg(d4 + q);
+        dr[4 * q] = t.x; dr[4 * q + 1] = t.y; dr[4 * q + 2] = t.z; dr[4 * q + 3] = t.w;
+      }
+      const float env = rr[20], denv = rr[21];
+      float w0 = bd0 * env, w1 = bd1 * env, w2 = bd2 * env;
+      float q0 = bd0 * denv, q1 = bd1 * denv, q2 = bd2 * denv;
+#pragma unroll
+      for (int n = 0; n < NRBF; ++n) {
+        w0 = fmaf(wd0[n], rr[n], w0); w1 = fmaf(wd1[n], rr[n], w1); w2 = fmaf(wd2[n], rr[n], w2);
+        q0 = fmaf(wd0[n], dr[n], q0); q1 = fmaf(wd1[n], dr[n], q1); q2 = fmaf(wd2[n], dr[n], q2);
+      }
+      // edge A: i receives from j
+      const float dxA1 = gsi;
+      const float dxA2 = gvix * g.x + gviy * g.y + gviz * g.z;
+      const float dxA0 = FIRST ? 0.f : (gvix * vjx + gviy * vjy + gviz * vjz);
+      // edge B: j receives from i (unit negated)
+      const float dxB1 = gsj;
+      const float dxB2 = -(gvjx * g.x + gvjy * g.y + gvjz * g.z);
+      const float dxB0 = FIRST ? 0.f : (gvjx * vix + gvjy * viy + gvjz * viz);
+      if (!FIRST) {
+        dp0 = fmaf(dxB0, w0, dp0); dp1 = fmaf(dxB1, w1, dp1); dp2 = fmaf(dxB2, w2, dp2);
+        const float t = pi0 * w0;
+        dvx = fmaf(t, gvjx, dvx); dvy = fmaf(t, gvjy, dvy); dvz = fmaf(t, gvjz, dvz);
+      }
+      // d(filter) chain: dd = sum_k (dwA_k + dwB_k) q_k
+      const float dd = (dxA0 * pj0 + dxB0 * pi0) * q0 + (dxA1 * pj1 + dxB1 * pi1) * q1 + (dxA2 * pj2 + dxB2 * pi2) * q2;
+      // unit-vector chain: delta = duA - duB,  duA = gv_i * (phi_j2 w2), duB = gv_j * (phi_i2 w2)
+      const float ta = pj2 * w2, tb = pi2 * w2;
+      const float ex = gvix * ta - gvjx * tb, ey = gviy * ta - gvjy * tb, ez = gviz * ta - gvjz * tb;
+      const float proj = ex * g.x + ey * g.y + ez * g.z;
+      const float inv_d = 1.0f / g.w;
+      gx -= dd * g.x + (ex - proj * g.x) * inv_d;
+      gy -= dd * g.y + (ey - proj * g.y) * inv_d;
+      gz -= dd * g.z + (ez - proj * g.z) * inv_d;
+    }
+    if (!FIRST) {
+      dphi[(long long)i * F3 + f] = dp0;
+      dphi[(long long)i * F3 + F + f] = dp1;
+      dphi[(long long)i * F3 + 2 * F + f] = dp2;
+      dv_in[(long long)i * 3 * F + f] = gvix + dvx;
+      dv_in[(long long)i * 3 * F + F + f] = gviy + dvy;
+      dv_in[(long long)i * 3 * F + 2 * F + f] = gviz + dvz;
+    }
+    // fixed-order block reduction of the position gradient over the 128 features
+    gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
+    __syncthreads();
+    if (lane == 0) { red[wid][0] = gx; red[wid][1] = gy; red[wid][2] = gz; }
+    __syncthreads();
+    if (f < 3) grad[3 * i + f] += (red[0][f] + red[1][f]) + (red[2][f] + red[3][f]);
+  }
+}
+
+struct Workspace {
+  // edge records
+  float4* eg; float* re; float* dre; float* evex; float* grad0;
+  // activations
+  float* s[NCONV + 1];      // [M,A,128]
+  float* v[NCONV + 1];      // [M,A,3,128]  (v[0] unused: zeros)
+  float* h1[NCONV]; float* phi[NCONV]; float* cat[NCONV]; float* vmid[NCONV]; float* UV[NCONV];
+  float* h3[NCONV]; float* a[NCONV];
+  float* h5; float* e_atom;
+  // gradients
+  float* ds; float* dvA; float* dvB; float* dphi; float* dh1; float* da; float* dh3; float* dcat; float* dUV;
+  size_t bytes;
+};
+
+Workspace carve(void* base, int M, int A, long long e_cap) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) -> float* {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += ((nfloats * sizeof(float) + 255) / 256) * 256;
+    return p;
+  };
+  const size_t MA = (size_t)M * (size_t)A;
+  w.eg = reinterpret_cast<float4*>(take((size_t)e_cap * 4));
+  w.re = take((size_t)e_cap * 24);
+  w.dre = take((size_t)e_cap * 20);
+  w.evex = take(A);
+  w.grad0 = take((size_t)A * 3);
+  for (int l = 0; l <= NCONV; ++l) w.s[l] = take(MA * F);
+  w.v[0] = nullptr;
+  for (int l = 1; l <= NCONV; ++l) w.v[l] = take(MA * 3 * F);
+  for (int l = 0; l < NCONV; ++l) {
+    w.h1[l] = take(MA * F); w.phi[l] = take(MA * F3); w.cat[l] = take(MA * 2 * F); w.vmid[l] = take(MA * 3 * F);
+    w.UV[l] = take(MA * 6 * F); w.h3[l] = take(MA * F); w.a[l] = take(MA * F3);
+  }
+  w.h5 = take(MA * FH); w.e_atom = take(MA);
+  w.ds = take(MA * F); w.dvA = take(MA * 3 * F); w.dvB = take(MA * 3 * F); w.dphi = take(MA * F3);
+  w.dh1 = take(MA * F); w.da = take(MA * F3); w.dh3 = take(MA * F); w.dcat = take(MA * 2 * F);
+  w.dUV = take(MA * 6 * F);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" int64_t vssr_painn_weight_floats(void) { return (int64_t)painn::W_TOTAL; }
+
+extern "C" size_t vssr_painn_workspace_bytes(int32_t n_models, int32_t n_atoms, int64_t e_cap) {
+  return carve(nullptr, n_models, n_atoms, e_cap).bytes;
+}
+
+extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, const float* pos, const int32_t* z,
+                                      const int32_t* atom_ptr, const float* cell, int32_t n_struct, int32_t n_atoms,
+                                      const int32_t* rowptr, const int32_t* col, const int8_t* shift, int64_t e_cap,
+                                      float cutoff, void* workspace, size_t workspace_bytes, double* energy,
+                                      float* grad, float* embedding, void* stream) {
+  if (!weights || !pos || !z || !atom_ptr || !cell || !rowptr || !col || !shift || !workspace || !energy || !grad)
+    return VSSR_ERR_ARG;
+  if (n_models <= 0 || n_struct <= 0 || n_atoms <= 0) return VSSR_ERR_ARG;
+  Workspace w = carve(workspace, n_models, n_atoms, e_cap);
+  if (w.bytes > workspace_bytes) return VSSR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = n_models, A = n_atoms;
+  const long long MA_F = (long long)A * F;  // per-model stride of [A,128]
+  const dim3 ew_grid(ceil_div((long long)A * F, 256), M);
+  const dim3 msg_grid(ceil_div(A, MSG_APB), M);
+
+  edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(pos, atom_ptr, cell, n_struct, A, rowptr, col, shift,
+                                                       (long long)e_cap, cutoff, w.eg, w.re, w.dre, w.evex, w.grad0);
+  VSSR_LAUNCH_CHECK();
+  embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]);
+  VSSR_LAUNCH_CHECK();
+
+  int rc;
+  for (int l = 0; l < NCONV; ++l) {
+    const float* wl = weights + W_LAYER0 + (long long)l * L_SIZE;
+    GemmArgs g{};
+    // F1
+    g = GemmArgs{w.s[l], F, MA_F, wl + L_W1T, F, W_TOTAL, wl + L_B1, W_TOTAL, nullptr, 0, 0, nullptr, 0,
+                 w.h1[l], F, MA_F, A, F, F};
+    if ((rc = launch_gemm<128, 0, 1>(g, M, st))) return rc;
+    // F2
+    g = GemmArgs{w.h1[l], F, MA_F, wl + L_W2T, F3, W_TOTAL, wl + L_B2, W_TOTAL, nullptr, 0, 0, nullptr, 0,
+                 w.phi[l], F3, (long long)A * F3, A, F3, F};
+    if ((rc = launch_gemm<128, 1, 1>(g, M, st))) return rc;
+    // F3
+    if (l == 0)
+      message_fwd_kernel<true><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
+                                                         w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]);
+    else
+      message_fwd_kernel<false><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
+                                                          w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]);
+    VSSR_LAUNCH_CHECK();
+    // F4
+    g = GemmArgs{w.vmid[l], F, (long long)A * 3 * F, wl + L_UVT, 2 * F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+                 w.UV[l], 2 * F, (long long)A * 6 * F, 3 * A, 2 * F, F};
+    if ((rc = launch_gemm<128, 0, 0>(g, M, st))) return rc;
+    // F5
+    nrm_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], A, w.cat[l]);
+    VSSR_LAUNCH_CHECK();
+    // F6
+    g = GemmArgs{w.cat[l], 2 * F, (long long)A * 2 * F, wl + L_W3T, F, W_TOTAL, wl + L_B3, W_TOTAL, nullptr, 0, 0,
+                 nullptr, 0, w.h3[l], F, MA_F, A, F, 2 * F};
+    if ((rc = launch_gemm<128, 0, 1>(g, M, st))) return rc;
+    // F7
+    g = GemmArgs{w.h3[l], F, MA_F, wl + L_W4T, F3, W_TOTAL, wl + L_B4, W_TOTAL, nullptr, 0, 0, nullptr, 0,
+                 w.a[l], F3, (long long)A * F3, A, F3, F};
+    if ((rc = launch_gemm<128, 1, 1>(g, M, st))) return rc;
+    // F8
+    update_fwd_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], w.a[l], w.cat[l], w.vmid[l], A, w.s[l + 1], w.v[l + 1]);
+    VSSR_LAUNCH_CHECK();
+  }
+  // readout
+  {
+    GemmArgs g{w.s[NCONV], F, MA_F, weights + R_W5T, FH, W_TOTAL, weights + R_B5, W_TOTAL, nullptr, 0, 0, nullptr, 0,
+               w.h5, FH, (long long)A * FH, A, FH, F};
+    if ((rc = launch_gemm<64, 0, 1>(g, M, st))) return rc;
+    readout_energy_kernel<<<dim3(ceil_div(A, 4), M), 128, 0, st>>>(weights, w.h5, w.evex, A, w.e_atom);
+    VSSR_LAUNCH_CHECK();
+    energy_reduce_kernel<<<dim3(ceil_div(n_struct, 4), M), 128, 0, st>>>(w.e_atom, atom_ptr, n_struct, A, energy);
+    VSSR_LAUNCH_CHECK();
+  }
+  if (embedding) {
+    VSSR_CUDA(cudaMemcpyAsync(embedding, w.s[NCONV], (size_t)M * A * F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+
+  // ---------------- backward ----------------
+  grad_init_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.grad0, 3 * A, grad);
+  VSSR_LAUNCH_CHECK();
+  {
+    // ds = (dswish(h5) * w6) . W5      [A,64]x[64,128]
+    GemmArgs g{w.h5, FH, (long long)A * FH, weights + R_W5, F, W_TOTAL, nullptr, 0, nullptr, 0, 0, weights + R_W6,
+               W_TOTAL, w.ds, F, MA_F, A, F, FH};
+    if ((rc = launch_gemm<128, 2, 0>(g, M, st))) return rc;
+  }
+  VSSR_CUDA(cudaMemsetAsync(w.dvA, 0, (size_t)M * A * 3 * F * sizeof(float), st));
+  float* dv_cur = w.dvA;
+  float* dv_nxt = w.dvB;
+  for (int l = NCONV - 1; l >= 0; --l) {
+    const float* wl = weights + W_LAYER0 + (long long)l * L_SIZE;
+    GemmArgs g{};
+    // B8
+    update_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.ds, dv_cur, w.UV[l], w.a[l], A, w.da, w.dUV);
+    VSSR_LAUNCH_CHECK();
+    // B7: dh3 = (da . W4) * dswish(h3)
+    g = GemmArgs{w.da, F3, (long long)A * F3, wl + L_W4, F, W_TOTAL, nullptr, 0, w.h3[l], F, MA_F, nullptr, 0,
+                 w.dh3, F, MA_F, A, F, F3};
+    if ((rc = launch_gemm<128, 0, 2>(g, M, st))) return rc;
+    // B6: dcat = dh3 . W3
+    g = GemmArgs{w.dh3, F, MA_F, wl + L_W3, 2 * F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+                 w.dcat, 2 * F, (long long)A * 2 * F, A, 2 * F, F};
+    if ((rc = launch_gemm<128, 0, 0>(g, M, st))) return rc;
+    // B5
+    nrm_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.dcat, w.cat[l], w.UV[l], A, w.ds, w.dUV);
+    VSSR_LAUNCH_CHECK();
+    // B4: dv += dUV . [U;V]      [3A,256]x[256,128]
+    g = GemmArgs{w.dUV, 2 * F, (long long)A * 6 * F, wl + L_UV, F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+                 dv_cur, F, (long long)A * 3 * F, 3 * A, F, 2 * F};
+    if ((rc = launch_gemm<128, 0, 3>(g, M, st))) return rc;
+    // B3
+    if (l == 0) {
+      message_bwd_kernel<true><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
+                                                         w.dre, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, grad);
+      VSSR_LAUNCH_CHECK();
+    } else {
+      message_bwd_kernel<false><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
+                                                          w.dre, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, grad);
+      VSSR_LAUNCH_CHECK();
+      // B2: dh1 = (dphi . W2) * dswish(h1)
+      g = GemmArgs{w.dphi, F3, (long long)A * F3, wl + L_W2, F, W_TOTAL, nullptr, 0, w.h1[l], F, MA_F, nullptr, 0,
+                   w.dh1, F, MA_F, A, F, F3};
+      if ((rc = launch_gemm<128, 0, 2>(g, M, st))) return rc;
+      // B1: ds += dh1 . W1
+      g = GemmArgs{w.dh1, F, MA_F, wl + L_W1, F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+                   w.ds, F, MA_F, A, F, F};
+      if ((rc = launch_gemm<128, 0, 3>(g, M, st))) return rc;
+      float* t = dv_cur; dv_cur = dv_nxt; dv_nxt = t;
+    }
+  }
+  return VSSR_OK;
+}

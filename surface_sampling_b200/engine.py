@@ -1,0 +1,368 @@
+"""Batch engines over libvssr_b200.so: many independent chains' slabs resident in HBM.
+
+PyTorch is plumbing only here (device memory, streams); all arithmetic runs in the hand-written
+CUDA kernels behind the C ABI (include/vssr_b200.h).  A *batch* is the ragged concatenation of
+the chains' structures ("ragged flat" layout, see the header).
+
+Reference mapping:
+  PainnEngine.energy_forces  ~ EnsembleNFF.calculate           (mcmc/calculators/calculators.py:484)
+  PainnEngine.relax          ~ optimize_slab(optimizer="FIRE") (mcmc/dynamics.py:83-170)
+  ClassicalEngine.*          ~ LAMMMPSCalc.run_lammps_energy/_opt (mcmc/calculators/calculators.py:600-640)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+KCAL_PER_EV = 23.06052
+HARTREE_TO_KCAL_MOL = 627.509
+HARTREE_TO_EV = HARTREE_TO_KCAL_MOL / KCAL_PER_EV
+
+SYMBOLS = {1: "H", 7: "N", 8: "O", 14: "Si", 22: "Ti", 25: "Mn", 29: "Cu", 31: "Ga", 38: "Sr", 57: "La", 79: "Au"}
+NUMBERS = {v: k for k, v in SYMBOLS.items()}
+
+F, F3, NRBF, NCONV, NEMB, FH = 128, 384, 20, 3, 100, 64
+
+# (name, shape) in packing order — mirror of csrc/painn_layout.h
+_LAYER_LAYOUT = [("W1T", (F, F)), ("B1", (F,)), ("W2T", (F, F3)), ("B2", (F3,)), ("WDT", (NRBF, F3)), ("BD", (F3,)),
+                 ("UVT", (F, 2 * F)), ("W3T", (2 * F, F)), ("B3", (F,)), ("W4T", (F, F3)), ("B4", (F3,)),
+                 ("W1", (F, F)), ("W2", (F3, F)), ("UV", (2 * F, F)), ("W3", (F, 2 * F)), ("W4", (F3, F))]
+_READ_LAYOUT = [("W5T", (F, FH)), ("B5", (FH,)), ("W6", (FH,)), ("B6", (4,)), ("W5", (FH, F))]
+
+
+def painn_weight_floats() -> int:
+    n = NEMB * F
+    n += NCONV * sum(int(np.prod(s)) for _, s in _LAYER_LAYOUT)
+    n += sum(int(np.prod(s)) for _, s in _READ_LAYOUT)
+    return n
+
+
+def pack_painn_weights(state: dict) -> np.ndarray:
+    """Pack one NFF-PaiNN state dict (keys as in the checkpoints) into the
+    flat fp32 layout of csrc/painn_layout.h."""
+    g = lambda k: np.asarray(state[k], dtype=np.float32)
+    parts = [g("embed_block.atom_embed.weight").reshape(NEMB, F)]
+    for l in range(NCONV):
+        p = f"message_blocks.{l}.inv_message."
+        u = f"update_blocks.{l}."
+        W1, b1 = g(p + "inv_dense.layers.0.weight"), g(p + "inv_dense.layers.0.bias")
+        W2, b2 = g(p + "inv_dense.layers.1.weight"), g(p + "inv_dense.layers.1.bias")
+        Wd, bd = g(p + "dist_embed.block.1.weight"), g(p + "dist_embed.block.1.bias")
+        U, V = g(u + "u_mat.weight"), g(u + "v_mat.weight")
+        W3, b3 = g(u + "s_dense.0.weight"), g(u + "s_dense.0.bias")
+        W4, b4 = g(u + "s_dense.1.weight"), g(u + "s_dense.1.bias")
+        t = {
+            "W1T": W1.T, "B1": b1, "W2T": W2.T, "B2": b2, "WDT": Wd.T, "BD": bd,
+            "UVT": np.concatenate([U.T, V.T], axis=1), "W3T": W3.T, "B3": b3, "W4T": W4.T, "B4": b4,
+            "W1": W1, "W2": W2, "UV": np.concatenate([U, V], axis=0), "W3": W3, "W4": W4,
+        }
+        for name, shape in _LAYER_LAYOUT:
+            a = np.ascontiguousarray(t[name], dtype=np.float32)
+            assert a.shape == shape, (name, a.shape, shape)
+            parts.append(a)
+    r = "readout_blocks.0.readoutdict.energy."
+    W5, b5, W6, b6 = g(r + "0.weight"), g(r + "0.bias"), g(r + "1.weight"), g(r + "1.bias")
+    t = {"W5T": W5.T, "B5": b5, "W6": W6.reshape(FH), "B6": np.array([b6.reshape(-1)[0], 0, 0, 0], np.float32),
+         "W5": W5}
+    for name, shape in _READ_LAYOUT:
+        a = np.ascontiguousarray(t[name], dtype=np.float32)
+        assert a.shape == shape, (name, a.shape, shape)
+        parts.append(a)
+    flat = np.concatenate([x.reshape(-1) for x in parts]).astype(np.float32)
+    assert flat.size == painn_weight_floats()
+    return flat
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.VssrError("a CUDA device is required: the engine has no CPU fallback")
+
+
+@dataclass
+class Batch:
+    """Ragged batch of structures resident on the device."""
+    pos: torch.Tensor        # [A,3] float64
+    z: torch.Tensor          # [A] int32 (atomic numbers, or type indices for classical potentials)
+    fixed: torch.Tensor      # [A] uint8
+    atom_ptr: torch.Tensor   # [B+1] int32
+    cell: torch.Tensor       # [B,3,3] float64
+    pbc: torch.Tensor        # [B,3] uint8
+    n_struct: int
+    n_atoms: int
+    atom_ptr_host: np.ndarray
+
+    @property
+    def cell32(self):
+        return self.cell.to(torch.float32)
+
+    @staticmethod
+    def from_arrays(pos_list, z_list, cell_list, pbc_list, fixed_list=None, device="cuda", pinned=True):
+        """Host arrays (one entry per chain) -> one pinned staging buffer each -> device."""
+        n = [len(p) for p in pos_list]
+        B = len(n)
+        ptr = np.zeros(B + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum(n)
+        A = int(ptr[-1])
+        pos = np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in pos_list]) if A else np.zeros((0, 3))
+        z = np.concatenate([np.asarray(q, dtype=np.int32).reshape(-1) for q in z_list]) if A else np.zeros(0, np.int32)
+        if fixed_list is None:
+            fixed = np.zeros(A, dtype=np.uint8)
+        else:
+            fixed = np.concatenate([np.asarray(q).astype(np.uint8).reshape(-1) for q in fixed_list])
+        cell = np.stack([np.asarray(c, dtype=np.float64).reshape(3, 3) for c in cell_list])
+        pbc = np.stack([np.asarray(p).astype(np.uint8).reshape(3) for p in pbc_list])
+        return Batch.from_flat(pos, z, fixed, ptr, cell, pbc, device=device, pinned=pinned)
+
+    @staticmethod
+    def from_flat(pos, z, fixed, ptr, cell, pbc, device="cuda", pinned=True):
+        def up(a, dt):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if pinned and torch.cuda.is_available():
+                t = t.pin_memory()
+            return t.to(device=device, dtype=dt, non_blocking=True)
+        ptr = np.asarray(ptr, dtype=np.int32)
+        return Batch(pos=up(pos, torch.float64), z=up(z, torch.int32), fixed=up(fixed, torch.uint8),
+                     atom_ptr=up(ptr, torch.int32), cell=up(cell, torch.float64), pbc=up(pbc, torch.uint8),
+                     n_struct=len(ptr) - 1, n_atoms=int(ptr[-1]), atom_ptr_host=ptr.copy())
+
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.pos, self.z, self.fixed, self.atom_ptr, self.cell, self.pbc))
+
+    def split_host(self, flat: np.ndarray):
+        p = self.atom_ptr_host
+        return [flat[p[b]:p[b + 1]] for b in range(self.n_struct)]
+
+
+class _Workspace:
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
+            self.buf = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=device)
+        return self.buf
+
+
+def neighbor_list(batch: Batch, cutoff: float, e_cap: int | None = None):
+    """Directed periodic neighbour list (vssr_nbr_build). Returns (rowptr[A+1], col[E], shift[E,4]) on
+    the device, exactly sized (re-runs once if the first capacity guess was too small)."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = batch.pos.device
+    A, B = batch.n_atoms, batch.n_struct
+    pos32 = batch.pos.to(torch.float32)
+    cell32 = batch.cell32.contiguous()
+    cap = int(e_cap) if e_cap else max(A * 96, 1024)
+    while True:
+        deg = torch.empty(max(A, 1), dtype=torch.int32, device=dev)
+        rowptr = torch.empty(A + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(cap, dtype=torch.int32, device=dev)
+        shift = torch.empty((cap, 4), dtype=torch.int8, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.vssr_nbr_build(_ptr(pos32), _ptr(batch.atom_ptr), _ptr(cell32), _ptr(batch.pbc), B, A,
+                                      float(cutoff), _ptr(deg), _ptr(rowptr), _ptr(col), _ptr(shift), cap,
+                                      _ptr(status), _stream()), "vssr_nbr_build")
+        n_edges = int(rowptr[-1].item())
+        if n_edges <= cap:
+            return rowptr, col[:n_edges], shift[:n_edges]
+        cap = n_edges
+
+
+class PainnEngine:
+    """3-model (or M-model) PaiNN ensemble on the GPU."""
+
+    def __init__(self, states: list[dict], offset_data: dict | None = None, cutoff: float = 5.0, skin: float = 1.0,
+                 device: str = "cuda", edges_per_atom: int = 96):
+        _require_cuda()
+        self.lib = _lib.load()
+        assert int(self.lib.vssr_painn_weight_floats()) == painn_weight_floats(), "weight layout mismatch"
+        self.device = torch.device(device)
+        self.n_models = len(states)
+        w = np.stack([pack_painn_weights(s) for s in states])
+        self.weights = torch.from_numpy(w).to(self.device)
+        self.offset_data = offset_data
+        self.cutoff, self.skin = float(cutoff), float(skin)
+        self.edges_per_atom = edges_per_atom
+        self._ws = _Workspace()
+        self._ws_relax = _Workspace()
+
+    # -- H5 stoichiometric offset (per structure, host, exact fp64) ---------------------------
+    def offsets_ev(self, z_host: np.ndarray, atom_ptr: np.ndarray) -> np.ndarray | None:
+        if self.offset_data is None:
+            return None
+        sto = self.offset_data["stoidict"]
+        per_z = np.zeros(120)
+        for zz, sym in SYMBOLS.items():
+            if sym in sto:
+                per_z[zz] = sto[sym]
+        csum = np.concatenate([[0.0], np.cumsum(per_z[np.asarray(z_host)])])
+        tot = csum[atom_ptr[1:]] - csum[atom_ptr[:-1]] + sto["offset"]
+        return tot * HARTREE_TO_KCAL_MOL / KCAL_PER_EV
+
+    def energy_forces(self, batch: Batch, z_host: np.ndarray | None = None, want_embedding=False, nbrs=None):
+        """One ensemble evaluation of every structure in the batch."""
+        lib, dev = self.lib, self.device
+        A, B, M = batch.n_atoms, batch.n_struct, self.n_models
+        if nbrs is None:
+            nbrs = neighbor_list(batch, self.cutoff + self.skin)
+        rowptr, col, shift = nbrs
+        e_cap = max(int(col.numel()), 1)
+        if col.numel() == 0:
+            col = torch.zeros(1, dtype=torch.int32, device=dev)
+            shift = torch.zeros((1, 4), dtype=torch.int8, device=dev)
+        pos32 = batch.pos.to(torch.float32)
+        cell32 = batch.cell32.contiguous()
+        nbytes = int(lib.vssr_painn_workspace_bytes(M, A, e_cap))
+        ws = self._ws.get(nbytes, dev)
+        energy = torch.empty((M, B), dtype=torch.float64, device=dev)
+        grad = torch.empty((M, A, 3), dtype=torch.float32, device=dev)
+        emb = torch.empty((M, A, F), dtype=torch.float32, device=dev) if want_embedding else None
+        _lib.check(lib.vssr_painn_energy_grad(_ptr(self.weights), M, _ptr(pos32), _ptr(batch.z), _ptr(batch.atom_ptr),
+                                              _ptr(cell32), B, A, _ptr(rowptr), _ptr(col), _ptr(shift), e_cap,
+                                              self.cutoff, _ptr(ws), ws.numel(), _ptr(energy), _ptr(grad), _ptr(emb),
+                                              _stream()), "vssr_painn_energy_grad")
+        off = None
+        if self.offset_data is not None:
+            zh = z_host if z_host is not None else batch.z.cpu().numpy()
+            off = torch.from_numpy(self.offsets_ev(zh, batch.atom_ptr_host)).to(dev)
+        e_mean = torch.empty(B, dtype=torch.float64, device=dev)
+        e_std = torch.empty(B, dtype=torch.float64, device=dev)
+        f_mean = torch.empty((A, 3), dtype=torch.float32, device=dev)
+        f_std = torch.empty((A, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.vssr_ensemble_stats(_ptr(energy), _ptr(grad), _ptr(off), _ptr(batch.atom_ptr), M, B, A,
+                                           _ptr(e_mean), _ptr(e_std), _ptr(f_mean), _ptr(f_std), _stream()),
+                   "vssr_ensemble_stats")
+        return {"energy": e_mean, "energy_std": e_std, "forces": f_mean, "forces_std": f_std,
+                "energy_kcal_per_model": energy, "grad_kcal_per_model": grad, "embedding": emb}
+
+    def relax(self, batch: Batch, relax_steps: int = 20, fmax: float = 0.01, z_host: np.ndarray | None = None,
+              want_std: bool = True, e_cap: int | None = None):
+        """optimize_slab(optimizer='FIRE') for every structure, no host round trip.  batch.pos is
+        updated in place.  Returns dict(out[B,8], forces, forces_std, status)."""
+        lib, dev = self.lib, self.device
+        A, B, M = batch.n_atoms, batch.n_struct, self.n_models
+        cap = int(e_cap) if e_cap else A * self.edges_per_atom
+        nbytes = int(lib.vssr_painn_relax_workspace_bytes(M, A, cap))
+        ws = self._ws_relax.get(nbytes, dev)
+        off = None
+        if self.offset_data is not None:
+            zh = z_host if z_host is not None else batch.z.cpu().numpy()
+            off = torch.from_numpy(self.offsets_ev(zh, batch.atom_ptr_host)).to(dev, non_blocking=True)
+        out = torch.empty((B, 8), dtype=torch.float64, device=dev)
+        forces = torch.empty((A, 3), dtype=torch.float32, device=dev)
+        fstd = torch.empty((A, 3), dtype=torch.float32, device=dev) if want_std else None
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        cell32 = batch.cell32.contiguous()
+        _lib.check(lib.vssr_painn_relax(_ptr(self.weights), M, _ptr(batch.pos), _ptr(batch.z), _ptr(batch.fixed),
+                                        _ptr(batch.atom_ptr), _ptr(cell32), _ptr(batch.pbc), _ptr(off), B, A,
+                                        self.cutoff, self.skin, int(relax_steps), float(fmax), cap, _ptr(ws),
+                                        ws.numel(), _ptr(out), _ptr(forces), _ptr(fstd), _ptr(status), _stream()),
+                   "vssr_painn_relax")
+        return {"out": out, "forces": forces, "forces_std": fstd, "status": status}
+
+
+RELAX_COLS = ("energy", "energy_std", "raw_energy", "max_abs_force", "nsteps", "converged", "energy_oob", "n_evals")
+
+POT_TERSOFF, POT_SW = 0, 1
+
+
+def tersoff_param_table(pot_json: dict, elements: list[str]) -> np.ndarray:
+    """[ntypes^3,14] table (LAMMPS elem3param order) from the parsed GaN.tersoff fixture."""
+    ne = len(elements)
+    tab = np.zeros((ne, ne, ne, 14))
+    seen = np.zeros((ne, ne, ne), bool)
+    for e in pot_json["entries"]:
+        if all(x in elements for x in e["elements"]):
+            a, b, c = (elements.index(x) for x in e["elements"])
+            tab[a, b, c] = e["params"]
+            seen[a, b, c] = True
+    if not seen.all():
+        raise ValueError("missing Tersoff entries for " + str(elements))
+    return tab.reshape(-1, 14)
+
+
+def sw_param_table(eps=2.1683, sigma=2.0951, a=1.80, lam=21.0, gamma=1.20, costheta0=-1.0 / 3.0, A=7.049556277,
+                   B=0.6022245584, p=4.0, q=0.0) -> np.ndarray:
+    """Single-element SW table [1,10] (LAMMPS `pair_style sw` order); SW-1985 Si by default."""
+    return np.array([[eps, sigma, a, lam, gamma, costheta0, A, B, p, q]], dtype=np.float64)
+
+
+class ClassicalEngine:
+    """Tersoff / Stillinger-Weber energy, forces and FIRE relaxation, one CTA per chain."""
+
+    def __init__(self, kind: int, params: np.ndarray, ntypes: int, n_max: int = 128, max_nbr: int = 32,
+                 skin: float = 0.5, device: str = "cuda"):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.kind, self.ntypes, self.n_max, self.max_nbr, self.skin = kind, ntypes, n_max, max_nbr, skin
+        self.device = torch.device(device)
+        self.params = torch.from_numpy(np.ascontiguousarray(params, dtype=np.float64)).to(self.device)
+        smem = int(self.lib.vssr_classical_smem_bytes(n_max, max_nbr))
+        if smem > 227 * 1024:
+            raise ValueError(f"n_max={n_max}, max_nbr={max_nbr} needs {smem} B shared memory (> 227 KB)")
+
+    def _check_status(self, status):
+        s = int(status.item())
+        if s & 2:
+            raise _lib.VssrError("classical kernel: neighbour slots overflowed (raise max_nbr)")
+        if s & 4:
+            raise _lib.VssrError("classical kernel: structure larger than n_max")
+
+    def energy_forces(self, batch: Batch, check=True):
+        dev = self.device
+        A, B = batch.n_atoms, batch.n_struct
+        energy = torch.empty(B, dtype=torch.float64, device=dev)
+        forces = torch.empty((A, 3), dtype=torch.float64, device=dev)
+        eat = torch.empty(A, dtype=torch.float64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.vssr_classical_energy_forces(self.kind, _ptr(self.params), self.ntypes, _ptr(batch.pos),
+                                                         _ptr(batch.z), _ptr(batch.atom_ptr), _ptr(batch.cell),
+                                                         _ptr(batch.pbc), B, self.n_max, self.max_nbr, _ptr(energy),
+                                                         _ptr(forces), _ptr(eat), _ptr(status), _stream()),
+                   "vssr_classical_energy_forces")
+        if check:
+            self._check_status(status)
+        return {"energy": energy, "forces": forces, "per_atom_energies": eat, "status": status}
+
+    def relax(self, batch: Batch, relax_steps: int = 100, fmax: float = 0.01, check=True):
+        dev = self.device
+        A, B = batch.n_atoms, batch.n_struct
+        out = torch.empty((B, 8), dtype=torch.float64, device=dev)
+        forces = torch.empty((A, 3), dtype=torch.float64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.vssr_classical_relax(self.kind, _ptr(self.params), self.ntypes, _ptr(batch.pos),
+                                                 _ptr(batch.z), _ptr(batch.fixed), _ptr(batch.atom_ptr),
+                                                 _ptr(batch.cell), _ptr(batch.pbc), B, self.n_max, self.max_nbr,
+                                                 int(relax_steps), float(fmax), float(self.skin), _ptr(out),
+                                                 _ptr(forces), _ptr(status), _stream()), "vssr_classical_relax")
+        if check:
+            self._check_status(status)
+        return {"out": out, "forces": forces, "status": status}
+
+
+def system_reduce(per_atom: torch.Tensor, batch: Batch) -> torch.Tensor:
+    """get_system_val (mcmc/uncertainty/prediction.py:181-223): [B,6] = sum,max,min,mean,mean_sq,rms."""
+    lib = _lib.load()
+    out = torch.empty((batch.n_struct, 6), dtype=torch.float32, device=per_atom.device)
+    _lib.check(lib.vssr_system_reduce(_ptr(per_atom.contiguous()), _ptr(batch.atom_ptr), batch.n_struct, _ptr(out),
+                                      _stream()), "vssr_system_reduce")
+    return out
+
+
+def atom_norm(vec: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(vec.shape[0], dtype=torch.float32, device=vec.device)
+    _lib.check(lib.vssr_atom_norm(_ptr(vec.contiguous()), vec.shape[0], _ptr(out), _stream()), "vssr_atom_norm")
+    return out

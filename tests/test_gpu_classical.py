@@ -1,0 +1,125 @@
+"""Tersoff / Stillinger-Weber CUDA kernels (fp64) vs the CPU oracle and the GaN golden value."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import perturbed, with_adsorbates
+from oracle import classical as ocl
+from oracle import relax as orelax
+
+pytestmark = pytest.mark.gpu
+
+
+def _types(numbers, table):
+    return np.array([table[int(z)] for z in numbers], dtype=np.int32)
+
+
+def _batch(structs, types, fixed=None):
+    from surface_sampling_b200 import engine
+    return engine.Batch.from_arrays([s["positions"] for s in structs], types, [s["cell"] for s in structs],
+                                    [s["pbc"] for s in structs], fixed)
+
+
+def test_tersoff_energy_forces(structures, potentials, golden_values):
+    from surface_sampling_b200 import engine
+    tab = engine.tersoff_param_table(potentials["GaN.tersoff"], ["Ga", "N"])
+    eng = engine.ClassicalEngine(engine.POT_TERSOFF, tab, 2, n_max=64, max_nbr=24)
+    prm = ocl.TersoffParams(potentials["GaN.tersoff"], ["Ga", "N"])
+    rng = np.random.default_rng(1)
+    base = structures["GaN_0001_3x3"]
+    structs = [base, perturbed(base, rng, 0.08), with_adsorbates(perturbed(base, rng, 0.05), rng, 12, [31], 1.8)]
+    types = [_types(s["numbers"], {31: 0, 7: 1}) for s in structs]
+    b = _batch(structs, types)
+    r = eng.energy_forces(b)
+    e = r["energy"].cpu().numpy()
+    f = b.split_host(r["forces"].cpu().numpy())
+    assert abs(e[0] - golden_values["tersoff_gan_pristine"]["energy"]) < 1e-3
+    for k, s in enumerate(structs):
+        e0, f0 = ocl.energy_forces(ocl.tersoff_energy, s["positions"], torch.tensor(types[k]).long(), s["cell"],
+                                   s["pbc"], prm)
+        assert abs(e[k] - e0) < 1e-9 * max(1.0, abs(e0)), (k, e[k], e0)
+        assert np.abs(f[k] - f0).max() < 1e-8, (k, np.abs(f[k] - f0).max())
+    eat = b.split_host(r["per_atom_energies"].cpu().numpy())
+    assert abs(eat[0].sum() - e[0]) < 1e-10
+
+
+def test_sw_energy_forces(structures):
+    from surface_sampling_b200 import engine
+    eng = engine.ClassicalEngine(engine.POT_SW, engine.sw_param_table(), 1, n_max=128, max_nbr=32)
+    rng = np.random.default_rng(4)
+    base = structures["Si_111_5x5"]
+    structs = [base, perturbed(base, rng, 0.1), with_adsorbates(base, rng, 5, [14], 2.0)]
+    types = [np.zeros(len(s["numbers"]), np.int32) for s in structs]
+    b = _batch(structs, types)
+    r = eng.energy_forces(b)
+    e = r["energy"].cpu().numpy()
+    f = b.split_host(r["forces"].cpu().numpy())
+    for k, s in enumerate(structs):
+        e0, f0 = ocl.energy_forces(ocl.sw_energy, s["positions"], s["cell"], s["pbc"], ocl.SWParams())
+        assert abs(e[k] - e0) < 1e-9 * abs(e0), (k, e[k], e0)
+        assert np.abs(f[k] - f0).max() < 1e-8
+
+
+@pytest.mark.parametrize("kind", ["tersoff", "sw"])
+def test_relax_vs_oracle_fire(structures, potentials, kind):
+    from surface_sampling_b200 import engine
+    rng = np.random.default_rng(9)
+    if kind == "tersoff":
+        tab = engine.tersoff_param_table(potentials["GaN.tersoff"], ["Ga", "N"])
+        eng = engine.ClassicalEngine(engine.POT_TERSOFF, tab, 2, n_max=64, max_nbr=24)
+        prm = ocl.TersoffParams(potentials["GaN.tersoff"], ["Ga", "N"])
+        base = structures["GaN_0001_3x3"]
+        structs = [with_adsorbates(base, rng, 6, [31], 1.8), with_adsorbates(base, rng, 12, [31], 1.8)]
+        types = [_types(s["numbers"], {31: 0, 7: 1}) for s in structs]
+        fixed = [np.arange(len(s["numbers"])) < 36 for s in structs]   # bulk_index 36 (GaN_0001_lammps_config.json)
+        steps = 100
+
+        def efn(k):
+            return lambda x: ocl.energy_forces(ocl.tersoff_energy, x, torch.tensor(types[k]).long(),
+                                               structs[k]["cell"], structs[k]["pbc"], prm)
+    else:
+        eng = engine.ClassicalEngine(engine.POT_SW, engine.sw_param_table(), 1, n_max=128, max_nbr=32)
+        base = structures["Si_111_5x5"]
+        structs = [perturbed(base, rng, 0.05), with_adsorbates(base, rng, 4, [14], 2.0)]
+        types = [np.zeros(len(s["numbers"]), np.int32) for s in structs]
+        fixed = [np.arange(len(s["numbers"])) < 75 for s in structs]   # bulk_index 75 (Si_111_5x5_lammps_config.json)
+        steps = 40
+
+        def efn(k):
+            return lambda x: ocl.energy_forces(ocl.sw_energy, x, structs[k]["cell"], structs[k]["pbc"], ocl.SWParams())
+    b = _batch(structs, types, fixed)
+    res = eng.relax(b, relax_steps=steps, fmax=0.01)
+    out = res["out"].cpu().numpy()
+    pos = b.split_host(b.pos.cpu().numpy())
+    for k, s in enumerate(structs):
+        o = orelax.relax(efn(k), s["positions"], fixed[k], optimizer="FIRE", relax_steps=steps, fmax=0.01)
+        assert int(out[k, 4]) == o["nsteps"] and bool(out[k, 5]) == o["converged"], (out[k], o["nsteps"])
+        assert abs(out[k, 2] - o["raw_energy"]) < 1e-7 * abs(o["raw_energy"]), (out[k, 2], o["raw_energy"])
+        assert np.abs(pos[k] - o["pos"]).max() < 1e-6
+        assert np.array_equal(pos[k][fixed[k]], s["positions"][fixed[k]])
+
+
+def test_host_buffer_entry_matches_device_entry(structures, potentials):
+    """vssr_classical_relax_host: the FFI-facing call with host pointers."""
+    import ctypes as C
+    from surface_sampling_b200 import _lib, engine
+    lib = _lib.load()
+    tab = np.ascontiguousarray(engine.tersoff_param_table(potentials["GaN.tersoff"], ["Ga", "N"]))
+    rng = np.random.default_rng(3)
+    s = with_adsorbates(structures["GaN_0001_3x3"], rng, 12, [31], 1.8)
+    types = _types(s["numbers"], {31: 0, 7: 1})
+    fixed = (np.arange(len(types)) < 36).astype(np.uint8)
+    eng = engine.ClassicalEngine(engine.POT_TERSOFF, tab, 2, n_max=64, max_nbr=24)
+    b = _batch([s], [types], [fixed])
+    ref = eng.relax(b, relax_steps=30)["out"].cpu().numpy()
+    pos = np.ascontiguousarray(s["positions"], dtype=np.float64).copy()
+    ptr = np.array([0, len(types)], np.int32)
+    cell = np.ascontiguousarray(s["cell"], dtype=np.float64)
+    pbc = np.ascontiguousarray(s["pbc"]).astype(np.uint8)
+    out = np.zeros((1, 8)); forces = np.zeros_like(pos); status = np.zeros(1, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.vssr_classical_relax_host(0, p(tab), 2, p(pos), p(types), p(fixed), p(ptr), p(cell), p(pbc), 1,
+                                       len(types), 64, 24, 30, 0.01, 0.5, p(out), p(forces), p(status))
+    assert rc == 0 and status[0] == 0
+    assert np.array_equal(out, ref)
+    assert np.array_equal(pos, b.pos.cpu().numpy())
