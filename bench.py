@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — relaxed VSSR-MC proposals/s on SrTiO3(001) 2x2 with the PaiNN 3-model ensemble.
+
+A "step" is one MC iteration of every chain on this GPU: propose (host, reference RNG order) ->
+ideal-site structure -> H2D -> neighbour list + <=20 FIRE steps with 21 ensemble force
+evaluations (GPU, no host round trip) -> 8 scalars per chain D2H -> Metropolis accept/reject.
+
+  value   = relaxed proposals/s with the step's inputs already resident in HBM (relax call only)
+  e2e     = the same metric through the public API (MultiChainMC.step) with HOST buffers:
+            pinned H2D of positions/species/masks and D2H of the result inside the timed region
+  roofline= dominant kernel class, timed live with CUDA-event pairs on the launching stream
+  cpu_baseline = the CPU oracle (torch fp32 PaiNN + autograd forces + numpy FIRE) on the host cores
+
+`--impl reference` times the reference path's CPU restatement (the oracle: the reference's own
+stack — ASE/NFF/LAMMPS — is not installable here) on the same config.
+Weak scaling: --chains-per-gpu chains on every rank (128 -> 1024 chains on 8 GPUs, BASELINE
+config 4); chains never interact, NCCL only gathers per-chain scalars.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+GOLD = ROOT / "tests" / "golden"
+
+CHEM_POTS = {"Sr": -2, "Ti": 0, "O": 0}
+ADSORBATES = ["Sr", "Ti", "O"]
+N_SITES = 64
+RELAX_STEPS = 20
+FREE = [7, 8, 22, 23, 37, 38, 52, 53]   # surface_depth=1 (tutorials/SrTiO3_001.ipynb cell 7 log)
+
+
+def load_workload():
+    z = np.load(GOLD / "structures.npz")
+    pots = json.loads((GOLD / "potentials.json").read_text())
+    n = "SrTiO3_001_2x2"
+    pos, num, cell = z[f"{n}/positions"], z[f"{n}/numbers"], z[f"{n}/cell"]
+    fixed = np.ones(len(num), bool)
+    fixed[FREE] = False
+    return pos, num, cell, fixed, pots["offset_data"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            t = [x.strip() for x in l.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0])); mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if t[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_proposals(n_proposals: int, threads: int, seed0: int = 0):
+    """Reference-path CPU restatement: single chain, oracle PaiNN (torch fp32, autograd forces) +
+    numpy FIRE, same MC host code.  Returns (proposals, seconds, atom_model_evals)."""
+    import torch
+    from oracle import relax as orelax
+    from oracle.painn import EnsembleOracle, init_random_weights, surface_energy
+    from surface_sampling_b200 import mc
+
+    torch.set_num_threads(threads)
+    pos, num, cell, fixed, od = load_workload()
+    states = [init_random_weights(s) for s in (0, 1, 2)]
+    ens = EnsembleOracle(states, od, dtype=torch.float32)
+    pbc = np.array([True, True, True])
+    evals = [0]
+
+    def relax_fn(pos_l, num_l, fix_l):
+        out = np.zeros((len(pos_l), 8))
+        for k, (p, zz, fx) in enumerate(zip(pos_l, num_l, fix_l)):
+            nb = ens.build_nbrs(p, cell, pbc)
+
+            def calc(x):
+                r = ens.calculate(x, zz, cell, pbc, nb)
+                evals[0] += 3 * len(zz)
+                return r["energy"][0], r["forces"]
+
+            o = orelax.relax(calc, p, fx, optimizer="FIRE", relax_steps=RELAX_STEPS, fmax=0.01)
+            out[k, 0], out[k, 2], out[k, 4] = o["energy"], o["raw_energy"], o["nsteps"]
+        return out
+
+    sites = mc.make_site_grid(pos, cell, N_SITES, 1.5)
+    drv = mc.MultiChainMC(num, pos, fixed, sites, ADSORBATES, relax_fn,
+                          lambda e, sym: surface_energy(e, [mc.NUMBERS[s] for s in sym], od, CHEM_POTS), [seed0])
+    drv._ensure_prev(drv.chains)   # the initial-state energy is not a proposal
+    drv.n_relaxed, evals[0] = 0, 0
+    t0 = time.perf_counter()
+    for _ in range(n_proposals):
+        drv.step()
+    dt = time.perf_counter() - t0
+    return drv.n_relaxed, dt, evals[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_oracle_proposals(1, threads)
+    n, dt, evals = 0, 0.0, 0
+    for s in range(args.steps):
+        a, b, c = cpu_oracle_proposals(1, threads, seed0=s)
+        n, dt, evals = n + a, dt + b, evals + c
+    val = n / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "relaxed_proposals_per_sec", "value": val, "unit": "proposals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} single-chain relaxed proposals (1 per step), oracle torch-CPU PaiNN + numpy FIRE"},
+        "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "painn_atom_model_evals_per_sec": evals / dt,
+    }))
+
+
+def workload_config(args, chains):
+    return {"workload": "SrTiO3(001) 2x2 VSSR-MC, PaiNN 3-model ensemble (random-init weights seeds 0,1,2), "
+                        f"semigrand Sr/Ti/O on {N_SITES} virtual sites, FIRE relax_steps={RELAX_STEPS} fmax=0.01 "
+                        "(BASELINE.json configs[3])",
+            "chains_per_gpu": chains, "atoms_per_chain": "60 + adsorbates", "cutoff_A": 5.0, "skin_A": 1.0,
+            "l2": "per-evaluation working set (activations, ~48 KB/atom/model) exceeds the 126 MB L2; no explicit flush",
+            "parallelism": f"chains sharded, {args.gpus} rank(s), no data-path collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains-per-gpu", type=int, default=128)
+    ap.add_argument("--cpu-baseline-proposals", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from oracle.painn import init_random_weights   # weight INIT only (random-init per BASELINE); not on the timed path
+    from surface_sampling_b200 import _lib, engine, mc
+    from surface_sampling_b200.calculators import surface_energy_from
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    C = args.chains_per_gpu
+    pos, num, cell, fixed, od = load_workload()
+    states = [init_random_weights(s) for s in (0, 1, 2)]
+    eng = engine.PainnEngine(states, od)
+    pbc = np.array([True, True, True])
+    io = {"h2d": 0, "d2h": 0}
+    e_cap = C * 72 * 96
+
+    def relax_fn(pos_l, num_l, fix_l):
+        b = engine.Batch.from_arrays(pos_l, num_l, [cell] * len(pos_l), [pbc] * len(pos_l), fix_l)
+        zh = np.concatenate(num_l)
+        r = eng.relax(b, relax_steps=RELAX_STEPS, fmax=0.01, z_host=zh, want_std=False, e_cap=e_cap)
+        out = r["out"].cpu().numpy()          # D2H of 8 scalars per chain (synchronises)
+        io["h2d"] = b.h2d_bytes() + 8 * b.n_struct
+        io["d2h"] = out.nbytes
+        return out
+
+    sites = mc.make_site_grid(pos, cell, N_SITES, 1.5)
+    seeds = [rank * C + c for c in range(C)]
+    drv = mc.MultiChainMC(num, pos, fixed, sites, ADSORBATES, relax_fn,
+                          lambda e, sym: surface_energy_from(e, sym, od, CHEM_POTS), seeds)
+    drv._ensure_prev(drv.chains)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------ e2e: public API, host buffers
+    for _ in range(args.warmup):
+        drv.step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = int(lib.vssr_launch_count())
+    ev0.record()
+    for _ in range(args.steps):
+        drv.step()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    e2e_launches = int(lib.vssr_launch_count()) - l0
+
+    # ------------------------------------------------------------ device-resident: relax call only
+    # stage K proposal batches (current chain states + one fresh proposal each) in HBM beforehand
+    staged, staged_host, atoms_total = [], [], 0
+    for k in range(args.steps + args.warmup):
+        pl, nl, fl = [], [], []
+        for c in drv.chains:
+            snap = c.snapshot()
+            c.apply(c.propose_change(ADSORBATES))
+            p, zz = c.arrays()
+            c.restore(snap)
+            pl.append(p); nl.append(zz)
+            fl.append(np.concatenate([fixed, np.zeros(len(zz) - len(fixed), bool)]))
+        b = engine.Batch.from_arrays(pl, nl, [cell] * C, [pbc] * C, fl)
+        staged.append((b, np.concatenate(nl)))
+        if k >= args.warmup:
+            atoms_total += b.n_atoms
+            if len(staged_host) < 2:
+                staged_host.append((pl, nl, fl))
+    for b, zh in staged[:args.warmup]:
+        eng.relax(b, RELAX_STEPS, 0.01, z_host=zh, want_std=False, e_cap=e_cap)
+    barrier()
+    l0 = int(lib.vssr_launch_count())
+    ev0.record()
+    for b, zh in staged[args.warmup:]:
+        eng.relax(b, RELAX_STEPS, 0.01, z_host=zh, want_std=False, e_cap=e_cap)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = int(lib.vssr_launch_count()) - l0
+    clocks = sampler.stop()
+
+    # ------------------------------------------------------------ per-kernel-class profile (same region again)
+    ncls = int(lib.vssr_kernel_class_count())
+    ms = np.zeros(ncls); cnt = np.zeros(ncls, np.int64)
+    lib.vssr_profile_enable(1)
+    fresh = [engine.Batch.from_arrays(pl, nl, [cell] * C, [pbc] * C, fl) for pl, nl, fl in staged_host]
+    for b, (_, zh) in zip(fresh, staged[args.warmup:][:2]):
+        eng.relax(b, RELAX_STEPS, 0.01, z_host=zh, want_std=False, e_cap=e_cap)
+    lib.vssr_profile_collect(ms.ctypes.data, cnt.ctypes.data, ncls)
+    lib.vssr_profile_enable(0)
+    names = ["nbr", "edge_geometry", "gemm_fp32", "message_fwd", "message_bwd", "elementwise", "readout",
+             "ensemble_stats", "fire", "classical"]
+    breakdown = {names[k]: {"ms": round(float(ms[k]), 3), "launches": int(cnt[k])} for k in range(ncls) if cnt[k]}
+    n_prof = len(fresh)
+    a_prof = sum(b.n_atoms for b in fresh)
+
+    # max over ranks
+    t = torch.tensor([e2e_ms, dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms, dev_ms = t.tolist()
+    total_props = C * args.steps * world
+    value = total_props / (dev_ms * 1e-3)
+    e2e = total_props / (e2e_ms * 1e-3)
+    evals_per_prop = (RELAX_STEPS + 1) * 3      # model force evaluations per proposal (3-model ensemble)
+    atom_evals = atoms_total * evals_per_prop * world / (dev_ms * 1e-3)
+
+    # roofline of the dominant kernel class
+    dom = max(breakdown, key=lambda k: breakdown[k]["ms"]) if breakdown else "gemm_fp32"
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else None
+    bf16 = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json, sustained bf16 / 2 = TF32 dense)" if peaks else "fallback"
+    n_evals_prof = n_prof * (RELAX_STEPS + 1)
+    E_per_atom = 2504 / 60.0
+    flops = {   # algorithmic FLOPs per model force-evaluation per atom (DESIGN.md / SURVEY.md 8d)
+        "gemm_fp32": 2 * 1491072.0,
+        "message_fwd": 3 * E_per_atom * 2 * (3 * 20 * 128 + 12 * 128),
+        "message_bwd": 3 * E_per_atom * 2 * (6 * 20 * 128 + 60 * 128),
+    }
+    roof = None
+    if dom in flops and breakdown[dom]["ms"] > 0:
+        fl = flops[dom] * 3 * a_prof * (RELAX_STEPS + 1) / n_prof * n_prof   # 3 models, all evals profiled
+        achieved = fl / (breakdown[dom]["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": bf16 / 2, "unit": "TFLOP/s",
+                "frac": achieved / (bf16 / 2), "traffic": None, "peak_source": peak_src,
+                "note": "fp32 FMA path this round (no tcgen05 yet); peak is the TF32 tensor pipe the GEMMs should use; "
+                        "CUDA-core fp32 peak is ~74 TFLOP/s"}
+    out = {
+        "metric": "relaxed_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, C),
+        "e2e": {"value": e2e, "unit": "proposals/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "gpu_launches_e2e": e2e_launches,
+        "painn_atom_model_evals_per_sec": atom_evals,
+        "roofline": roof, "kernel_breakdown_ms": breakdown, "clocks": clocks,
+    }
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            n, dt, ev = cpu_oracle_proposals(args.cpu_baseline_proposals, threads)
+            out["cpu_baseline"] = {"value": n / dt, "unit": "proposals/s", "cores": threads, "kind": "port",
+                                   "sample": f"{n} single-chain relaxed proposals of the same workload "
+                                             f"({dt:.1f} s), oracle torch-CPU fp32 PaiNN + numpy FIRE",
+                                   "painn_atom_model_evals_per_sec": ev / dt}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -167,6 +167,14 @@ int vssr_classical_relax_host(int32_t kind, const double* params, int32_t ntypes
 /* number of kernel launches this library has enqueued since load (bench.py: gpu_launches)     */
 int64_t vssr_launch_count(void);
 
+/* Optional per-kernel-class profile (bench.py roofline): when enabled, every launch is bracketed
+ * by a cudaEvent pair on its own stream.  Classes: 0 nbr, 1 edge geometry, 2 GEMM, 3 message fwd,
+ * 4 message bwd, 5 elementwise, 6 readout, 7 ensemble stats, 8 FIRE, 9 classical.
+ * vssr_profile_collect synchronises the device and returns summed milliseconds / launch counts. */
+int vssr_kernel_class_count(void);
+int vssr_profile_enable(int on);
+int vssr_profile_collect(double* ms /*[n_class]*/, int64_t* launches /*[n_class]*/, int n_class);
+
 #ifdef __cplusplus
 }
 #endif

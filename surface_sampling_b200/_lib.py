@@ -23,6 +23,9 @@ SIGNATURES = {
     "vssr_version": (c_int, []),
     "vssr_device_cc": (c_int, []),
     "vssr_launch_count": (c_i64, []),
+    "vssr_kernel_class_count": (c_int, []),
+    "vssr_profile_enable": (c_int, [c_int]),
+    "vssr_profile_collect": (c_int, [c_void_p, c_void_p, c_int]),
     "vssr_nbr_build": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "vssr_painn_weight_floats": (c_i64, []),

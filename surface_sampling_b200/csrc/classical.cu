@@ -593,10 +593,9 @@ extern "C" int vssr_classical_energy_forces(int32_t kind, const double* params, 
   if (smem > 227 * 1024) return VSSR_ERR_ARG;
   int rc = set_smem<false>(smem);
   if (rc) return rc;
-  classical_kernel<false><<<n_struct, NT, smem, (cudaStream_t)stream>>>(
+  VSSR_PROF(VSSR_K_CLASSICAL, (cudaStream_t)stream, classical_kernel<false><<<n_struct, NT, smem, (cudaStream_t)stream>>>(
       kind, params, ntypes, const_cast<double*>(pos), types, nullptr, atom_ptr, cell, pbc, n_max, max_nbr, 0, 0.0, 0.0,
-      energy, nullptr, forces, per_atom_energy, status);
-  VSSR_LAUNCH_CHECK();
+      energy, nullptr, forces, per_atom_energy, status));
   return VSSR_OK;
 }
 
@@ -613,10 +612,9 @@ extern "C" int vssr_classical_relax(int32_t kind, const double* params, int32_t 
   if (smem > 227 * 1024) return VSSR_ERR_ARG;
   int rc = set_smem<true>(smem);
   if (rc) return rc;
-  classical_kernel<true><<<n_struct, NT, smem, (cudaStream_t)stream>>>(kind, params, ntypes, pos, types, fixed, atom_ptr,
+  VSSR_PROF(VSSR_K_CLASSICAL, (cudaStream_t)stream, classical_kernel<true><<<n_struct, NT, smem, (cudaStream_t)stream>>>(kind, params, ntypes, pos, types, fixed, atom_ptr,
                                                                       cell, pbc, n_max, max_nbr, relax_steps, fmax, skin,
-                                                                      nullptr, out, forces, nullptr, status);
-  VSSR_LAUNCH_CHECK();
+                                                                      nullptr, out, forces, nullptr, status));
   return VSSR_OK;
 }
 

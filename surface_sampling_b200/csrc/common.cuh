@@ -7,11 +7,28 @@
 
 extern long long g_vssr_launches;  // defined in api.cu
 
+// Kernel classes for the optional per-class CUDA-event profile (bench.py roofline).
+enum VssrKernelClass {
+  VSSR_K_NBR = 0, VSSR_K_GEOM, VSSR_K_GEMM, VSSR_K_MSG_FWD, VSSR_K_MSG_BWD, VSSR_K_ELEMWISE, VSSR_K_READOUT,
+  VSSR_K_ENSEMBLE, VSSR_K_FIRE, VSSR_K_CLASSICAL, VSSR_K_NCLASS
+};
+void vssr_prof_begin(int cls, cudaStream_t st);  // no-ops unless vssr_profile_enable(1)
+void vssr_prof_end(int cls, cudaStream_t st);
+
 #define VSSR_LAUNCH_CHECK()                                  \
   do {                                                       \
     ++g_vssr_launches;                                       \
     cudaError_t _e = cudaGetLastError();                     \
     if (_e != cudaSuccess) return (int)_e;                   \
+  } while (0)
+
+// launch wrapper: VSSR_PROF(cls, stream, kernel<<<...>>>(...));
+#define VSSR_PROF(cls, st, ...)                              \
+  do {                                                       \
+    vssr_prof_begin((cls), (st));                            \
+    __VA_ARGS__;                                             \
+    vssr_prof_end((cls), (st));                              \
+    VSSR_LAUNCH_CHECK();                                     \
   } while (0)
 
 #define VSSR_CUDA(call)                                      \

@@ -260,26 +260,22 @@ extern "C" int vssr_ensemble_stats(const double* energy, const float* grad, cons
   (void)atom_ptr;
   if (!energy || !grad || !e_mean || !e_std || !f_mean) return VSSR_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  ensemble_energy_kernel<<<ceil_div(n_struct, 128), 128, 0, st>>>(energy, offset_ev, n_models, n_struct, e_mean, e_std);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_ENSEMBLE, st, ensemble_energy_kernel<<<ceil_div(n_struct, 128), 128, 0, st>>>(energy, offset_ev, n_models, n_struct, e_mean, e_std));
   const long long n3 = 3LL * n_atoms;
-  ensemble_force_kernel<<<ceil_div(n3, 256), 256, 0, st>>>(grad, n_models, n3, f_mean, f_std);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_ENSEMBLE, st, ensemble_force_kernel<<<ceil_div(n3, 256), 256, 0, st>>>(grad, n_models, n3, f_mean, f_std));
   return VSSR_OK;
 }
 
 extern "C" int vssr_system_reduce(const float* per_atom, const int32_t* atom_ptr, int32_t n_struct, float* out,
                                   void* stream) {
   if (!per_atom || !atom_ptr || !out) return VSSR_ERR_ARG;
-  system_reduce_kernel<<<ceil_div(n_struct, 4), 128, 0, (cudaStream_t)stream>>>(per_atom, atom_ptr, n_struct, out);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_ENSEMBLE, (cudaStream_t)stream, system_reduce_kernel<<<ceil_div(n_struct, 4), 128, 0, (cudaStream_t)stream>>>(per_atom, atom_ptr, n_struct, out));
   return VSSR_OK;
 }
 
 extern "C" int vssr_atom_norm(const float* vec, int32_t n_atoms, float* out, void* stream) {
   if (!vec || !out) return VSSR_ERR_ARG;
-  atom_norm_kernel<<<ceil_div(n_atoms, 256), 256, 0, (cudaStream_t)stream>>>(vec, n_atoms, out);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_ENSEMBLE, (cudaStream_t)stream, atom_norm_kernel<<<ceil_div(n_atoms, 256), 256, 0, (cudaStream_t)stream>>>(vec, n_atoms, out));
   return VSSR_OK;
 }
 
@@ -287,8 +283,7 @@ extern "C" int vssr_fire_init(double* fire_state, double* vel, int32_t n_struct,
   if (!fire_state || !vel) return VSSR_ERR_ARG;
   const long long n3 = 3LL * n_atoms;
   const long long n = n3 > n_struct ? n3 : n_struct;
-  fire_init_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(fire_state, vel, n_struct, n3);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_FIRE, (cudaStream_t)stream, fire_init_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(fire_state, vel, n_struct, n3));
   return VSSR_OK;
 }
 
@@ -296,9 +291,8 @@ extern "C" int vssr_fire_step(double* pos, float* pos32, double* vel, const floa
                               const int32_t* atom_ptr, int32_t n_struct, double* fire_state, int32_t max_steps,
                               double fmax, void* stream) {
   if (!pos || !pos32 || !vel || !forces || !fixed || !atom_ptr || !fire_state) return VSSR_ERR_ARG;
-  fire_step_kernel<<<n_struct, 128, 0, (cudaStream_t)stream>>>(pos, pos32, vel, forces, fixed, atom_ptr, fire_state,
-                                                               max_steps, fmax);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_FIRE, (cudaStream_t)stream, fire_step_kernel<<<n_struct, 128, 0, (cudaStream_t)stream>>>(pos, pos32, vel, forces, fixed, atom_ptr, fire_state,
+                                                               max_steps, fmax));
   return VSSR_OK;
 }
 
@@ -321,8 +315,7 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   const long long n3 = 3LL * n_atoms;
-  to_float_kernel<<<ceil_div(n3, 256), 256, 0, st>>>(pos, n3, w.pos32);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_FIRE, st, to_float_kernel<<<ceil_div(n3, 256), 256, 0, st>>>(pos, n3, w.pos32));
   if ((rc = vssr_nbr_build(w.pos32, atom_ptr, cell, pbc, n_struct, n_atoms, cutoff + skin, w.deg, w.rowptr, w.col,
                            w.shift, e_cap, status, stream)))
     return rc;
@@ -340,7 +333,6 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
                              stream)))
       return rc;
   }
-  relax_finalize_kernel<<<ceil_div(n_struct, 128), 128, 0, st>>>(w.e_mean, w.e_std, w.state, n_struct, out);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_FIRE, st, relax_finalize_kernel<<<ceil_div(n_struct, 128), 128, 0, st>>>(w.e_mean, w.e_std, w.state, n_struct, out));
   return VSSR_OK;
 }

@@ -190,13 +190,10 @@ extern "C" int vssr_nbr_build(const float* pos, const int32_t* atom_ptr, const f
   }
   const int warps_per_block = 4;
   const int grid = ceil_div(n_atoms, warps_per_block);
-  nbr_kernel<false><<<grid, 128, 0, st>>>(pos, atom_ptr, cell, pbc, n_struct, n_atoms, cutoff, deg, nullptr, nullptr,
-                                          nullptr, 0, status);
-  VSSR_LAUNCH_CHECK();
-  scan_kernel<<<1, 1024, 0, st>>>(deg, n_atoms, rowptr);
-  VSSR_LAUNCH_CHECK();
-  nbr_kernel<true><<<grid, 128, 0, st>>>(pos, atom_ptr, cell, pbc, n_struct, n_atoms, cutoff, deg, rowptr, col, shift,
-                                         (long long)e_cap, status);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_NBR, st, nbr_kernel<false><<<grid, 128, 0, st>>>(pos, atom_ptr, cell, pbc, n_struct, n_atoms, cutoff, deg, nullptr, nullptr,
+                                          nullptr, 0, status));
+  VSSR_PROF(VSSR_K_NBR, st, scan_kernel<<<1, 1024, 0, st>>>(deg, n_atoms, rowptr));
+  VSSR_PROF(VSSR_K_NBR, st, nbr_kernel<true><<<grid, 128, 0, st>>>(pos, atom_ptr, cell, pbc, n_struct, n_atoms, cutoff, deg, rowptr, col, shift,
+                                         (long long)e_cap, status));
   return VSSR_OK;
 }

@@ -168,8 +168,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
 template <int BN, int AMODE, int EPI>
 int launch_gemm(const GemmArgs& g, int n_models, cudaStream_t st) {
   dim3 grid(ceil_div(g.M, 128), g.N / BN, n_models);
-  gemm_kernel<BN, AMODE, EPI><<<grid, 256, 0, st>>>(g);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_GEMM, st, gemm_kernel<BN, AMODE, EPI><<<grid, 256, 0, st>>>(g));
   return 0;
 }
 
@@ -657,11 +656,9 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const dim3 ew_grid(ceil_div((long long)A * F, 256), M);
   const dim3 msg_grid(ceil_div(A, MSG_APB), M);
 
-  edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(pos, atom_ptr, cell, n_struct, A, rowptr, col, shift,
-                                                       (long long)e_cap, cutoff, w.eg, w.re, w.dre, w.evex, w.grad0);
-  VSSR_LAUNCH_CHECK();
-  embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(pos, atom_ptr, cell, n_struct, A, rowptr, col, shift,
+                                                       (long long)e_cap, cutoff, w.eg, w.re, w.dre, w.evex, w.grad0));
+  VSSR_PROF(VSSR_K_ELEMWISE, st, embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]));
 
   int rc;
   for (int l = 0; l < NCONV; ++l) {
@@ -680,16 +677,14 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       message_fwd_kernel<true><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
                                                          w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]);
     else
-      message_fwd_kernel<false><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
-                                                          w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]);
-    VSSR_LAUNCH_CHECK();
+      VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<false><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
+                                                          w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
     // F4
     g = GemmArgs{w.vmid[l], F, (long long)A * 3 * F, wl + L_UVT, 2 * F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  w.UV[l], 2 * F, (long long)A * 6 * F, 3 * A, 2 * F, F};
     if ((rc = launch_gemm<128, 0, 0>(g, M, st))) return rc;
     // F5
-    nrm_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], A, w.cat[l]);
-    VSSR_LAUNCH_CHECK();
+    VSSR_PROF(VSSR_K_ELEMWISE, st, nrm_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], A, w.cat[l]));
     // F6
     g = GemmArgs{w.cat[l], 2 * F, (long long)A * 2 * F, wl + L_W3T, F, W_TOTAL, wl + L_B3, W_TOTAL, nullptr, 0, 0,
                  nullptr, 0, w.h3[l], F, MA_F, A, F, 2 * F};
@@ -699,26 +694,22 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
                  w.a[l], F3, (long long)A * F3, A, F3, F};
     if ((rc = launch_gemm<128, 1, 1>(g, M, st))) return rc;
     // F8
-    update_fwd_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], w.a[l], w.cat[l], w.vmid[l], A, w.s[l + 1], w.v[l + 1]);
-    VSSR_LAUNCH_CHECK();
+    VSSR_PROF(VSSR_K_ELEMWISE, st, update_fwd_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], w.a[l], w.cat[l], w.vmid[l], A, w.s[l + 1], w.v[l + 1]));
   }
   // readout
   {
     GemmArgs g{w.s[NCONV], F, MA_F, weights + R_W5T, FH, W_TOTAL, weights + R_B5, W_TOTAL, nullptr, 0, 0, nullptr, 0,
                w.h5, FH, (long long)A * FH, A, FH, F};
     if ((rc = launch_gemm<64, 0, 1>(g, M, st))) return rc;
-    readout_energy_kernel<<<dim3(ceil_div(A, 4), M), 128, 0, st>>>(weights, w.h5, w.evex, A, w.e_atom);
-    VSSR_LAUNCH_CHECK();
-    energy_reduce_kernel<<<dim3(ceil_div(n_struct, 4), M), 128, 0, st>>>(w.e_atom, atom_ptr, n_struct, A, energy);
-    VSSR_LAUNCH_CHECK();
+    VSSR_PROF(VSSR_K_READOUT, st, readout_energy_kernel<<<dim3(ceil_div(A, 4), M), 128, 0, st>>>(weights, w.h5, w.evex, A, w.e_atom));
+    VSSR_PROF(VSSR_K_READOUT, st, energy_reduce_kernel<<<dim3(ceil_div(n_struct, 4), M), 128, 0, st>>>(w.e_atom, atom_ptr, n_struct, A, energy));
   }
   if (embedding) {
     VSSR_CUDA(cudaMemcpyAsync(embedding, w.s[NCONV], (size_t)M * A * F * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
 
   // ---------------- backward ----------------
-  grad_init_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.grad0, 3 * A, grad);
-  VSSR_LAUNCH_CHECK();
+  VSSR_PROF(VSSR_K_ELEMWISE, st, grad_init_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.grad0, 3 * A, grad));
   {
     // ds = (dswish(h5) * w6) . W5      [A,64]x[64,128]
     GemmArgs g{w.h5, FH, (long long)A * FH, weights + R_W5, F, W_TOTAL, nullptr, 0, nullptr, 0, 0, weights + R_W6,
@@ -732,8 +723,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     const float* wl = weights + W_LAYER0 + (long long)l * L_SIZE;
     GemmArgs g{};
     // B8
-    update_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.ds, dv_cur, w.UV[l], w.a[l], A, w.da, w.dUV);
-    VSSR_LAUNCH_CHECK();
+    VSSR_PROF(VSSR_K_ELEMWISE, st, update_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.ds, dv_cur, w.UV[l], w.a[l], A, w.da, w.dUV));
     // B7: dh3 = (da . W4) * dswish(h3)
     g = GemmArgs{w.da, F3, (long long)A * F3, wl + L_W4, F, W_TOTAL, nullptr, 0, w.h3[l], F, MA_F, nullptr, 0,
                  w.dh3, F, MA_F, A, F, F3};
@@ -743,21 +733,18 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
                  w.dcat, 2 * F, (long long)A * 2 * F, A, 2 * F, F};
     if ((rc = launch_gemm<128, 0, 0>(g, M, st))) return rc;
     // B5
-    nrm_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.dcat, w.cat[l], w.UV[l], A, w.ds, w.dUV);
-    VSSR_LAUNCH_CHECK();
+    VSSR_PROF(VSSR_K_ELEMWISE, st, nrm_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.dcat, w.cat[l], w.UV[l], A, w.ds, w.dUV));
     // B4: dv += dUV . [U;V]      [3A,256]x[256,128]
     g = GemmArgs{w.dUV, 2 * F, (long long)A * 6 * F, wl + L_UV, F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  dv_cur, F, (long long)A * 3 * F, 3 * A, F, 2 * F};
     if ((rc = launch_gemm<128, 0, 3>(g, M, st))) return rc;
     // B3
     if (l == 0) {
-      message_bwd_kernel<true><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
-                                                         w.dre, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, grad);
-      VSSR_LAUNCH_CHECK();
+      VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<true><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
+                                                         w.dre, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, grad));
     } else {
-      message_bwd_kernel<false><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
-                                                          w.dre, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, grad);
-      VSSR_LAUNCH_CHECK();
+      VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<false><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
+                                                          w.dre, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, grad));
       // B2: dh1 = (dphi . W2) * dswish(h1)
       g = GemmArgs{w.dphi, F3, (long long)A * F3, wl + L_W2, F, W_TOTAL, nullptr, 0, w.h1[l], F, MA_F, nullptr, 0,
                    w.dh1, F, MA_F, A, F, F3};

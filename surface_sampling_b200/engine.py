@@ -203,12 +203,17 @@ class PainnEngine:
         if self.offset_data is None:
             return None
         sto = self.offset_data["stoidict"]
-        per_z = np.zeros(120)
-        for zz, sym in SYMBOLS.items():
-            if sym in sto:
-                per_z[zz] = sto[sym]
-        csum = np.concatenate([[0.0], np.cumsum(per_z[np.asarray(z_host)])])
-        tot = csum[atom_ptr[1:]] - csum[atom_ptr[:-1]] + sto["offset"]
+        z_host = np.asarray(z_host)
+        # exact integer element counts per structure -> the result is independent of what else is
+        # in the batch (bitwise batch invariance), unlike a float cumsum over atoms
+        tot = np.full(len(atom_ptr) - 1, float(sto["offset"]))
+        for zz in sorted(SYMBOLS):
+            sym = SYMBOLS[zz]
+            if sym not in sto:
+                continue
+            csum = np.concatenate([[0], np.cumsum(z_host == zz, dtype=np.int64)])
+            cnt = csum[atom_ptr[1:]] - csum[atom_ptr[:-1]]
+            tot = tot + cnt * float(sto[sym])
         return tot * HARTREE_TO_KCAL_MOL / KCAL_PER_EV
 
     def energy_forces(self, batch: Batch, z_host: np.ndarray | None = None, want_embedding=False, nbrs=None):

@@ -1,0 +1,298 @@
+"""Multi-chain VSSR-MC driver: the callers on either side of the hot path, batched over chains.
+
+Reference semantics kept exactly:
+  * state per chain = ``occ`` (atom index adsorbed at each virtual site, 0 = empty), appended
+    adsorbate atoms with ASE index semantics (append at end; deletion shifts higher indices) and
+    the ``ads_group`` tag — mcmc/slab.py:235-395, mcmc/system.py:149-182;
+  * RNG draw order per iteration — semigrand: ``np.random.choice(range(n_sites))`` ->
+    ``random.choice(ads_choices)`` -> ``np.random.rand()`` (events/proposal.py:85,99,
+    events/criterion.py:168); canonical: ``random.sample(types, 2)`` -> ``random.choices`` x2 ->
+    ``np.random.rand()`` (slab.py:70,219-222).  Every chain owns a private legacy
+    ``np.random.RandomState(seed)`` and ``random.Random(seed)``, so chain c replays exactly what the
+    single-chain reference does after ``np.random.seed(seed); random.seed(seed)``;
+  * every proposal is relaxed from the IDEAL-site structure (system.py:348-357,370); Metropolis
+    compares SURFACE energies; one uniform is drawn per iteration even when p >= 1; the very
+    first iteration recomputes the missing ``prev`` energy (criterion.py:144-149).
+All chains advance in lock step: one batched relax call per MC iteration, only 8 scalars per chain
+come back from the GPU.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+import random
+from collections import Counter
+
+import numpy as np
+
+from .engine import NUMBERS, SYMBOLS
+
+# mcmc/slab.py:22-32
+ATOM_GROUPS = {
+    "HO": (["O", "H"], np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]])),
+    "H2O": (["O", "H", "H"], np.array([[0.0, 0.0, 0.0], [0.5, -math.sqrt(3) / 2, 0.0], [0.5, math.sqrt(3) / 2, 0.0]])),
+}
+
+
+def hill_formula(symbols) -> str:
+    c = Counter(symbols)
+    keys = sorted(c)
+    if "C" in c:
+        keys = ["C"] + (["H"] if "H" in c else []) + [k for k in keys if k not in ("C", "H")]
+    return "".join(f"{k}{c[k] if c[k] > 1 else ''}" for k in keys)
+
+
+class ChainState:
+    """SurfaceSystem state restricted to what the MC loop mutates."""
+
+    def __init__(self, numbers0, positions0, ads_coords, occ=None, seed=0):
+        self.n0 = len(numbers0)
+        self.numbers = list(int(z) for z in numbers0)          # real_atoms numbers
+        self.positions = [np.asarray(p, dtype=float) for p in positions0]
+        self.ads_group = [0] * self.n0
+        self.ads_coords = np.asarray(ads_coords, dtype=float)
+        self.occ = np.zeros(len(self.ads_coords), dtype=int) if occ is None else np.array(occ, dtype=int)
+        self.results = {}
+        self.np_rng = np.random.RandomState(seed)
+        self.py_rng = random.Random(seed)
+
+    def __len__(self):
+        return len(self.numbers)
+
+    # ---- save/restore (system.py:149-182) ----
+    def snapshot(self):
+        return (list(self.numbers), list(self.positions), list(self.ads_group), self.occ.copy(), dict(self.results))
+
+    def restore(self, snap):
+        self.numbers, self.positions, self.ads_group, self.occ, self.results = (
+            list(snap[0]), list(snap[1]), list(snap[2]), snap[3].copy(), dict(snap[4]))
+
+    @property
+    def num_adsorbates(self):
+        return int(np.count_nonzero(self.occ))
+
+    def symbols_at_site(self, site_idx):
+        """get_start_ads (slab.py:277-289): all atoms whose ads_group == occ[site]."""
+        idx = self.occ[site_idx]
+        return [SYMBOLS[self.numbers[a]] for a in range(len(self)) if self.ads_group[a] == idx]
+
+    # ---- slab.py:235-395 ----
+    def change_site(self, site_idx, end_ads):
+        if site_idx >= len(self.occ):
+            raise IndexError("site index out of range")
+        if self.occ[site_idx] != 0:
+            self.remove_atom(site_idx, self.symbols_at_site(site_idx))
+        if end_ads != "None":
+            if end_ads in ATOM_GROUPS:
+                self.add_atom_group(site_idx, end_ads)
+            else:
+                self.add_atom(site_idx, end_ads)
+
+    def add_atom(self, site_idx, adsorbate):
+        idx = len(self)
+        self.occ[site_idx] = idx
+        self.numbers.append(NUMBERS[adsorbate])
+        self.positions.append(self.ads_coords[site_idx].copy())
+        self.ads_group.append(idx)
+
+    def add_atom_group(self, site_idx, group_name):
+        if group_name not in ATOM_GROUPS:
+            raise ValueError(f"Unknown group name: {group_name}")
+        syms, offs = ATOM_GROUPS[group_name]
+        idx = len(self)
+        self.occ[site_idx] = idx
+        for s, o in zip(syms, offs):
+            self.numbers.append(NUMBERS[s])
+            self.positions.append(self.ads_coords[site_idx] + o)
+            self.ads_group.append(idx)
+
+    def remove_atom(self, site_idx, start_ads):
+        idx = int(self.occ[site_idx])
+        assert np.count_nonzero(self.occ == idx) == 1, "no sites found" if not np.any(self.occ == idx) else "more than 1 site found"
+        n = len(start_ads)
+        if n > 1 and hill_formula(start_ads) not in ATOM_GROUPS:
+            raise ValueError(f"Unknown group name: {hill_formula(start_ads)}")
+        del self.numbers[idx:idx + n]
+        del self.positions[idx:idx + n]
+        del self.ads_group[idx:idx + n]
+        self.occ = np.where(self.occ >= idx, self.occ - n, self.occ)
+        self.ads_group = [g - n if g >= idx else g for g in self.ads_group]
+        self.occ = np.where(self.occ < 0, 0, self.occ)
+        self.ads_group = [0 if g < 0 else g for g in self.ads_group]
+        self.occ[site_idx] = 0
+
+    # ---- proposals ----
+    def propose_change(self, adsorbates, site_idx=None):
+        """ChangeProposal.get_action (events/proposal.py:74-106)."""
+        choices = list(adsorbates) + ["None"]
+        if site_idx is None:
+            site_idx = int(self.np_rng.choice(range(len(self.occ))))
+        if self.occ[site_idx] != 0:
+            start = hill_formula(self.symbols_at_site(site_idx))
+            choices.remove(start)
+        else:
+            start = "None"
+            choices.remove("None")
+        end = self.py_rng.choice(choices)
+        return {"name": "change", "site_idx": site_idx, "start_ads": start, "end_ads": end}
+
+    def propose_switch(self):
+        """SwitchProposal.get_action -> get_complementary_idx with uniform weights (slab.py:168-232).
+        Note the reference's groupby-into-dict keeps only the LAST run of each symbol; replicated."""
+        filled = np.argwhere(self.occ != 0).flatten().tolist()
+        curr = {k: list(g) for k, g in itertools.groupby(filled, key=lambda x: SYMBOLS[self.numbers[self.occ[x]]])}
+        empty = np.argwhere(self.occ == 0).flatten().tolist()
+        if empty:
+            curr["None"] = empty
+        t1, t2 = self.py_rng.sample(list(curr.keys()), 2)
+        s1, s2 = (self.py_rng.choices(curr[t], weights=np.ones_like(curr[t]), k=1)[0] for t in (t1, t2))
+        return {"name": "switch", "site1_idx": s1, "site2_idx": s2, "site1_ads": t1, "site2_ads": t2}
+
+    def apply(self, action):
+        if action["name"] == "change":
+            self.change_site(action["site_idx"], action["end_ads"])
+        else:  # Exchange.forward (events/event.py:138-155)
+            self.change_site(action["site1_idx"], action["site2_ads"])
+            self.change_site(action["site2_idx"], action["site1_ads"])
+
+    def arrays(self):
+        return np.array(self.positions, dtype=np.float64).reshape(-1, 3), np.array(self.numbers, dtype=np.int64)
+
+
+def create_anneal_schedule(start_temp=1.0, total_sweeps=1000, alpha=0.99):
+    """mcmc/utils/sampling.py:10-71 (single-anneal branch)."""
+    temps = [start_temp]
+    t = start_temp
+    while len(temps) < total_sweeps:
+        t *= alpha
+        temps.append(t)
+    return temps[:total_sweeps]
+
+
+def make_site_grid(positions, cell, n_sites, height=1.5):
+    """Deterministic synthetic virtual-site grid (pymatgen's AdsorbateSiteFinder is unavailable:
+    SURVEY.md 8d): nx x ny fractional grid at z_top + height, truncated to n_sites."""
+    cell = np.asarray(cell, dtype=float)
+    ratio = np.linalg.norm(cell[0]) / np.linalg.norm(cell[1])
+    nx = max(1, int(round(math.sqrt(n_sites * ratio))))
+    ny = int(math.ceil(n_sites / nx))
+    z = float(np.asarray(positions)[:, 2].max()) + height
+    pts = []
+    for a in range(nx):
+        for b in range(ny):
+            f = np.array([(a + 0.25) / nx, (b + 0.25) / ny, 0.0])
+            p = f @ cell
+            p[2] = z
+            pts.append(p)
+    return np.array(pts[:n_sites])
+
+
+class MultiChainMC:
+    """C independent chains in lock step over one batched engine.
+
+    ``relax_fn(pos_list, num_list, fixed_list) -> out[C,8]`` is the hot-path call (engine relax);
+    ``surface_energy_fn(energy, symbols) -> float`` is the host scalar (H6/H7)."""
+
+    def __init__(self, numbers0, positions0, fixed0, ads_coords, adsorbates, relax_fn, surface_energy_fn, seeds,
+                 canonical=False, num_ads_atoms=0, occ0=None):
+        self.adsorbates = list(adsorbates)
+        self.relax_fn, self.surface_energy_fn = relax_fn, surface_energy_fn
+        self.fixed0 = np.asarray(fixed0, dtype=bool)
+        self.chains = [ChainState(numbers0, positions0, ads_coords, occ=occ0, seed=s) for s in seeds]
+        self.canonical, self.num_ads_atoms = canonical, num_ads_atoms
+        if canonical:
+            assert num_ads_atoms > 0, "for canonical runs, need number of adsorbed atoms greater than 0"
+        self.temp = 1.0
+        self.n_relaxed = 0
+        self.decisions = [[] for _ in seeds]        # per chain: (accept, curr, prev, u)
+
+    # -- hot path call ------------------------------------------------------------------------
+    def _energies(self, chains):
+        pos, num, fix = [], [], []
+        for c in chains:
+            p, z = c.arrays()
+            pos.append(p)
+            num.append(z)
+            fix.append(np.concatenate([self.fixed0, np.zeros(len(z) - len(self.fixed0), dtype=bool)]))
+        out = self.relax_fn(pos, num, fix)
+        self.n_relaxed += len(chains)
+        # the OOB clamp of optimize_slab is invisible to Metropolis (system.py:466-469): raw energy is used
+        return [self.surface_energy_fn(float(out[k, 2]), [SYMBOLS[int(q)] for q in num[k]]) for k in range(len(chains))]
+
+    def _ensure_prev(self, chains):
+        missing = [c for c in chains if "surface_energy" not in c.results]
+        if missing:
+            for c, e in zip(missing, self._energies(missing)):
+                c.results["surface_energy"] = e
+
+    def step(self, active=None, force_semigrand=None):
+        """One MC iteration for the chains in `active` (default all). Returns accept flags."""
+        idx = list(range(len(self.chains))) if active is None else list(active)
+        chains = [self.chains[i] for i in idx]
+        snaps, actions = [], []
+        for k, c in enumerate(chains):
+            semigrand = (not self.canonical) or (force_semigrand is not None and force_semigrand[k])
+            action = c.propose_change(self.adsorbates) if semigrand else c.propose_switch()
+            snaps.append(c.snapshot())
+            actions.append(action)
+        # criterion: prev from the "before" state (recomputed when missing), curr from "after"
+        self._ensure_prev(chains)
+        prev = [c.results["surface_energy"] for c in chains]
+        for c, a in zip(chains, actions):
+            c.apply(a)
+        curr = self._energies(chains)
+        accepts = []
+        for k, c in enumerate(chains):
+            diff = float(curr[k] - prev[k])
+            with np.errstate(over="ignore"):
+                base_prob = np.exp(-diff / self.temp)
+            u = c.np_rng.rand()
+            acc = bool(u < base_prob)
+            if acc:
+                c.results["surface_energy"] = curr[k]
+            else:
+                snap = snaps[k]
+                res = dict(snap[4])
+                res["surface_energy"] = prev[k]
+                c.restore((snap[0], snap[1], snap[2], snap[3], res))
+            self.decisions[idx[k]].append((acc, curr[k], prev[k], u))
+            accepts.append(acc)
+        return accepts
+
+    def prepare_canonical(self):
+        """MCMC.prepare_canonical (mcmc.py:150-188): semigrand steps until num_ads_atoms adsorbed."""
+        while True:
+            todo = [i for i, c in enumerate(self.chains) if c.num_adsorbates < self.num_ads_atoms]
+            if not todo:
+                return
+            self.step(active=todo, force_semigrand=[True] * len(todo))
+
+    def run(self, total_sweeps=10, sweep_size=20, start_temp=1.0, perform_annealing=True, alpha=0.99,
+            anneal_schedule=None, gather=None):
+        """MCMC.run (mcmc.py:301-390) for every chain; returns per-chain histories
+        (energy_hist, frac_accept_hist, adsorption_count_hist) as [C, total_sweeps] arrays."""
+        self.temp = start_temp
+        if self.canonical:
+            self.prepare_canonical()
+        if anneal_schedule is not None:
+            temps = list(anneal_schedule)
+        elif perform_annealing:
+            temps = create_anneal_schedule(start_temp, total_sweeps, alpha)
+        else:
+            temps = [start_temp] * total_sweeps
+        C = len(self.chains)
+        energy_hist = np.zeros((C, total_sweeps))
+        frac_accept = np.zeros((C, total_sweeps))
+        ads_count = np.zeros((C, total_sweeps), dtype=int)
+        for i in range(total_sweeps):
+            self.temp = temps[i]
+            n_acc = np.zeros(C)
+            for _ in range(sweep_size):
+                n_acc += np.array(self.step(), dtype=float)
+            self._ensure_prev(self.chains)
+            energy_hist[:, i] = [c.results["surface_energy"] for c in self.chains]
+            frac_accept[:, i] = n_acc / sweep_size
+            ads_count[:, i] = [c.num_adsorbates for c in self.chains]
+            if gather is not None:
+                gather(i, energy_hist[:, i], frac_accept[:, i], ads_count[:, i])
+        return {"energy_hist": energy_hist, "frac_accept_hist": frac_accept, "adsorption_count_hist": ads_count}

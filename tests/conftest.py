@@ -55,6 +55,6 @@ def with_adsorbates(s, rng, n_ads, species, height=1.5):
         new_p.append(pos[a] + np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), height]))
         new_z.append(rng.choice(species))
     out = dict(s)
-    out["positions"] = np.concatenate([pos, np.array(new_p)])
+    out["positions"] = np.concatenate([pos, np.array(new_p, dtype=float).reshape(-1, 3)])
     out["numbers"] = np.concatenate([num, np.array(new_z, dtype=num.dtype)])
     return out

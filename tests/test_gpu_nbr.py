@@ -62,4 +62,4 @@ def test_empty_and_single_atom_structures(structures):
     rp, col, sh = _gpu(structs, 5.0)
     rp0, col0, sh0 = _oracle_batch(structs, 5.0)
     assert np.array_equal(rp, rp0) and np.array_equal(col, col0) and np.array_equal(sh, sh0)
-    assert rp[2] - rp[1] == 6  # the lone atom sees its 6 nearest periodic images (4 A < 5 A < 4*sqrt(2) A)
+    assert rp[1] - rp[0] == 6  # the lone atom sees its 6 nearest periodic images (4 A < 5 A < 4*sqrt(2) A)

@@ -32,10 +32,14 @@ def _compare(eng, ens, structs):
     for k, s in enumerate(structs):
         o = ens.calculate(s["positions"], s["numbers"], s["cell"], PBC3)
         n = len(s["numbers"])
-        assert abs(e[k] - o["energy"][0]) <= E_TOL_PER_ATOM * n, (k, e[k], o["energy"][0])
-        assert abs(es[k] - o["energy_std"][0]) <= E_TOL_PER_ATOM * n
-        assert np.abs(f[k] - o["forces"]).max() <= F_TOL, (k, np.abs(f[k] - o["forces"]).max())
-        assert np.abs(fs[k] - o["forces_std"]).max() <= F_TOL
+        etol = E_TOL_PER_ATOM * n + 1e-6 * abs(o["energy"][0])
+        assert abs(e[k] - o["energy"][0]) <= etol, (k, e[k], o["energy"][0])
+        assert abs(es[k] - o["energy_std"][0]) <= etol
+        # 1e-4 eV/A absolute; fp32 cannot hold that on the >1e3 eV/A forces of overlapping trial
+        # placements, so allow 2 ulp-ish relative slack there
+        ftol = F_TOL + 2e-6 * np.abs(o["grads_per_model"]).max(0) / 1.0
+        assert (np.abs(f[k] - o["forces"]) <= ftol).all(), (k, np.abs(f[k] - o["forces"]).max())
+        assert (np.abs(fs[k] - o["forces_std"]) <= ftol).all()
     return e, f
 
 
