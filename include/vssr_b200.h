@@ -79,7 +79,11 @@ size_t vssr_painn_workspace_bytes(int32_t n_models, int32_t n_atoms, int64_t e_c
 int vssr_painn_energy_grad(const float* weights, int32_t n_models,
                            const float* pos /*[A,3]*/, const int32_t* z /*[A]*/,
                            const int32_t* atom_ptr, const float* cell, int32_t n_struct,
-                           int32_t n_atoms, const int32_t* rowptr, const int32_t* col,
+                           int32_t n_atoms,
+                           int32_t max_atoms_per_struct /* host-known max of atom_ptr[b+1]-atom_ptr[b];
+                              selects the shared-memory staged message kernels (<= 90 atoms); 0 = unknown
+                              -> global-gather kernels */,
+                           const int32_t* rowptr, const int32_t* col,
                            const int8_t* shift, int64_t e_cap, float cutoff,
                            void* workspace, size_t workspace_bytes,
                            double* energy /*[M,B]*/, float* grad /*[M,A,3]*/,
@@ -124,7 +128,7 @@ size_t vssr_painn_relax_workspace_bytes(int32_t n_models, int32_t n_atoms, int64
 int vssr_painn_relax(const float* weights, int32_t n_models, double* pos /*[A,3] in/out*/,
                      const int32_t* z, const uint8_t* fixed, const int32_t* atom_ptr,
                      const float* cell, const uint8_t* pbc, const double* offset_ev,
-                     int32_t n_struct, int32_t n_atoms, float cutoff, float skin,
+                     int32_t n_struct, int32_t n_atoms, int32_t max_atoms_per_struct, float cutoff, float skin,
                      int32_t relax_steps, double fmax, int64_t e_cap, void* workspace,
                      size_t workspace_bytes, double* out /*[B,8]*/, float* forces /*[A,3]*/,
                      float* forces_std /*[A,3] or NULL*/, int32_t* status, void* stream);

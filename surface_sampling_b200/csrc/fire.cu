@@ -303,7 +303,8 @@ extern "C" size_t vssr_painn_relax_workspace_bytes(int32_t n_models, int32_t n_a
 
 extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* pos, const int32_t* z,
                                 const uint8_t* fixed, const int32_t* atom_ptr, const float* cell, const uint8_t* pbc,
-                                const double* offset_ev, int32_t n_struct, int32_t n_atoms, float cutoff, float skin,
+                                const double* offset_ev, int32_t n_struct, int32_t n_atoms,
+                                int32_t max_atoms_per_struct, float cutoff, float skin,
                                 int32_t relax_steps, double fmax, int64_t e_cap, void* workspace,
                                 size_t workspace_bytes, double* out, float* forces, float* forces_std,
                                 int32_t* status, void* stream) {
@@ -321,7 +322,8 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
     return rc;
   if ((rc = vssr_fire_init(w.state, w.vel, n_struct, n_atoms, stream))) return rc;
   for (int it = 0; it <= relax_steps; ++it) {
-    if ((rc = vssr_painn_energy_grad(weights, n_models, w.pos32, z, atom_ptr, cell, n_struct, n_atoms, w.rowptr,
+    if ((rc = vssr_painn_energy_grad(weights, n_models, w.pos32, z, atom_ptr, cell, n_struct, n_atoms,
+                                     max_atoms_per_struct, w.rowptr,
                                      w.col, w.shift, e_cap, cutoff, w.painn, w.painn_bytes, w.energy, w.grad, nullptr,
                                      stream)))
       return rc;

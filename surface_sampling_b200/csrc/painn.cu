@@ -103,11 +103,12 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     }
   };
 
-  float acc[8][TN];
+  // accumulators as adjacent-column pairs: packed fp32x2 FMAs (SASS FFMA2) double the FMA issue rate on sm_100
+  float2 acc[8][TN / 2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   load_tiles(0);
   store_tiles(0);
@@ -118,20 +119,23 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     if (kt + 1 < nk) load_tiles((kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float a[8], b[TN];
+      float a[8];
+      float2 b[TN / 2];
       const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
       const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
       a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
       const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      b[0] = make_float2(b0.x, b0.y); b[1] = make_float2(b0.z, b0.w);
       if (TN == 8) {
         const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][(BN / 2) + tx * 4]);
-        b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
+        b[TN / 2 - 2] = make_float2(b1.x, b1.y); b[TN / 2 - 1] = make_float2(b1.z, b1.w);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float2 aa = make_float2(a[i], a[i]);
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN / 2; ++j) acc[i][j] = __ffma2_rn(aa, b[j], acc[i][j]);
+      }
     }
     if (kt + 1 < nk) {
       store_tiles(buf ^ 1);
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
 #pragma unroll
     for (int h = 0; h < TN / 4; ++h) {
       const int c = n0 + (h == 0 ? tx * 4 : (BN / 2) + tx * 4);
-      float4 v = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+      float4 v = make_float4(acc[i][h * 2].x, acc[i][h * 2].y, acc[i][h * 2 + 1].x, acc[i][h * 2 + 1].y);
       if (EPI == 1) {
         const float4 bb = *reinterpret_cast<const float4*>(bias + c);
         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
@@ -174,17 +178,23 @@ int launch_gemm(const GemmArgs& g, int n_models, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // Edge geometry (shared by all models and layers) + excluded volume.
-// One warp per receiver atom; lanes over the row.  Record per edge:
-//   eg  float4 (ux,uy,uz,d)   d < 0  <=> edge outside the model cutoff for this evaluation
-//   re  [24]  = rbf_n*env (n=1..20), env, denv, 0, 0
-//   dre [20]  = d(rbf_n*env)/dd
+// One warp per receiver atom; lanes over the row in chunks of 32.  Edges inside the model cutoff
+// are COMPACTED to the front of the row (order preserved: ballot + popc), nvalid[i] of them:
+//   ej  [e]      sender (global atom index)
+//   eg  [e]      float4 (ux,uy,uz,d)
+//   re2 [e][44]  (rbf_n*env) duplicated as pairs (v,v) for n=1..20, then (env,env),(denv,denv)
+//   dre2[e][40]  d(rbf_n*env)/dd duplicated as pairs
+// The pair duplication feeds the packed FFMA2 path (sm_100 fma.rn.f32x2) without register moves.
 // grad0[a] = excluded-volume gradient (same for every model); evex[a] its energy.
 // ------------------------------------------------------------------------------------------
+constexpr int RE2 = 44, DRE2 = 40;
+
 __global__ void __launch_bounds__(128) edge_geometry_kernel(
     const float* __restrict__ pos, const int32_t* __restrict__ atom_ptr, const float* __restrict__ cell, int n_struct,
     int n_atoms, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-    const int8_t* __restrict__ shift, long long e_cap, float cutoff, float4* __restrict__ eg, float* __restrict__ re,
-    float* __restrict__ dre, float* __restrict__ evex, float* __restrict__ grad0) {
+    const int8_t* __restrict__ shift, long long e_cap, float cutoff, int32_t* __restrict__ nvalid,
+    int32_t* __restrict__ ej, float4* __restrict__ eg, float* __restrict__ re2, float* __restrict__ dre2,
+    float* __restrict__ evex, float* __restrict__ grad0) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n_atoms) return;
@@ -195,64 +205,77 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
   const float xi = __ldg(pos + 3 * i), yi = __ldg(pos + 3 * i + 1), zi = __ldg(pos + 3 * i + 2);
   long long e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
   if (e1 > e_cap) e1 = e_cap;
+  if (e0 > e_cap) e0 = e_cap;
   const float pi_over_rc = 3.14159265358979323846f / cutoff;
   float ev = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-  for (long long e = e0 + lane; e < e1; e += 32) {
-    const int j = __ldg(col + e);
-    const char4 s = reinterpret_cast<const char4*>(shift)[e];
-    const float f0 = (float)s.x, f1 = (float)s.y, f2 = (float)s.z;
-    // same fp32 offset arithmetic as the neighbour list
-    const float ox = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[0]), __fmul_rn(f1, c[3])), __fmul_rn(f2, c[6]));
-    const float oy = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[1]), __fmul_rn(f1, c[4])), __fmul_rn(f2, c[7]));
-    const float oz = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[2]), __fmul_rn(f1, c[5])), __fmul_rn(f2, c[8]));
-    const float rx = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j), xi), ox);
-    const float ry = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j + 1), yi), oy);
-    const float rz = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j + 2), zi), oz);
-    const float d2p = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
-    const float dp = sqrtf(d2p);
-    float* rrow = re + e * 24;
-    float* drow = dre + e * 20;
-    if (!(dp <= cutoff)) {
-      eg[e] = make_float4(0.f, 0.f, 0.f, -1.f);
-      continue;
+  int nv = 0;
+  for (long long base = e0; base < e1; base += 32) {
+    const long long e = base + lane;
+    bool valid = false;
+    int j = 0;
+    float rx = 0.f, ry = 0.f, rz = 0.f, dp = 0.f;
+    if (e < e1) {
+      j = __ldg(col + e);
+      const char4 s = reinterpret_cast<const char4*>(shift)[e];
+      const float f0 = (float)s.x, f1 = (float)s.y, f2 = (float)s.z;
+      // same fp32 offset arithmetic as the neighbour list
+      const float ox = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[0]), __fmul_rn(f1, c[3])), __fmul_rn(f2, c[6]));
+      const float oy = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[1]), __fmul_rn(f1, c[4])), __fmul_rn(f2, c[7]));
+      const float oz = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[2]), __fmul_rn(f1, c[5])), __fmul_rn(f2, c[8]));
+      rx = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j), xi), ox);
+      ry = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j + 1), yi), oy);
+      rz = __fadd_rn(__fsub_rn(__ldg(pos + 3 * j + 2), zi), oz);
+      const float d2p = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+      dp = sqrtf(d2p);
+      valid = dp <= cutoff;
     }
-    const float d = sqrtf((rx * rx + 1e-10f) + (ry * ry + 1e-10f) + (rz * rz + 1e-10f));
-    const float inv_d = 1.0f / d;
-    const float ux = rx * inv_d, uy = ry * inv_d, uz = rz * inv_d;
-    eg[e] = make_float4(ux, uy, uz, d);
-    float env = 0.f, denv = 0.f;
-    const bool inside = d < cutoff;
-    if (inside) {
-      float sn, cs;
-      sincosf(pi_over_rc * d, &sn, &cs);
-      env = 0.5f * (cs + 1.0f);
-      denv = -0.5f * pi_over_rc * sn;
-    }
-#pragma unroll
-    for (int n = 0; n < NRBF; ++n) {
-      float r = 0.f, dr = 0.f;
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const long long w = e0 + nv + __popc(mask & ((1u << lane) - 1u));
+      const float d = sqrtf((rx * rx + 1e-10f) + (ry * ry + 1e-10f) + (rz * rz + 1e-10f));
+      const float inv_d = 1.0f / d;
+      const float ux = rx * inv_d, uy = ry * inv_d, uz = rz * inv_d;
+      ej[w] = j;
+      eg[w] = make_float4(ux, uy, uz, d);
+      float env = 0.f, denv = 0.f;
+      const bool inside = d < cutoff;
       if (inside) {
-        const float coef = (float)(n + 1) * pi_over_rc;
         float sn, cs;
-        sincosf(coef * d, &sn, &cs);
-        r = sn * inv_d;
-        dr = (coef * cs - r) * inv_d;
+        sincosf(pi_over_rc * d, &sn, &cs);
+        env = 0.5f * (cs + 1.0f);
+        denv = -0.5f * pi_over_rc * sn;
       }
-      rrow[n] = r * env;
-      drow[n] = dr * env + r * denv;
+      float2* rrow = reinterpret_cast<float2*>(re2 + w * RE2);
+      float2* drow = reinterpret_cast<float2*>(dre2 + w * DRE2);
+#pragma unroll
+      for (int n = 0; n < NRBF; ++n) {
+        float r = 0.f, dr = 0.f;
+        if (inside) {
+          const float coef = (float)(n + 1) * pi_over_rc;
+          float sn, cs;
+          sincosf(coef * d, &sn, &cs);
+          r = sn * inv_d;
+          dr = (coef * cs - r) * inv_d;
+        }
+        const float a = r * env, bq = dr * env + r * denv;
+        rrow[n] = make_float2(a, a);
+        drow[n] = make_float2(bq, bq);
+      }
+      rrow[20] = make_float2(env, env);
+      rrow[21] = make_float2(denv, denv);
+      // excluded volume (sigma/d)^12 on the plain distance
+      const float q = 1.5f / dp;
+      const float q2 = q * q, q4 = q2 * q2;
+      const float vex = q4 * q4 * q4;
+      ev += vex;
+      const float gg = 24.0f * vex / dp;      // -2 * dvex/dd : edge A and its reverse B
+      gx += gg * ux; gy += gg * uy; gz += gg * uz;
     }
-    rrow[20] = env; rrow[21] = denv; rrow[22] = 0.f; rrow[23] = 0.f;
-    // excluded volume (sigma/d)^12 on the plain distance
-    const float q = 1.5f / dp;
-    const float q2 = q * q, q4 = q2 * q2;
-    const float vex = q4 * q4 * q4;
-    ev += vex;
-    const float dv = -12.0f * vex / dp;     // dvex/dd
-    const float gg = -2.0f * dv;            // edge A and its reverse B
-    gx += gg * ux; gy += gg * uy; gz += gg * uz;
+    nv += __popc(mask);
   }
   ev = warp_sum(ev); gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
   if (lane == 0) {
+    nvalid[i] = nv;
     evex[i] = ev;
     grad0[3 * i] = gx; grad0[3 * i + 1] = gy; grad0[3 * i + 2] = gz;
   }
@@ -279,9 +302,9 @@ constexpr int MSG_APB = 4;
 template <bool FIRST>
 __global__ void __launch_bounds__(128) message_fwd_kernel(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ col, long long e_cap, const float4* __restrict__ eg, const float* __restrict__ re,
-    const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
-    float* __restrict__ cat, float* __restrict__ v_mid) {
+    const int32_t* __restrict__ nvalid, const int32_t* __restrict__ ej, const float4* __restrict__ eg,
+    const float* __restrict__ re2, const float* __restrict__ phi, const float* __restrict__ s_in,
+    const float* __restrict__ v_in, float* __restrict__ cat, float* __restrict__ v_mid) {
   const int m = blockIdx.y, f = threadIdx.x;
   const float* __restrict__ wl = weights + (long long)m * W_TOTAL + W_LAYER0 + (long long)layer * L_SIZE;
   float wd0[NRBF], wd1[NRBF], wd2[NRBF];
@@ -298,13 +321,11 @@ __global__ void __launch_bounds__(128) message_fwd_kernel(
 
   const int i_end = min(n_atoms, (int)(blockIdx.x + 1) * MSG_APB);
   for (int i = blockIdx.x * MSG_APB; i < i_end; ++i) {
-    long long e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
-    if (e1 > e_cap) e1 = e_cap;
+    const long long e0 = __ldg(rowptr + i), e1 = e0 + __ldg(nvalid + i);
     float ds = 0.f, dvx = 0.f, dvy = 0.f, dvz = 0.f;
     for (long long e = e0; e < e1; ++e) {
       const float4 g = __ldg(eg + e);
-      if (g.w < 0.f) continue;
-      const int j = __ldg(col + e);
+      const int j = __ldg(ej + e);
       const float p0 = __ldg(phi + (long long)j * F3 + f);
       const float p1 = __ldg(phi + (long long)j * F3 + F + f);
       const float p2 = __ldg(phi + (long long)j * F3 + 2 * F + f);
@@ -314,14 +335,14 @@ __global__ void __launch_bounds__(128) message_fwd_kernel(
         vjy = __ldg(v_in + (long long)j * 3 * F + F + f);
         vjz = __ldg(v_in + (long long)j * 3 * F + 2 * F + f);
       }
-      const float4* r4 = reinterpret_cast<const float4*>(re + e * 24);
-      float rr[24];
+      const float4* r4 = reinterpret_cast<const float4*>(re2 + e * RE2);
+      float rr[NRBF];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const float4 t = __ldg(r4 + q);
-        rr[4 * q] = t.x; rr[4 * q + 1] = t.y; rr[4 * q + 2] = t.z; rr[4 * q + 3] = t.w;
+      for (int q = 0; q < NRBF / 2; ++q) {
+        const float4 t = __ldg(r4 + q);   // (r,r,r',r') duplicated pairs
+        rr[2 * q] = t.x; rr[2 * q + 1] = t.z;
       }
-      const float env = rr[20];
+      const float env = __ldg(r4 + 10).x;
       float w0 = bd0 * env, w1 = bd1 * env, w2 = bd2 * env;
 #pragma unroll
       for (int n = 0; n < NRBF; ++n) {
@@ -471,8 +492,9 @@ __global__ void nrm_bwd_kernel(const float* __restrict__ dcat, const float* __re
 template <bool FIRST>
 __global__ void __launch_bounds__(128) message_bwd_kernel(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ col, long long e_cap, const float4* __restrict__ eg, const float* __restrict__ re,
-    const float* __restrict__ dre, const float* __restrict__ phi, const float* __restrict__ v_in,
+    const int32_t* __restrict__ nvalid, const int32_t* __restrict__ ej, const float4* __restrict__ eg,
+    const float* __restrict__ re2, const float* __restrict__ dre2, const float* __restrict__ phi,
+    const float* __restrict__ v_in,
     const float* __restrict__ ds, const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in,
     float* __restrict__ grad) {
   __shared__ float red[4][3];
@@ -492,8 +514,7 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
 
   const int i_end = min(n_atoms, (int)(blockIdx.x + 1) * MSG_APB);
   for (int i = blockIdx.x * MSG_APB; i < i_end; ++i) {
-    long long e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
-    if (e1 > e_cap) e1 = e_cap;
+    const long long e0 = __ldg(rowptr + i), e1 = e0 + __ldg(nvalid + i);
     const float gsi = __ldg(ds + (long long)i * F + f);
     const float gvix = __ldg(dv + (long long)i * 3 * F + f);
     const float gviy = __ldg(dv + (long long)i * 3 * F + F + f);
@@ -512,8 +533,7 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
     float gx = 0.f, gy = 0.f, gz = 0.f;           // per-feature partial of dE/dx_i
     for (long long e = e0; e < e1; ++e) {
       const float4 g = __ldg(eg + e);
-      if (g.w < 0.f) continue;
-      const int j = __ldg(col + e);
+      const int j = __ldg(ej + e);
       const float pj0 = __ldg(phi + (long long)j * F3 + f);
       const float pj1 = __ldg(phi + (long long)j * F3 + F + f);
       const float pj2 = __ldg(phi + (long long)j * F3 + 2 * F + f);
@@ -527,20 +547,18 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
         vjy = __ldg(v_in + (long long)j * 3 * F + F + f);
         vjz = __ldg(v_in + (long long)j * 3 * F + 2 * F + f);
       }
-      const float4* r4 = reinterpret_cast<const float4*>(re + e * 24);
-      const float4* d4 = reinterpret_cast<const float4*>(dre + e * 20);
-      float rr[24], dr[20];
+      const float4* r4 = reinterpret_cast<const float4*>(re2 + e * RE2);
+      const float4* d4 = reinterpret_cast<const float4*>(dre2 + e * DRE2);
+      float rr[NRBF], dr[NRBF];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
+      for (int q = 0; q < NRBF / 2; ++q) {
         const float4 t = __ldg(r4 + q);
-        rr[4 * q] = t.x; rr[4 * q + 1] = t.y; rr[4 * q + 2] = t.z; rr[4 * q + 3] = t.w;
+        const float4 u = __ldg(d4 + q);
+        rr[2 * q] = t.x; rr[2 * q + 1] = t.z;
+        dr[2 * q] = u.x; dr[2 * q + 1] = u.z;
       }
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const float4 t = __ldg(d4 + q);
-        dr[4 * q] = t.x; dr[4 * q + 1] = t.y; dr[4 * q + 2] = t.z; dr[4 * q + 3] = t.w;
-      }
-      const float env = rr[20], denv = rr[21];
+      const float4 ev = __ldg(r4 + 10);
+      const float env = ev.x, denv = ev.z;
       float w0 = bd0 * env, w1 = bd1 * env, w2 = bd2 * env;
       float q0 = bd0 * denv, q1 = bd1 * denv, q2 = bd2 * denv;
 #pragma unroll
@@ -589,9 +607,11 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
   }
 }
 
+#include "painn_message.cuh"
+
 struct Workspace {
-  // edge records
-  float4* eg; float* re; float* dre; float* evex; float* grad0;
+  // edge records (compacted per row by edge_geometry_kernel)
+  int32_t* nvalid; int32_t* ej; float4* eg; float* re2; float* dre2; float* evex; float* grad0; float* gradp;
   // activations
   float* s[NCONV + 1];      // [M,A,128]
   float* v[NCONV + 1];      // [M,A,3,128]  (v[0] unused: zeros)
@@ -612,11 +632,14 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
     return p;
   };
   const size_t MA = (size_t)M * (size_t)A;
+  w.nvalid = reinterpret_cast<int32_t*>(take(A));
+  w.ej = reinterpret_cast<int32_t*>(take((size_t)e_cap));
   w.eg = reinterpret_cast<float4*>(take((size_t)e_cap * 4));
-  w.re = take((size_t)e_cap * 24);
-  w.dre = take((size_t)e_cap * 20);
+  w.re2 = take((size_t)e_cap * RE2);
+  w.dre2 = take((size_t)e_cap * DRE2);
   w.evex = take(A);
   w.grad0 = take((size_t)A * 3);
+  w.gradp = take(MA * 2 * 3);
   for (int l = 0; l <= NCONV; ++l) w.s[l] = take(MA * F);
   w.v[0] = nullptr;
   for (int l = 1; l <= NCONV; ++l) w.v[l] = take(MA * 3 * F);
@@ -642,9 +665,10 @@ extern "C" size_t vssr_painn_workspace_bytes(int32_t n_models, int32_t n_atoms, 
 
 extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, const float* pos, const int32_t* z,
                                       const int32_t* atom_ptr, const float* cell, int32_t n_struct, int32_t n_atoms,
-                                      const int32_t* rowptr, const int32_t* col, const int8_t* shift, int64_t e_cap,
-                                      float cutoff, void* workspace, size_t workspace_bytes, double* energy,
-                                      float* grad, float* embedding, void* stream) {
+                                      int32_t max_atoms_per_struct, const int32_t* rowptr, const int32_t* col,
+                                      const int8_t* shift, int64_t e_cap, float cutoff, void* workspace,
+                                      size_t workspace_bytes, double* energy, float* grad, float* embedding,
+                                      void* stream) {
   if (!weights || !pos || !z || !atom_ptr || !cell || !rowptr || !col || !shift || !workspace || !energy || !grad)
     return VSSR_ERR_ARG;
   if (n_models <= 0 || n_struct <= 0 || n_atoms <= 0) return VSSR_ERR_ARG;
@@ -656,8 +680,24 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const dim3 ew_grid(ceil_div((long long)A * F, 256), M);
   const dim3 msg_grid(ceil_div(A, MSG_APB), M);
 
-  VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(pos, atom_ptr, cell, n_struct, A, rowptr, col, shift,
-                                                       (long long)e_cap, cutoff, w.eg, w.re, w.dre, w.evex, w.grad0));
+  // message kernels: shared-memory staged FFMA2 path when every structure fits, else global-gather path
+  const int nmax = max_atoms_per_struct;
+  const size_t smem_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4, smem_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4;
+  const size_t smem_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4, smem_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4;
+  const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
+  const int n_chunks = 2;
+  const dim3 v2_grid(n_struct * n_chunks, F / MSG_FC, M);
+  if (staged) {
+    static size_t cfg[4] = {0, 0, 0, 0};
+    if (smem_fwd0 > cfg[0]) { VSSR_CUDA(cudaFuncSetAttribute(message_fwd_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd0)); cfg[0] = smem_fwd0; }
+    if (smem_fwd > cfg[1]) { VSSR_CUDA(cudaFuncSetAttribute(message_fwd_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd)); cfg[1] = smem_fwd; }
+    if (smem_bwd0 > cfg[2]) { VSSR_CUDA(cudaFuncSetAttribute(message_bwd_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd0)); cfg[2] = smem_bwd0; }
+    if (smem_bwd > cfg[3]) { VSSR_CUDA(cudaFuncSetAttribute(message_bwd_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd)); cfg[3] = smem_bwd; }
+  }
+
+  VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(
+      pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, w.nvalid, w.ej, w.eg, w.re2,
+      w.dre2, w.evex, w.grad0));
   VSSR_PROF(VSSR_K_ELEMWISE, st, embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]));
 
   int rc;
@@ -673,12 +713,23 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
                  w.phi[l], F3, (long long)A * F3, A, F3, F};
     if ((rc = launch_gemm<128, 1, 1>(g, M, st))) return rc;
     // F3
-    if (l == 0)
-      message_fwd_kernel<true><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
-                                                         w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]);
-    else
-      VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<false><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
-                                                          w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
+    if (staged) {
+      if (l == 0)
+        VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.phi[l], w.s[l], nullptr,
+            w.cat[l], w.vmid[l]));
+      else
+        VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.phi[l], w.s[l], w.v[l],
+            w.cat[l], w.vmid[l]));
+    } else {
+      if (l == 0)
+        VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<true><<<msg_grid, 128, 0, st>>>(
+            weights, l, A, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
+      else
+        VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<false><<<msg_grid, 128, 0, st>>>(
+            weights, l, A, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
+    }
     // F4
     g = GemmArgs{w.vmid[l], F, (long long)A * 3 * F, wl + L_UVT, 2 * F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  w.UV[l], 2 * F, (long long)A * 6 * F, 3 * A, 2 * F, F};
@@ -694,7 +745,8 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
                  w.a[l], F3, (long long)A * F3, A, F3, F};
     if ((rc = launch_gemm<128, 1, 1>(g, M, st))) return rc;
     // F8
-    VSSR_PROF(VSSR_K_ELEMWISE, st, update_fwd_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], w.a[l], w.cat[l], w.vmid[l], A, w.s[l + 1], w.v[l + 1]));
+    VSSR_PROF(VSSR_K_ELEMWISE, st, update_fwd_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], w.a[l], w.cat[l], w.vmid[l], A,
+                                                                           w.s[l + 1], w.v[l + 1]));
   }
   // readout
   {
@@ -739,12 +791,27 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
                  dv_cur, F, (long long)A * 3 * F, 3 * A, F, 2 * F};
     if ((rc = launch_gemm<128, 0, 3>(g, M, st))) return rc;
     // B3
-    if (l == 0) {
-      VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<true><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
-                                                         w.dre, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, grad));
+    if (staged) {
+      if (l == 0)
+        VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.dre2, w.phi[l], nullptr, w.ds,
+            dv_cur, nullptr, nullptr, w.gradp));
+      else
+        VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.dre2, w.phi[l], w.v[l], w.ds,
+            dv_cur, w.dphi, dv_nxt, w.gradp));
+      VSSR_PROF(VSSR_K_ELEMWISE, st, grad_accum_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.gradp, 3 * A, grad));
     } else {
-      VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<false><<<msg_grid, 128, 0, st>>>(weights, l, A, rowptr, col, (long long)e_cap, w.eg, w.re,
-                                                          w.dre, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, grad));
+      if (l == 0)
+        VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<true><<<msg_grid, 128, 0, st>>>(
+            weights, l, A, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.dre2, w.phi[l], nullptr, w.ds, dv_cur, nullptr,
+            nullptr, grad));
+      else
+        VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<false><<<msg_grid, 128, 0, st>>>(
+            weights, l, A, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.dre2, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt,
+            grad));
+    }
+    if (l > 0) {
       // B2: dh1 = (dphi . W2) * dswish(h1)
       g = GemmArgs{w.dphi, F3, (long long)A * F3, wl + L_W2, F, W_TOTAL, nullptr, 0, w.h1[l], F, MA_F, nullptr, 0,
                    w.dh1, F, MA_F, A, F, F3};

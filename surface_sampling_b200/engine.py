@@ -22,7 +22,10 @@ KCAL_PER_EV = 23.06052
 HARTREE_TO_KCAL_MOL = 627.509
 HARTREE_TO_EV = HARTREE_TO_KCAL_MOL / KCAL_PER_EV
 
-SYMBOLS = {1: "H", 7: "N", 8: "O", 14: "Si", 22: "Ti", 25: "Mn", 29: "Cu", 31: "Ga", 38: "Sr", 57: "La", 79: "Au"}
+_PERIODIC = ("H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr "
+             "Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu "
+             "Hf Ta W Re Os Ir Pt Au Hg Tl Pb Bi Po At Rn").split()
+SYMBOLS = {k + 1: s for k, s in enumerate(_PERIODIC)}
 NUMBERS = {v: k for k, v in SYMBOLS.items()}
 
 F, F3, NRBF, NCONV, NEMB, FH = 128, 384, 20, 3, 100, 64
@@ -106,6 +109,10 @@ class Batch:
     @property
     def cell32(self):
         return self.cell.to(torch.float32)
+
+    @property
+    def max_atoms(self) -> int:
+        return int(np.diff(self.atom_ptr_host).max()) if self.n_struct else 0
 
     @staticmethod
     def from_arrays(pos_list, z_list, cell_list, pbc_list, fixed_list=None, device="cuda", pinned=True):
@@ -235,7 +242,7 @@ class PainnEngine:
         grad = torch.empty((M, A, 3), dtype=torch.float32, device=dev)
         emb = torch.empty((M, A, F), dtype=torch.float32, device=dev) if want_embedding else None
         _lib.check(lib.vssr_painn_energy_grad(_ptr(self.weights), M, _ptr(pos32), _ptr(batch.z), _ptr(batch.atom_ptr),
-                                              _ptr(cell32), B, A, _ptr(rowptr), _ptr(col), _ptr(shift), e_cap,
+                                              _ptr(cell32), B, A, batch.max_atoms, _ptr(rowptr), _ptr(col), _ptr(shift), e_cap,
                                               self.cutoff, _ptr(ws), ws.numel(), _ptr(energy), _ptr(grad), _ptr(emb),
                                               _stream()), "vssr_painn_energy_grad")
         off = None
@@ -272,7 +279,7 @@ class PainnEngine:
         cell32 = batch.cell32.contiguous()
         _lib.check(lib.vssr_painn_relax(_ptr(self.weights), M, _ptr(batch.pos), _ptr(batch.z), _ptr(batch.fixed),
                                         _ptr(batch.atom_ptr), _ptr(cell32), _ptr(batch.pbc), _ptr(off), B, A,
-                                        self.cutoff, self.skin, int(relax_steps), float(fmax), cap, _ptr(ws),
+                                        batch.max_atoms, self.cutoff, self.skin, int(relax_steps), float(fmax), cap, _ptr(ws),
                                         ws.numel(), _ptr(out), _ptr(forces), _ptr(fstd), _ptr(status), _stream()),
                    "vssr_painn_relax")
         return {"out": out, "forces": forces, "forces_std": fstd, "status": status}

@@ -45,11 +45,11 @@ def hill_formula(symbols) -> str:
 class ChainState:
     """SurfaceSystem state restricted to what the MC loop mutates."""
 
-    def __init__(self, numbers0, positions0, ads_coords, occ=None, seed=0):
+    def __init__(self, numbers0, positions0, ads_coords, occ=None, seed=0, ads_group0=None):
         self.n0 = len(numbers0)
         self.numbers = list(int(z) for z in numbers0)          # real_atoms numbers
         self.positions = [np.asarray(p, dtype=float) for p in positions0]
-        self.ads_group = [0] * self.n0
+        self.ads_group = [0] * self.n0 if ads_group0 is None else [int(g) for g in ads_group0]
         self.ads_coords = np.asarray(ads_coords, dtype=float)
         self.occ = np.zeros(len(self.ads_coords), dtype=int) if occ is None else np.array(occ, dtype=int)
         self.results = {}

@@ -1,0 +1,77 @@
+"""Multi-chain driver vs the single-chain oracle loop under the same per-chain seeds: identical
+accept/reject sequences and occupancies (synthetic energy function, CPU only).  Also the
+world_size-2 gloo path of the per-sweep statistics gather."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import mc as omc
+from surface_sampling_b200 import mc
+from surface_sampling_b200.engine import NUMBERS, SYMBOLS
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def toy_energy(symbols, pos):
+    """Deterministic, permutation-dependent-free toy 'relaxed surface energy'."""
+    z = np.array([NUMBERS[s] for s in symbols], float)
+    d = np.linalg.norm(pos[:, None, :] - pos[None, :, :], axis=-1) + np.eye(len(pos))
+    return float(np.sum(np.triu(np.sqrt(z[:, None] * z[None, :]) * np.exp(-d) * np.cos(1.3 * d), 1)) - 0.05 * len(z))
+
+
+def _driver(seeds, canonical=False, num_ads=0):
+    numbers0 = [NUMBERS[s] for s in ["Sr", "Ti", "O", "O"]]
+    pos0 = np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0], [2, 2, 0.5]], float)
+    sites = np.array([[x, y, 1.5] for x in (0.0, 1.0, 2.0) for y in (0.0, 1.0, 2.0)])
+
+    def relax_fn(pos_l, num_l, fix_l):
+        out = np.zeros((len(pos_l), 8))
+        for k, (p, z) in enumerate(zip(pos_l, num_l)):
+            out[k, 2] = out[k, 0] = toy_energy([SYMBOLS[int(q)] for q in z], p)
+        return out
+
+    drv = mc.MultiChainMC(numbers0, pos0, np.ones(4, bool), sites, ["Sr", "O"], relax_fn, lambda e, sym: e, seeds,
+                          canonical=canonical, num_ads_atoms=num_ads)
+    return drv, (["Sr", "Ti", "O", "O"], pos0, sites)
+
+
+@pytest.mark.parametrize("canonical", [False, True])
+def test_decisions_match_single_chain_oracle(canonical):
+    seeds = [0, 1, 7, 11, 12345]
+    drv, (sym0, pos0, sites) = _driver(seeds, canonical, 3 if canonical else 0)
+    res = drv.run(total_sweeps=3, sweep_size=8, start_temp=0.5, perform_annealing=True, alpha=0.9)
+    for k, s in enumerate(seeds):
+        o = omc.run_chain(s, sym0, pos0, sites, ["Sr", "O"], toy_energy, 3, 8, start_temp=0.5, alpha=0.9,
+                          canonical=canonical, num_ads_atoms=3 if canonical else 0)
+        assert [d[0] for d in drv.decisions[k]] == [d[0] for d in o["decisions"]]
+        assert [d[3] for d in drv.decisions[k]] == [d[3] for d in o["decisions"]]       # same uniforms
+        assert np.allclose([d[1] for d in drv.decisions[k]], [d[1] for d in o["decisions"]], rtol=0, atol=0)
+        assert list(drv.chains[k].occ) == o["final"].occ
+        assert np.array_equal(res["energy_hist"][k], o["energy_hist"])
+        assert np.array_equal(res["frac_accept_hist"][k], o["frac_accept_hist"])
+        assert np.array_equal(res["adsorption_count_hist"][k], o["ads_hist"])
+
+
+def test_overflowing_boltzmann_factor_accepts():
+    drv, _ = _driver([3])
+    drv.temp = 1e-320   # exp(+huge) -> inf -> accept (criterion.py:162-165 never catches numpy overflow)
+    c = drv.chains[0]
+    c.results["surface_energy"] = 1e6
+    assert drv.step() == [True]
+
+
+@pytest.mark.timeout(120)
+def test_sharded_statistics_gather_gloo_world2(tmp_path):
+    """Chains shard across ranks with no data-path collective; only per-sweep scalars are gathered."""
+    script = ROOT / "tests" / "_gloo_worker.py"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", PYTHONPATH=str(ROOT))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", str(tmp_path)], env=env) for r in range(2)]
+    assert all(p.wait(timeout=100) == 0 for p in procs)
+    got = np.load(tmp_path / "gathered.npy")
+    drv, _ = _driver(list(range(6)))
+    ref = drv.run(total_sweeps=2, sweep_size=4, start_temp=0.5, perform_annealing=False)
+    assert np.array_equal(got[0], ref["energy_hist"]) and np.array_equal(got[2], ref["adsorption_count_hist"])
