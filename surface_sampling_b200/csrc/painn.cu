@@ -180,21 +180,21 @@ int launch_gemm(const GemmArgs& g, int n_models, cudaStream_t st) {
 // Edge geometry (shared by all models and layers) + excluded volume.
 // One warp per receiver atom; lanes over the row in chunks of 32.  Edges inside the model cutoff
 // are COMPACTED to the front of the row (order preserved: ballot + popc), nvalid[i] of them:
-//   ej  [e]      sender (global atom index)
-//   eg  [e]      float4 (ux,uy,uz,d)
-//   re2 [e][44]  (rbf_n*env) duplicated as pairs (v,v) for n=1..20, then (env,env),(denv,denv)
-//   dre2[e][40]  d(rbf_n*env)/dd duplicated as pairs
+// one 384-byte record per edge, erec[e][96 floats]:
+//   [0..3]   (ux,uy,uz,d)        [4] sender (global atom index, int bits)   [5..7] pad
+//   [8..51]  (rbf_n*env) duplicated as pairs (v,v) for n=1..20, then (env,env),(denv,denv)
+//   [52..91] d(rbf_n*env)/dd duplicated as pairs                              [92..95] pad
+// (a record is what one warp prefetches with a single cp.async per lane)
 // The pair duplication feeds the packed FFMA2 path (sm_100 fma.rn.f32x2) without register moves.
 // grad0[a] = excluded-volume gradient (same for every model); evex[a] its energy.
 // ------------------------------------------------------------------------------------------
-constexpr int RE2 = 44, DRE2 = 40;
+constexpr int REC = 96, REC_EJ = 4, REC_RE = 8, REC_DRE = 52;
 
 __global__ void __launch_bounds__(128) edge_geometry_kernel(
     const float* __restrict__ pos, const int32_t* __restrict__ atom_ptr, const float* __restrict__ cell, int n_struct,
     int n_atoms, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const int8_t* __restrict__ shift, long long e_cap, float cutoff, int32_t* __restrict__ nvalid,
-    int32_t* __restrict__ ej, float4* __restrict__ eg, float* __restrict__ re2, float* __restrict__ dre2,
-    float* __restrict__ evex, float* __restrict__ grad0) {
+    float* __restrict__ erec, float* __restrict__ evex, float* __restrict__ grad0) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n_atoms) return;
@@ -235,8 +235,9 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
       const float d = sqrtf((rx * rx + 1e-10f) + (ry * ry + 1e-10f) + (rz * rz + 1e-10f));
       const float inv_d = 1.0f / d;
       const float ux = rx * inv_d, uy = ry * inv_d, uz = rz * inv_d;
-      ej[w] = j;
-      eg[w] = make_float4(ux, uy, uz, d);
+      float* rec = erec + w * REC;
+      *reinterpret_cast<float4*>(rec) = make_float4(ux, uy, uz, d);
+      *reinterpret_cast<float4*>(rec + 4) = make_float4(__int_as_float(j), 0.f, 0.f, 0.f);
       float env = 0.f, denv = 0.f;
       const bool inside = d < cutoff;
       if (inside) {
@@ -245,8 +246,8 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
         env = 0.5f * (cs + 1.0f);
         denv = -0.5f * pi_over_rc * sn;
       }
-      float2* rrow = reinterpret_cast<float2*>(re2 + w * RE2);
-      float2* drow = reinterpret_cast<float2*>(dre2 + w * DRE2);
+      float2* rrow = reinterpret_cast<float2*>(rec + REC_RE);
+      float2* drow = reinterpret_cast<float2*>(rec + REC_DRE);
 #pragma unroll
       for (int n = 0; n < NRBF; ++n) {
         float r = 0.f, dr = 0.f;
@@ -302,9 +303,9 @@ constexpr int MSG_APB = 4;
 template <bool FIRST>
 __global__ void __launch_bounds__(128) message_fwd_kernel(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ nvalid, const int32_t* __restrict__ ej, const float4* __restrict__ eg,
-    const float* __restrict__ re2, const float* __restrict__ phi, const float* __restrict__ s_in,
-    const float* __restrict__ v_in, float* __restrict__ cat, float* __restrict__ v_mid) {
+    const int32_t* __restrict__ nvalid, const float* __restrict__ erec, const float* __restrict__ phi,
+    const float* __restrict__ s_in, const float* __restrict__ v_in, float* __restrict__ cat,
+    float* __restrict__ v_mid) {
   const int m = blockIdx.y, f = threadIdx.x;
   const float* __restrict__ wl = weights + (long long)m * W_TOTAL + W_LAYER0 + (long long)layer * L_SIZE;
   float wd0[NRBF], wd1[NRBF], wd2[NRBF];
@@ -324,8 +325,9 @@ __global__ void __launch_bounds__(128) message_fwd_kernel(
     const long long e0 = __ldg(rowptr + i), e1 = e0 + __ldg(nvalid + i);
     float ds = 0.f, dvx = 0.f, dvy = 0.f, dvz = 0.f;
     for (long long e = e0; e < e1; ++e) {
-      const float4 g = __ldg(eg + e);
-      const int j = __ldg(ej + e);
+      const float* rec = erec + e * REC;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(rec));
+      const int j = __float_as_int(__ldg(rec + REC_EJ));
       const float p0 = __ldg(phi + (long long)j * F3 + f);
       const float p1 = __ldg(phi + (long long)j * F3 + F + f);
       const float p2 = __ldg(phi + (long long)j * F3 + 2 * F + f);
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(128) message_fwd_kernel(
         vjy = __ldg(v_in + (long long)j * 3 * F + F + f);
         vjz = __ldg(v_in + (long long)j * 3 * F + 2 * F + f);
       }
-      const float4* r4 = reinterpret_cast<const float4*>(re2 + e * RE2);
+      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
       float rr[NRBF];
 #pragma unroll
       for (int q = 0; q < NRBF / 2; ++q) {
@@ -492,8 +494,7 @@ __global__ void nrm_bwd_kernel(const float* __restrict__ dcat, const float* __re
 template <bool FIRST>
 __global__ void __launch_bounds__(128) message_bwd_kernel(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ nvalid, const int32_t* __restrict__ ej, const float4* __restrict__ eg,
-    const float* __restrict__ re2, const float* __restrict__ dre2, const float* __restrict__ phi,
+    const int32_t* __restrict__ nvalid, const float* __restrict__ erec, const float* __restrict__ phi,
     const float* __restrict__ v_in,
     const float* __restrict__ ds, const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in,
     float* __restrict__ grad) {
@@ -532,8 +533,9 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
     float dvx = 0.f, dvy = 0.f, dvz = 0.f;        // sender-side dv_in
     float gx = 0.f, gy = 0.f, gz = 0.f;           // per-feature partial of dE/dx_i
     for (long long e = e0; e < e1; ++e) {
-      const float4 g = __ldg(eg + e);
-      const int j = __ldg(ej + e);
+      const float* rec = erec + e * REC;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(rec));
+      const int j = __float_as_int(__ldg(rec + REC_EJ));
       const float pj0 = __ldg(phi + (long long)j * F3 + f);
       const float pj1 = __ldg(phi + (long long)j * F3 + F + f);
       const float pj2 = __ldg(phi + (long long)j * F3 + 2 * F + f);
@@ -547,8 +549,8 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
         vjy = __ldg(v_in + (long long)j * 3 * F + F + f);
         vjz = __ldg(v_in + (long long)j * 3 * F + 2 * F + f);
       }
-      const float4* r4 = reinterpret_cast<const float4*>(re2 + e * RE2);
-      const float4* d4 = reinterpret_cast<const float4*>(dre2 + e * DRE2);
+      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
+      const float4* d4 = reinterpret_cast<const float4*>(rec + REC_DRE);
       float rr[NRBF], dr[NRBF];
 #pragma unroll
       for (int q = 0; q < NRBF / 2; ++q) {
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
 
 struct Workspace {
   // edge records (compacted per row by edge_geometry_kernel)
-  int32_t* nvalid; int32_t* ej; float4* eg; float* re2; float* dre2; float* evex; float* grad0; float* gradp;
+  int32_t* nvalid; float* erec; float* evex; float* grad0; float* gradp;
   // activations
   float* s[NCONV + 1];      // [M,A,128]
   float* v[NCONV + 1];      // [M,A,3,128]  (v[0] unused: zeros)
@@ -633,10 +635,7 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
   };
   const size_t MA = (size_t)M * (size_t)A;
   w.nvalid = reinterpret_cast<int32_t*>(take(A));
-  w.ej = reinterpret_cast<int32_t*>(take((size_t)e_cap));
-  w.eg = reinterpret_cast<float4*>(take((size_t)e_cap * 4));
-  w.re2 = take((size_t)e_cap * RE2);
-  w.dre2 = take((size_t)e_cap * DRE2);
+  w.erec = take((size_t)e_cap * REC);
   w.evex = take(A);
   w.grad0 = take((size_t)A * 3);
   w.gradp = take(MA * 2 * 3);
@@ -682,8 +681,8 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
 
   // message kernels: shared-memory staged FFMA2 path when every structure fits, else global-gather path
   const int nmax = max_atoms_per_struct;
-  const size_t smem_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4, smem_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4;
-  const size_t smem_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4, smem_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4;
+  const size_t smem_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4 + MSG_PIPE_BYTES, smem_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4 + MSG_PIPE_BYTES;
+  const size_t smem_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4 + MSG_PIPE_BYTES, smem_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4 + MSG_PIPE_BYTES;
   const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
   const int n_chunks = 2;
   const dim3 v2_grid(n_struct * n_chunks, F / MSG_FC, M);
@@ -696,8 +695,8 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   }
 
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(
-      pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, w.nvalid, w.ej, w.eg, w.re2,
-      w.dre2, w.evex, w.grad0));
+      pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, w.nvalid, w.erec, w.evex,
+      w.grad0));
   VSSR_PROF(VSSR_K_ELEMWISE, st, embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]));
 
   int rc;
@@ -716,19 +715,19 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if (staged) {
       if (l == 0)
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.phi[l], w.s[l], nullptr,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
             w.cat[l], w.vmid[l]));
       else
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.phi[l], w.s[l], w.v[l],
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
             w.cat[l], w.vmid[l]));
     } else {
       if (l == 0)
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<true><<<msg_grid, 128, 0, st>>>(
-            weights, l, A, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
+            weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
       else
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<false><<<msg_grid, 128, 0, st>>>(
-            weights, l, A, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
+            weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
     }
     // F4
     g = GemmArgs{w.vmid[l], F, (long long)A * 3 * F, wl + L_UVT, 2 * F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
@@ -794,21 +793,21 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if (staged) {
       if (l == 0)
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.dre2, w.phi[l], nullptr, w.ds,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
             dv_cur, nullptr, nullptr, w.gradp));
       else
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.dre2, w.phi[l], w.v[l], w.ds,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
             dv_cur, w.dphi, dv_nxt, w.gradp));
       VSSR_PROF(VSSR_K_ELEMWISE, st, grad_accum_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.gradp, 3 * A, grad));
     } else {
       if (l == 0)
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<true><<<msg_grid, 128, 0, st>>>(
-            weights, l, A, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.dre2, w.phi[l], nullptr, w.ds, dv_cur, nullptr,
+            weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], nullptr, w.ds, dv_cur, nullptr,
             nullptr, grad));
       else
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<false><<<msg_grid, 128, 0, st>>>(
-            weights, l, A, rowptr, w.nvalid, w.ej, w.eg, w.re2, w.dre2, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt,
+            weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt,
             grad));
     }
     if (l > 0) {

@@ -7,14 +7,18 @@
 // one receiver atom at a time and lane l owns the adjacent feature pair (2l, 2l+1) of the chunk.
 // All arithmetic on the pair is issued as packed fp32x2 instructions (fma.rn.f32x2 -> SASS FFMA2),
 // which on B200 sustain 66 TFLOP/s vs 42 for scalar FFMA (profiles/microbench/ffma2.cu).  The
-// radial filter w(d) = Wd.(rbf*env) + bd*env lives in 60 register pairs per lane; the per-edge
-// rbf records arrive pre-duplicated as (v,v) pairs so no register moves are needed.
+// radial filter w(d) = Wd.(rbf*env) + bd*env lives in 60 register pairs per lane.
+// Per-edge records (384 B: unit vector, sender, rbf rows pre-duplicated as (v,v) pairs) stream
+// through a private 3-stage cp.async ring per warp, so the L2 latency of the next edges hides
+// behind the current edge's ~60-120 FFMA2.
 // Determinism: a lane walks its receiver's CSR row serially; there are no atomics.
 #pragma once
 
 constexpr int MSG_FC = 64;        // features per CTA
 constexpr int MSG_THREADS = 256;  // 8 warps
 constexpr int MSG_WARPS = MSG_THREADS / 32;
+constexpr int MSG_STAGES = 3;     // cp.async ring depth per warp
+constexpr int MSG_PIPE_BYTES = MSG_WARPS * MSG_STAGES * REC * 4;
 
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
@@ -37,16 +41,32 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ dst_atom0, int pe
   }
 }
 
+// one 16-byte cp.async per lane for the first n16*16 bytes of a record, then commit (always commits,
+// so group accounting stays uniform even past the end of the row)
+__device__ __forceinline__ void prefetch_record(float* dst, const float* src, int lane, int n16, bool live) {
+  if (live && lane < n16) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + lane * 4);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + lane * 4));
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+__device__ __forceinline__ void wait_record() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(MSG_STAGES - 2));
+  __syncwarp();
+}
+
 template <bool FIRST>
 __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid, const int32_t* __restrict__ ej,
-    const float4* __restrict__ eg, const float* __restrict__ re2, const float* __restrict__ phi,
-    const float* __restrict__ s_in, const float* __restrict__ v_in, float* __restrict__ cat,
-    float* __restrict__ v_mid) {
-  extern __shared__ __align__(16) float smem[];
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid, const float* __restrict__ erec,
+    const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
+    float* __restrict__ cat, float* __restrict__ v_mid) {
+  extern __shared__ __align__(16) float smem_all[];
   constexpr int PER = MsgFwdLayout<FIRST>::PER;
+  constexpr int N16 = (REC_RE + 44) / 4;  // 13 x 16 B: geometry + rbf rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* ring = smem_all + warp * MSG_STAGES * REC;
+  float* smem = smem_all + MSG_WARPS * MSG_STAGES * REC;
   const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
   const int h = blockIdx.y, m = blockIdx.z;
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
@@ -74,20 +94,27 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
 
   for (int il = ch + n_chunks * warp; il < n; il += n_chunks * MSG_WARPS) {
     const int i = a0 + il;
-    const long long e0 = __ldg(rowptr + i);
+    const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
     const int ne = __ldg(nvalid + i);
     float2 ds = dup2(0.f), dvx = dup2(0.f), dvy = dup2(0.f), dvz = dup2(0.f);
-    for (long long e = e0; e < e0 + ne; ++e) {
-      const float4 g = __ldg(eg + e);
-      const float* sj = smem + (__ldg(ej + e) - a0) * PER + 2 * lane;
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < MSG_STAGES - 1; ++s) prefetch_record(ring + s * REC, rec0 + (long long)s * REC, lane, N16, s < ne);
+    for (int e = 0; e < ne; ++e) {
+      wait_record();
+      const int nx = e + MSG_STAGES - 1;
+      prefetch_record(ring + (nx % MSG_STAGES) * REC, rec0 + (long long)nx * REC, lane, N16, nx < ne);
+      const float* rec = ring + (e % MSG_STAGES) * REC;
+      const float4 g = *reinterpret_cast<const float4*>(rec);
+      const float* sj = smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane;
       const float2 p0 = ld2(sj), p1 = ld2(sj + MSG_FC), p2 = ld2(sj + 2 * MSG_FC);
-      const float4* r4 = reinterpret_cast<const float4*>(re2 + e * RE2);
-      const float4 ev = __ldg(r4 + 10);  // (env,env,denv,denv)
+      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
+      const float4 ev = r4[10];  // (env,env,denv,denv)
       const float2 env2 = make_float2(ev.x, ev.y);
       float2 w0 = __fmul2_rn(bd0, env2), w1 = __fmul2_rn(bd1, env2), w2 = __fmul2_rn(bd2, env2);
 #pragma unroll
       for (int q = 0; q < NRBF / 2; ++q) {
-        const float4 t = __ldg(r4 + q);
+        const float4 t = r4[q];
         const float2 ra = make_float2(t.x, t.y), rb = make_float2(t.z, t.w);
         w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);
         w0 = __ffma2_rn(wd0[2 * q + 1], rb, w0); w1 = __ffma2_rn(wd1[2 * q + 1], rb, w1);
@@ -124,16 +151,18 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
 template <bool FIRST>
 __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid, const int32_t* __restrict__ ej,
-    const float4* __restrict__ eg, const float* __restrict__ re2, const float* __restrict__ dre2,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid, const float* __restrict__ erec,
     const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
     const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in, float* __restrict__ gradp) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(16) float smem_all[];
   constexpr int PER = MsgBwdLayout<FIRST>::PER;
   constexpr int O_V = 3 * MSG_FC;                          // only when !FIRST
   constexpr int O_DS = FIRST ? 3 * MSG_FC : 6 * MSG_FC;
   constexpr int O_DV = O_DS + MSG_FC;
+  constexpr int N16 = (REC_DRE + 40) / 4;                  // 23 x 16 B: whole record
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* ring = smem_all + warp * MSG_STAGES * REC;
+  float* smem = smem_all + MSG_WARPS * MSG_STAGES * REC;
   const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
   const int h = blockIdx.y, m = blockIdx.z;
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
@@ -165,7 +194,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
 
   for (int il = ch + n_chunks * warp; il < n; il += n_chunks * MSG_WARPS) {
     const int i = a0 + il;
-    const long long e0 = __ldg(rowptr + i);
+    const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
     const int ne = __ldg(nvalid + i);
     const float* si = smem + il * PER + 2 * lane;
     const float2 pi0 = ld2(si), pi1 = ld2(si + MSG_FC), pi2 = ld2(si + 2 * MSG_FC);
@@ -176,22 +205,29 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     float2 dp0 = dup2(0.f), dp1 = dup2(0.f), dp2n = dup2(0.f);   // dphi_i (dp2n holds -dphi_i[2])
     float2 dvx = dup2(0.f), dvy = dup2(0.f), dvz = dup2(0.f);    // sender-side dv_in
     float2 gnx = dup2(0.f), gny = dup2(0.f), gnz = dup2(0.f);    // -(per-feature dE/dx_i)
-    for (long long e = e0; e < e0 + ne; ++e) {
-      const float4 g = __ldg(eg + e);
-      const float* sj = smem + (__ldg(ej + e) - a0) * PER + 2 * lane;
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < MSG_STAGES - 1; ++s) prefetch_record(ring + s * REC, rec0 + (long long)s * REC, lane, N16, s < ne);
+    for (int e = 0; e < ne; ++e) {
+      wait_record();
+      const int nx = e + MSG_STAGES - 1;
+      prefetch_record(ring + (nx % MSG_STAGES) * REC, rec0 + (long long)nx * REC, lane, N16, nx < ne);
+      const float* rec = ring + (e % MSG_STAGES) * REC;
+      const float4 g = *reinterpret_cast<const float4*>(rec);
+      const float* sj = smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane;
       const float2 pj0 = ld2(sj), pj1 = ld2(sj + MSG_FC), pj2 = ld2(sj + 2 * MSG_FC);
       const float2 gsj = ld2(sj + O_DS);
       const float2 gvjx = ld2(sj + O_DV), gvjy = ld2(sj + O_DV + MSG_FC), gvjz = ld2(sj + O_DV + 2 * MSG_FC);
-      const float4* r4 = reinterpret_cast<const float4*>(re2 + e * RE2);
-      const float4* d4 = reinterpret_cast<const float4*>(dre2 + e * DRE2);
-      const float4 ev = __ldg(r4 + 10);
+      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
+      const float4* d4 = reinterpret_cast<const float4*>(rec + REC_DRE);
+      const float4 ev = r4[10];
       const float2 env2 = make_float2(ev.x, ev.y), denv2 = make_float2(ev.z, ev.w);
       float2 w0 = __fmul2_rn(bd0, env2), w1 = __fmul2_rn(bd1, env2), w2 = __fmul2_rn(bd2, env2);
       float2 q0 = __fmul2_rn(bd0, denv2), q1 = __fmul2_rn(bd1, denv2), q2 = __fmul2_rn(bd2, denv2);
 #pragma unroll
       for (int q = 0; q < NRBF / 2; ++q) {
-        const float4 t = __ldg(r4 + q);
-        const float4 u = __ldg(d4 + q);
+        const float4 t = r4[q];
+        const float4 u = d4[q];
         const float2 ra = make_float2(t.x, t.y), rb = make_float2(t.z, t.w);
         const float2 da = make_float2(u.x, u.y), db = make_float2(u.z, u.w);
         w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);

@@ -1,0 +1,131 @@
+"""The drop-in boundary on the GPU: reference-named calculators, optimize_slab, and accept/reject
+parity of the multi-chain driver against the single-chain oracle loop with the oracle's physics."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import classical as ocl
+from oracle import mc as omc
+from oracle import relax as orelax
+from oracle.painn import EnsembleOracle, surface_energy
+
+pytestmark = pytest.mark.gpu
+CHEM = {"Sr": -2, "Ti": 0, "O": 0}
+
+
+def _sto_atoms(structures):
+    from surface_sampling_b200.atoms import Atoms, FixAtoms
+    s = structures["SrTiO3_001_2x2"]
+    fixed = orelax.fixed_mask_from_surface_depth(s["positions"], s["cell"], 1)
+    return Atoms(numbers=s["numbers"], positions=s["positions"], cell=s["cell"], pbc=True,
+                 constraint=FixAtoms(mask=fixed)), s, fixed
+
+
+def test_ensemble_nff_surface_calculator(structures, potentials, sto_weights, golden_values):
+    from surface_sampling_b200.calculators import EnsembleNFFSurface, get_std_devs_single, get_embeddings_single
+    od = potentials["offset_data"]
+    calc = EnsembleNFFSurface(sto_weights, offset_data=od)
+    changed = calc.set(chem_pots=CHEM, offset_data=od, relax_atoms=True, relax_steps=20, optimizer="FIRE")
+    assert set(changed) >= {"chem_pots", "offset_data"} and calc.parameters.copy()["relax_steps"] == 20
+    assert "surface_energy" in calc.implemented_properties and len(calc.models) == 3
+    atoms, s, _ = _sto_atoms(structures)
+    atoms.calc = calc
+    e = atoms.get_potential_energy()
+    assert e.shape == (1,) and abs(float(e[0]) - golden_values["painn_ensemble_step0"]["SrTiO3_001_2x2"]["energy"]) < 1e-4
+    f = atoms.get_forces()                      # FixAtoms applied like ASE
+    assert np.abs(np.linalg.norm(f, axis=1).max() - 0.204407) < 2e-5
+    se = calc.get_property("surface_energy", atoms=atoms)
+    assert abs(se - surface_energy(float(e[0]), s["numbers"], od, CHEM)) < 1e-9
+    assert calc.results["forces_std"].shape == (60, 3) and get_std_devs_single(atoms, calc) > 0
+    assert get_embeddings_single(atoms, calc).shape == (128,)
+    c2 = copy.deepcopy(calc)                    # SurfaceSystem.copy(copy_calc=True)
+    assert c2.engine is calc.engine and c2.parameters == calc.parameters
+    with pytest.raises(Exception):
+        calc.get_property("stress_free_energy", atoms=atoms)
+
+
+def test_optimize_slab_fused_and_trajectory_agree(structures, potentials, sto_weights):
+    from surface_sampling_b200.calculators import EnsembleNFFSurface
+    from surface_sampling_b200.dynamics import optimize_slab
+    od = potentials["offset_data"]
+    calc = EnsembleNFFSurface(sto_weights, offset_data=od)
+    calc.set(chem_pots=CHEM, offset_data=od)
+    atoms, s, fixed = _sto_atoms(structures)
+    atoms.calc = calc
+    slab1, traj1, e1, oob1 = optimize_slab(atoms, optimizer="FIRE", save_traj=False, relax_steps=10)
+    slab2, traj2, e2, oob2 = optimize_slab(atoms, optimizer="FIRE", save_traj=True, relax_steps=10, record_interval=5)
+    assert traj1 is None and not oob1 and not oob2
+    assert e1 == e2 and np.array_equal(slab1.get_positions(), slab2.get_positions())   # same kernels, same bits
+    assert len(traj2["atoms"]) == 3 and len(traj2["energies"]) == 3                    # steps 0, 5, 10
+    assert traj2["energies"][0] > traj2["energies"][-1] and np.all(traj2["forces"][0][fixed] == 0)
+    assert np.array_equal(atoms.get_positions(), s["positions"])                       # works on a copy
+    # calculator is primed with the final evaluation: no recomputation needed for the surface energy
+    se = calc.get_property("surface_energy", atoms=slab1)
+    assert abs(se - surface_energy(e1, s["numbers"], od, CHEM)) < 1e-4
+    with pytest.raises(NotImplementedError):
+        optimize_slab(atoms, optimizer="BFGS")
+
+
+def test_lammps_surf_calc_and_oob(structures, potentials, golden_values):
+    from surface_sampling_b200 import engine
+    from surface_sampling_b200.atoms import Atoms
+    from surface_sampling_b200.calculators import LAMMPSSurfCalc
+    from surface_sampling_b200.dynamics import optimize_slab
+    s = structures["GaN_0001_3x3"]
+    calc = LAMMPSSurfCalc("tersoff", engine.tersoff_param_table(potentials["GaN.tersoff"], ["Ga", "N"]), ["Ga", "N"],
+                          bulk_index=36, n_max=64, max_nbr=24)
+    calc.set(relax_steps=50, run_dir=".")
+    atoms = Atoms(numbers=s["numbers"], positions=s["positions"], cell=s["cell"], pbc=s["pbc"], calculator=calc)
+    e = calc.get_property("surface_energy", atoms=atoms)
+    assert abs(e - golden_values["tersoff_gan_pristine"]["energy"]) < 1e-3
+    assert abs(calc.results["per_atom_energies"].sum() - e) < 1e-9
+    ads = atoms.copy(); ads.append("Ga", s["positions"][35] + np.array([0.3, 0.2, 1.9])); ads.calc = calc
+    slab, traj, e_rel, oob = optimize_slab(ads, optimizer="LAMMPS", relax_steps=50)
+    assert traj is None and not oob and e_rel < calc.get_potential_energy(atoms=ads)
+    assert np.array_equal(slab.get_positions()[:36], s["positions"])       # bulk group frozen
+    # overlapping atoms -> |E| or |F| > 1000 -> clamp (dynamics.py:159-168)
+    n_idx = int(np.where(s["numbers"] == 7)[0][-1])   # N on top of N: |F| ~ lambda1*A = 3.7e3 eV/A
+    bad = atoms.copy(); bad.append("N", s["positions"][n_idx] + np.array([0.05, 0.0, 0.05])); bad.calc = calc
+    _, _, e_bad, oob_bad = optimize_slab(bad, optimizer="LAMMPS", relax_steps=0)
+    assert oob_bad and e_bad == 1000
+
+
+def test_accept_reject_parity_tersoff(structures, potentials):
+    """Same seeds -> the multi-chain GPU run makes exactly the decisions of the single-chain oracle loop
+    (oracle Tersoff + oracle FIRE, fp64)."""
+    from surface_sampling_b200 import engine, mc
+    s = structures["GaN_0001_3x3"]
+    tab = engine.tersoff_param_table(potentials["GaN.tersoff"], ["Ga", "N"])
+    eng = engine.ClassicalEngine(engine.POT_TERSOFF, tab, 2, n_max=64, max_nbr=24)
+    prm = ocl.TersoffParams(potentials["GaN.tersoff"], ["Ga", "N"])
+    sites = mc.make_site_grid(s["positions"], s["cell"], 12, 1.8)
+    fixed0 = np.ones(36, bool)
+    tmap = {31: 0, 7: 1}
+    steps = 15
+
+    def relax_fn(pos_l, num_l, fix_l):
+        types = [np.array([tmap[int(z)] for z in zz], np.int32) for zz in num_l]
+        b = engine.Batch.from_arrays(pos_l, types, [s["cell"]] * len(pos_l), [s["pbc"]] * len(pos_l), fix_l)
+        return eng.relax(b, relax_steps=steps)["out"].cpu().numpy()
+
+    seeds = [0, 5]
+    drv = mc.MultiChainMC(s["numbers"], s["positions"], fixed0, sites, ["Ga"], relax_fn, lambda e, sym: e, seeds)
+    res = drv.run(total_sweeps=2, sweep_size=4, start_temp=0.5, perform_annealing=True, alpha=0.9)
+
+    def energy_fn(symbols, pos):
+        types = torch.tensor([0 if q == "Ga" else 1 for q in symbols])
+        fx = np.arange(len(symbols)) < 36
+        o = orelax.relax(lambda x: ocl.energy_forces(ocl.tersoff_energy, x, types, s["cell"], s["pbc"], prm), pos, fx,
+                         optimizer="FIRE", relax_steps=steps)
+        return o["raw_energy"]
+
+    sym0 = ["Ga" if z == 31 else "N" for z in s["numbers"]]
+    for k, sd in enumerate(seeds):
+        o = omc.run_chain(sd, sym0, s["positions"], sites, ["Ga"], energy_fn, 2, 4, start_temp=0.5, alpha=0.9)
+        assert [d[0] for d in drv.decisions[k]] == [d[0] for d in o["decisions"]]
+        assert np.allclose([d[1] for d in drv.decisions[k]], [d[1] for d in o["decisions"]], rtol=1e-9, atol=1e-7)
+        assert list(drv.chains[k].occ) == o["final"].occ
+        # no decision sat inside the energy-tolerance band of its uniform draw
+        assert all(abs(np.exp(-(c - p) / 0.5) - u) > 1e-6 or c <= p for _, c, p, u in o["decisions"])
