@@ -18,6 +18,7 @@
 //
 // Vector features are stored [A,3,128] (Cartesian-major) so U/V act as plain row GEMMs.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "painn_layout.h"
@@ -176,6 +177,27 @@ int launch_gemm(const GemmArgs& g, int n_models, cudaStream_t st) {
   return 0;
 }
 
+#include "gemm_tc.cuh"
+
+// GEMM dispatcher.  Bkn = [K][N] copy of the weight (FMA path), Bnk = its K-major [N][K] copy, both
+// inside the exact-fp32 block of the packed weights; the TF32 hi/lo parts of Bnk live one and two
+// W_TOTAL further (see painn_layout.h).  VSSR_GEMM=fma forces the CUDA-core path.
+inline bool use_tensor_cores() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VSSR_GEMM");
+    v = (e && e[0] == 'f') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BN, int AMODE, int EPI>
+int run_gemm(GemmArgs g, const float* Bkn, int ldb_kn, const float* Bnk, int n_models, cudaStream_t st) {
+  g.B = Bkn; g.ldb = ldb_kn; g.sB = W_STRIDE;
+  if (use_tensor_cores()) return launch_gemm_tc<BN, AMODE, EPI>(g, Bnk + W_TOTAL, Bnk + 2 * W_TOTAL, W_STRIDE, n_models, st);
+  return launch_gemm<BN, AMODE, EPI>(g, n_models, st);
+}
+
 // ------------------------------------------------------------------------------------------
 // Edge geometry (shared by all models and layers) + excluded volume.
 // One warp per receiver atom; lanes over the row in chunks of 32.  Edges inside the model cutoff
@@ -291,7 +313,7 @@ __global__ void embed_kernel(const float* __restrict__ weights, const int32_t* _
   const int a = (int)(idx / (F / 4)), f4 = (int)(idx % (F / 4));
   int zz = __ldg(z + a);
   zz = zz < 0 ? 0 : (zz >= NEMB ? NEMB - 1 : zz);
-  const float4* emb = reinterpret_cast<const float4*>(weights + (long long)m * W_TOTAL + W_EMBED);
+  const float4* emb = reinterpret_cast<const float4*>(weights + (long long)m * W_STRIDE + W_EMBED);
   reinterpret_cast<float4*>(s0 + (long long)m * n_atoms * F)[idx] = emb[zz * (F / 4) + f4];
 }
 
@@ -307,7 +329,7 @@ __global__ void __launch_bounds__(128) message_fwd_kernel(
     const float* __restrict__ s_in, const float* __restrict__ v_in, float* __restrict__ cat,
     float* __restrict__ v_mid) {
   const int m = blockIdx.y, f = threadIdx.x;
-  const float* __restrict__ wl = weights + (long long)m * W_TOTAL + W_LAYER0 + (long long)layer * L_SIZE;
+  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
   float wd0[NRBF], wd1[NRBF], wd2[NRBF];
 #pragma unroll
   for (int n = 0; n < NRBF; ++n) {
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(128) readout_energy_kernel(const float* __rest
   const int m = blockIdx.y;
   const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (a >= n_atoms) return;
-  const float* w = weights + (long long)m * W_TOTAL;
+  const float* w = weights + (long long)m * W_STRIDE;
   const float* h = h5 + ((long long)m * n_atoms + a) * FH;
   float acc = swishf_(h[lane]) * __ldg(w + R_W6 + lane) + swishf_(h[lane + 32]) * __ldg(w + R_W6 + lane + 32);
   acc = warp_sum(acc);
@@ -500,7 +522,7 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
     float* __restrict__ grad) {
   __shared__ float red[4][3];
   const int m = blockIdx.y, f = threadIdx.x, lane = f & 31, wid = f >> 5;
-  const float* __restrict__ wl = weights + (long long)m * W_TOTAL + W_LAYER0 + (long long)layer * L_SIZE;
+  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
   float wd0[NRBF], wd1[NRBF], wd2[NRBF];
 #pragma unroll
   for (int n = 0; n < NRBF; ++n) {
@@ -656,7 +678,7 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
 
 }  // namespace
 
-extern "C" int64_t vssr_painn_weight_floats(void) { return (int64_t)painn::W_TOTAL; }
+extern "C" int64_t vssr_painn_weight_floats(void) { return (int64_t)painn::W_STRIDE; }
 
 extern "C" size_t vssr_painn_workspace_bytes(int32_t n_models, int32_t n_atoms, int64_t e_cap) {
   return carve(nullptr, n_models, n_atoms, e_cap).bytes;
@@ -704,13 +726,13 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     const float* wl = weights + W_LAYER0 + (long long)l * L_SIZE;
     GemmArgs g{};
     // F1
-    g = GemmArgs{w.s[l], F, MA_F, wl + L_W1T, F, W_TOTAL, wl + L_B1, W_TOTAL, nullptr, 0, 0, nullptr, 0,
+    g = GemmArgs{w.s[l], F, MA_F, wl + L_W1T, F, W_STRIDE, wl + L_B1, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.h1[l], F, MA_F, A, F, F};
-    if ((rc = launch_gemm<128, 0, 1>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W1T, F, wl + L_W1, M, st))) return rc;
     // F2
-    g = GemmArgs{w.h1[l], F, MA_F, wl + L_W2T, F3, W_TOTAL, wl + L_B2, W_TOTAL, nullptr, 0, 0, nullptr, 0,
+    g = GemmArgs{w.h1[l], F, MA_F, wl + L_W2T, F3, W_STRIDE, wl + L_B2, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.phi[l], F3, (long long)A * F3, A, F3, F};
-    if ((rc = launch_gemm<128, 1, 1>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 1, 1>(g, wl + L_W2T, F3, wl + L_W2, M, st))) return rc;
     // F3
     if (staged) {
       if (l == 0)
@@ -730,28 +752,28 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
             weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
     }
     // F4
-    g = GemmArgs{w.vmid[l], F, (long long)A * 3 * F, wl + L_UVT, 2 * F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+    g = GemmArgs{w.vmid[l], F, (long long)A * 3 * F, wl + L_UVT, 2 * F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  w.UV[l], 2 * F, (long long)A * 6 * F, 3 * A, 2 * F, F};
-    if ((rc = launch_gemm<128, 0, 0>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 0>(g, wl + L_UVT, 2 * F, wl + L_UV, M, st))) return rc;
     // F5
     VSSR_PROF(VSSR_K_ELEMWISE, st, nrm_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], A, w.cat[l]));
     // F6
-    g = GemmArgs{w.cat[l], 2 * F, (long long)A * 2 * F, wl + L_W3T, F, W_TOTAL, wl + L_B3, W_TOTAL, nullptr, 0, 0,
+    g = GemmArgs{w.cat[l], 2 * F, (long long)A * 2 * F, wl + L_W3T, F, W_STRIDE, wl + L_B3, W_STRIDE, nullptr, 0, 0,
                  nullptr, 0, w.h3[l], F, MA_F, A, F, 2 * F};
-    if ((rc = launch_gemm<128, 0, 1>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W3T, F, wl + L_W3, M, st))) return rc;
     // F7
-    g = GemmArgs{w.h3[l], F, MA_F, wl + L_W4T, F3, W_TOTAL, wl + L_B4, W_TOTAL, nullptr, 0, 0, nullptr, 0,
+    g = GemmArgs{w.h3[l], F, MA_F, wl + L_W4T, F3, W_STRIDE, wl + L_B4, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.a[l], F3, (long long)A * F3, A, F3, F};
-    if ((rc = launch_gemm<128, 1, 1>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 1, 1>(g, wl + L_W4T, F3, wl + L_W4, M, st))) return rc;
     // F8
     VSSR_PROF(VSSR_K_ELEMWISE, st, update_fwd_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], w.a[l], w.cat[l], w.vmid[l], A,
                                                                            w.s[l + 1], w.v[l + 1]));
   }
   // readout
   {
-    GemmArgs g{w.s[NCONV], F, MA_F, weights + R_W5T, FH, W_TOTAL, weights + R_B5, W_TOTAL, nullptr, 0, 0, nullptr, 0,
+    GemmArgs g{w.s[NCONV], F, MA_F, weights + R_W5T, FH, W_STRIDE, weights + R_B5, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                w.h5, FH, (long long)A * FH, A, FH, F};
-    if ((rc = launch_gemm<64, 0, 1>(g, M, st))) return rc;
+    if ((rc = run_gemm<64, 0, 1>(g, weights + R_W5T, FH, weights + R_W5, M, st))) return rc;
     VSSR_PROF(VSSR_K_READOUT, st, readout_energy_kernel<<<dim3(ceil_div(A, 4), M), 128, 0, st>>>(weights, w.h5, w.evex, A, w.e_atom));
     VSSR_PROF(VSSR_K_READOUT, st, energy_reduce_kernel<<<dim3(ceil_div(n_struct, 4), M), 128, 0, st>>>(w.e_atom, atom_ptr, n_struct, A, energy));
   }
@@ -763,9 +785,9 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   VSSR_PROF(VSSR_K_ELEMWISE, st, grad_init_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.grad0, 3 * A, grad));
   {
     // ds = (dswish(h5) * w6) . W5      [A,64]x[64,128]
-    GemmArgs g{w.h5, FH, (long long)A * FH, weights + R_W5, F, W_TOTAL, nullptr, 0, nullptr, 0, 0, weights + R_W6,
-               W_TOTAL, w.ds, F, MA_F, A, F, FH};
-    if ((rc = launch_gemm<128, 2, 0>(g, M, st))) return rc;
+    GemmArgs g{w.h5, FH, (long long)A * FH, weights + R_W5, F, W_STRIDE, nullptr, 0, nullptr, 0, 0, weights + R_W6,
+               W_STRIDE, w.ds, F, MA_F, A, F, FH};
+    if ((rc = run_gemm<128, 2, 0>(g, weights + R_W5, F, weights + R_W5T, M, st))) return rc;
   }
   VSSR_CUDA(cudaMemsetAsync(w.dvA, 0, (size_t)M * A * 3 * F * sizeof(float), st));
   float* dv_cur = w.dvA;
@@ -776,19 +798,19 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     // B8
     VSSR_PROF(VSSR_K_ELEMWISE, st, update_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.ds, dv_cur, w.UV[l], w.a[l], A, w.da, w.dUV));
     // B7: dh3 = (da . W4) * dswish(h3)
-    g = GemmArgs{w.da, F3, (long long)A * F3, wl + L_W4, F, W_TOTAL, nullptr, 0, w.h3[l], F, MA_F, nullptr, 0,
+    g = GemmArgs{w.da, F3, (long long)A * F3, wl + L_W4, F, W_STRIDE, nullptr, 0, w.h3[l], F, MA_F, nullptr, 0,
                  w.dh3, F, MA_F, A, F, F3};
-    if ((rc = launch_gemm<128, 0, 2>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 2>(g, wl + L_W4, F, wl + L_W4T, M, st))) return rc;
     // B6: dcat = dh3 . W3
-    g = GemmArgs{w.dh3, F, MA_F, wl + L_W3, 2 * F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+    g = GemmArgs{w.dh3, F, MA_F, wl + L_W3, 2 * F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  w.dcat, 2 * F, (long long)A * 2 * F, A, 2 * F, F};
-    if ((rc = launch_gemm<128, 0, 0>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 0>(g, wl + L_W3, 2 * F, wl + L_W3T, M, st))) return rc;
     // B5
     VSSR_PROF(VSSR_K_ELEMWISE, st, nrm_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.dcat, w.cat[l], w.UV[l], A, w.ds, w.dUV));
     // B4: dv += dUV . [U;V]      [3A,256]x[256,128]
-    g = GemmArgs{w.dUV, 2 * F, (long long)A * 6 * F, wl + L_UV, F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+    g = GemmArgs{w.dUV, 2 * F, (long long)A * 6 * F, wl + L_UV, F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  dv_cur, F, (long long)A * 3 * F, 3 * A, F, 2 * F};
-    if ((rc = launch_gemm<128, 0, 3>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 3>(g, wl + L_UV, F, wl + L_UVT, M, st))) return rc;
     // B3
     if (staged) {
       if (l == 0)
@@ -812,13 +834,13 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     }
     if (l > 0) {
       // B2: dh1 = (dphi . W2) * dswish(h1)
-      g = GemmArgs{w.dphi, F3, (long long)A * F3, wl + L_W2, F, W_TOTAL, nullptr, 0, w.h1[l], F, MA_F, nullptr, 0,
+      g = GemmArgs{w.dphi, F3, (long long)A * F3, wl + L_W2, F, W_STRIDE, nullptr, 0, w.h1[l], F, MA_F, nullptr, 0,
                    w.dh1, F, MA_F, A, F, F3};
-      if ((rc = launch_gemm<128, 0, 2>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 2>(g, wl + L_W2, F, wl + L_W2T, M, st))) return rc;
       // B1: ds += dh1 . W1
-      g = GemmArgs{w.dh1, F, MA_F, wl + L_W1, F, W_TOTAL, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+      g = GemmArgs{w.dh1, F, MA_F, wl + L_W1, F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                    w.ds, F, MA_F, A, F, F};
-      if ((rc = launch_gemm<128, 0, 3>(g, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 3>(g, wl + L_W1, F, wl + L_W1T, M, st))) return rc;
       float* t = dv_cur; dv_cur = dv_nxt; dv_nxt = t;
     }
   }

@@ -40,4 +40,7 @@ constexpr long long R_W6 = R_B5 + FH;                // [64]
 constexpr long long R_B6 = R_W6 + FH;                // [1] (+3 pad)
 constexpr long long R_W5 = R_B6 + 4;                 // [64][128]
 constexpr long long W_TOTAL = R_W5 + FH * F;
+// packed block per model = [exact fp32 | TF32 part (hi) | remainder (lo = w - hi)], each W_TOTAL floats;
+// the hi/lo copies feed the 3xTF32 tcgen05 GEMM (gemm_tc.cuh)
+constexpr long long W_STRIDE = 3 * W_TOTAL;
 }  // namespace painn

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
   if (!FIRST) stage_rows(smem, PER, 3 * MSG_FC, v_in, 3 * F, F, 3, n, tid);
 
   const int f0 = h * MSG_FC + 2 * lane;  // first feature of this lane's pair
-  const float* __restrict__ wl = weights + (long long)m * W_TOTAL + W_LAYER0 + (long long)layer * L_SIZE;
+  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
   float2 wd0[NRBF], wd1[NRBF], wd2[NRBF];
 #pragma unroll
   for (int q = 0; q < NRBF; ++q) {
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
   stage_rows(smem, PER, O_DV, dv, 3 * F, F, 3, n, tid);
 
   const int f0 = h * MSG_FC + 2 * lane;
-  const float* __restrict__ wl = weights + (long long)m * W_TOTAL + W_LAYER0 + (long long)layer * L_SIZE;
+  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
   float2 wd0[NRBF], wd1[NRBF], wd2[NRBF];
 #pragma unroll
   for (int q = 0; q < NRBF; ++q) {

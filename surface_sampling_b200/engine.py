@@ -41,7 +41,7 @@ def painn_weight_floats() -> int:
     n = NEMB * F
     n += NCONV * sum(int(np.prod(s)) for _, s in _LAYER_LAYOUT)
     n += sum(int(np.prod(s)) for _, s in _READ_LAYOUT)
-    return n
+    return 3 * n   # exact + TF32 hi + lo copies
 
 
 def pack_painn_weights(state: dict) -> np.ndarray:
@@ -76,8 +76,15 @@ def pack_painn_weights(state: dict) -> np.ndarray:
         assert a.shape == shape, (name, a.shape, shape)
         parts.append(a)
     flat = np.concatenate([x.reshape(-1) for x in parts]).astype(np.float32)
-    assert flat.size == painn_weight_floats()
-    return flat
+    assert flat.size * 3 == painn_weight_floats()
+    # [exact | TF32 part | remainder]: operands of the 3xTF32 tcgen05 GEMM (csrc/gemm_tc.cuh)
+    def tf32_rn(x):
+        bits = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        return (((bits + 0x0FFF + ((bits >> 13) & 1)) & 0xFFFFE000) & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+
+    hi = tf32_rn(flat)
+    lo = tf32_rn((flat - hi).astype(np.float32))   # exactly representable: no truncation inside the tensor core
+    return np.concatenate([flat, hi, lo])
 
 
 def _ptr(t):

@@ -37,7 +37,7 @@ def test_ensemble_nff_surface_calculator(structures, potentials, sto_weights, go
     f = atoms.get_forces()                      # FixAtoms applied like ASE
     assert np.abs(np.linalg.norm(f, axis=1).max() - 0.204407) < 2e-5
     se = calc.get_property("surface_energy", atoms=atoms)
-    assert abs(se - surface_energy(float(e[0]), s["numbers"], od, CHEM)) < 1e-9
+    assert abs(float(se) - surface_energy(float(e[0]), s["numbers"], od, CHEM)) < 2e-5   # results are fp32 like NFF
     assert calc.results["forces_std"].shape == (60, 3) and get_std_devs_single(atoms, calc) > 0
     assert get_embeddings_single(atoms, calc).shape == (128,)
     c2 = copy.deepcopy(calc)                    # SurfaceSystem.copy(copy_calc=True)
