@@ -276,7 +276,8 @@ def main():
         eng.relax(b, RELAX_STEPS, 0.01, z_host=zh, want_std=False, e_cap=e_cap)
     lib.vssr_profile_collect(ms.ctypes.data, cnt.ctypes.data, ncls)
     lib.vssr_profile_enable(0)
-    names = ["nbr", "edge_geometry", "gemm_fp32", "message_fwd", "message_bwd", "elementwise", "readout",
+    gemm_name = "gemm_fp32_ffma2" if os.environ.get("VSSR_GEMM", "tc").startswith("f") else "gemm_tcgen05_3xtf32"
+    names = ["nbr", "edge_geometry", gemm_name, "message_fwd", "message_bwd", "elementwise", "readout",
              "ensemble_stats", "fire", "classical"]
     breakdown = {names[k]: {"ms": round(float(ms[k]), 3), "launches": int(cnt[k])} for k in range(ncls) if cnt[k]}
     n_prof = len(fresh)
@@ -294,25 +295,35 @@ def main():
     atom_evals = atoms_total * evals_per_prop * world / (dev_ms * 1e-3)
 
     # roofline of the dominant kernel class
-    dom = max(breakdown, key=lambda k: breakdown[k]["ms"]) if breakdown else "gemm_fp32"
+    dom = max(breakdown, key=lambda k: breakdown[k]["ms"]) if breakdown else gemm_name
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else None
     bf16 = peaks["bf16_tflops_sustained"] if peaks else 1400.0
     peak_src = "measured (MEASURED_PEAKS.json, sustained bf16 / 2 = TF32 dense)" if peaks else "fallback"
     n_evals_prof = n_prof * (RELAX_STEPS + 1)
     E_per_atom = 2504 / 60.0
     flops = {   # algorithmic FLOPs per model force-evaluation per atom (DESIGN.md / SURVEY.md 8d)
-        "gemm_fp32": 2 * 1491072.0,
+        gemm_name: 2 * 1491072.0,
         "message_fwd": 3 * E_per_atom * 2 * (3 * 20 * 128 + 12 * 128),
         "message_bwd": 3 * E_per_atom * 2 * (6 * 20 * 128 + 60 * 128),
     }
+    FFMA2_PEAK = 65.8   # TFLOP/s, packed fp32x2 FMA measured on this pool's B200 (profiles/microbench/ffma2.cu)
+
+    def tflops(name):
+        if name not in breakdown or breakdown[name]["ms"] <= 0:
+            return None
+        return flops[name] * 3 * a_prof * (RELAX_STEPS + 1) / (breakdown[name]["ms"] * 1e-3) / 1e12
+
     roof = None
-    if dom in flops and breakdown[dom]["ms"] > 0:
-        fl = flops[dom] * 3 * a_prof * (RELAX_STEPS + 1) / n_prof * n_prof   # 3 models, all evals profiled
-        achieved = fl / (breakdown[dom]["ms"] * 1e-3) / 1e12
+    if dom in flops and tflops(dom):
+        achieved = tflops(dom)
+        is_gemm = dom == gemm_name
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": bf16 / 2, "unit": "TFLOP/s",
                 "frac": achieved / (bf16 / 2), "traffic": None, "peak_source": peak_src,
-                "note": "fp32 FMA path this round (no tcgen05 yet); peak is the TF32 tensor pipe the GEMMs should use; "
-                        "CUDA-core fp32 peak is ~74 TFLOP/s"}
+                "achieved_algorithmic_tflops": {k: tflops(k) for k in flops},
+                "frac_of_measured_ffma2_peak": None if is_gemm else achieved / FFMA2_PEAK,
+                "note": ("3xTF32 on tcgen05: 3 tensor-core MACs per algorithmic MAC" if is_gemm else
+                         "message passing runs on the fp32 FMA pipe (packed FFMA2, measured peak 65.8 TFLOP/s); the "
+                         "tensor-pipe peak is quoted because the schema has no fp32-FMA bound")}
     out = {
         "metric": "relaxed_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,

@@ -14,8 +14,7 @@
 // The A operand is produced by the CTA itself (global fp32 -> optional swish / dswish transform ->
 // hi/lo split -> swizzled st.shared), so no TMA tensor maps are needed for activations; the weight
 // operand B arrives pre-split (hi/lo, K-major [N][K]) from the packed weight block.
-// Several CTAs are resident per SM (64 KB smem, 128 TMEM columns each); one CTA's MMAs and epilogue
-// overlap another's operand staging.  Tiles are walked persistently (tile = blockIdx.x + k*gridDim.x).
+// Tiles are walked persistently (tile = blockIdx.x + k*gridDim.x) by one warp-specialised CTA per SM.
 #pragma once
 
 namespace tc {
@@ -104,176 +103,283 @@ struct TcArgs {
   long long sBw;         // per-model stride of Bhi/Blo
   int n_models;
   int mode;              // 0: 3xTF32 (default), 1: plain TF32 (accuracy studies)
+  unsigned long long* dbg;  // optional [gridDim.x][8] globaltimer stamps (VSSR_TC_DEBUG=1)
 };
 
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised, persistent version (default).  One CTA per SM, 11 warps:
+//   warps 0-11 producers: stage s of the 3-deep operand ring is owned by warps 4s..4s+3 (32 rows of A
+//              and BN/4 rows of B each); A goes global -> registers -> transform/split -> swizzled
+//              st.shared, B (pre-split weights) goes global -> shared with cp.async (no registers)
+//   warp  12   MMA issuer: one elected lane waits full[s], issues 12 tcgen05.mma per chunk, and
+//              tcgen05.commit's to empty[s] (and to tmem_full[acc] after the last chunk of a tile)
+//   warps 13-16 epilogue: TMEM lane quarter (warp&3) -> registers -> fused op -> global
+// TMEM holds two accumulator sets (main + correction, 2 x 2BN = 512 columns) so the epilogue of
+// tile t overlaps the MMAs of tile t+1; 3 x 64 KB ring stages keep ~3 chunks of loads in flight.
+// ------------------------------------------------------------------------------------------
+constexpr int WS_STAGES = 3;
+constexpr int WS_PW = 4;                       // producer warps per ring stage
+constexpr int WS_PRODUCER_WARPS = WS_PW * WS_STAGES;
+constexpr int WS_MMA_WARP = WS_PRODUCER_WARPS;
+constexpr int WS_EPI_WARP0 = WS_MMA_WARP + 1;
+constexpr int WS_THREADS = (WS_EPI_WARP0 + 4) * 32;
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(k) do { if (p.dbg) p.dbg[blockIdx.x * 16 + (k)] = gtime(); } while (0)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int BN, int AMODE, int EPI>
-__global__ void __launch_bounds__(THREADS) gemm_tc_kernel(TcArgs p) {
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc_ws_kernel(TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte aligned operand tiles
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sAhi = base;
-  uint8_t* sAlo = sAhi + BM * BK * 4;
-  uint8_t* sBhi = sAlo + BM * BK * 4;
-  uint8_t* sBlo = sBhi + BN * BK * 4;
-  __shared__ __align__(8) uint64_t bar;
+  constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[WS_STAGES], empty_bar[WS_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
   const GemmArgs& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * BN));
+  if (tid == 0) TC_STAMP(0);
+  if (warp == WS_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(4 * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], WS_PW); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem_d = tmem_base_s;
-  uint32_t phase = 0;
+  const uint32_t tmem0 = tmem_base_s;
+  if (tid == 0) TC_STAMP(1);
 
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN;
   const int total = m_tiles * n_tiles * p.n_models;
   const int nchunks = g.K / BK;
   constexpr uint32_t idesc = make_idesc(BM, BN);
 
-  for (int t = blockIdx.x; t < total; t += gridDim.x) {
-    const int model = t / (m_tiles * n_tiles);
-    const int rem = t % (m_tiles * n_tiles);
-    const int m0 = (rem / n_tiles) * BM, n0 = (rem % n_tiles) * BN;
-    const float* __restrict__ A = g.A + (long long)model * g.sA;
-    const float* __restrict__ Bh = p.Bhi + (long long)model * p.sBw + (long long)n0 * g.K;
-    const float* __restrict__ Bl = p.Blo + (long long)model * p.sBw + (long long)n0 * g.K;
-    const float* __restrict__ avec = AMODE == 2 ? g.avec + (long long)model * g.sAvec : nullptr;
-
-    for (int c = 0; c < nchunks; ++c) {
-      const int k0 = c * BK;
-      // ---- stage A (transform + hi/lo split) ----
-#pragma unroll
-      for (int q = 0; q < (BM * 8) / THREADS; ++q) {
-        const int idx = tid + q * THREADS;
-        const int r = idx >> 3, ch = idx & 7;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m0 + r < g.M) {
-          x = __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * g.lda + k0) + ch);
-          if (AMODE == 1) {
-            x.x = swishf_(x.x); x.y = swishf_(x.y); x.z = swishf_(x.z); x.w = swishf_(x.w);
-          } else if (AMODE == 2) {
-            const float4 av = __ldg(reinterpret_cast<const float4*>(avec + k0) + ch);
-            x.x = dswishf_(x.x) * av.x; x.y = dswishf_(x.y) * av.y; x.z = dswishf_(x.z) * av.z; x.w = dswishf_(x.w) * av.w;
-          }
+  if (warp < WS_PRODUCER_WARPS) {
+    // ================= producers =================
+    const int s = warp / WS_PW, part = warp % WS_PW;   // this warp fills rows [part*BM/WS_PW, ...) of stage s
+    uint8_t* st = base + s * STAGE_BYTES;
+    uint8_t* sAhi = st; uint8_t* sAlo = st + A_BYTES; uint8_t* sBhi = st + 2 * A_BYTES; uint8_t* sBlo = sBhi + B_BYTES;
+    int gchunk = 0;   // running chunk counter of this CTA
+    uint32_t use = 0; // how many times this stage was filled
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int model = t / (m_tiles * n_tiles);
+      const int rem = t % (m_tiles * n_tiles);
+      const int m0 = (rem / n_tiles) * BM, n0 = (rem % n_tiles) * BN;
+      const float* __restrict__ A = g.A + (long long)model * g.sA;
+      const float* __restrict__ Bh = p.Bhi + (long long)model * p.sBw + (long long)n0 * g.K;
+      const float* __restrict__ Bl = p.Blo + (long long)model * p.sBw + (long long)n0 * g.K;
+      const float* __restrict__ avec = AMODE == 2 ? g.avec + (long long)model * g.sAvec : nullptr;
+      for (int c = 0; c < nchunks; ++c, ++gchunk) {
+        if (gchunk % WS_STAGES != s) continue;
+        const int k0 = c * BK;
+        mbar_wait(&empty_bar[s], (use & 1) ^ 1);
+        ++use;
+        const bool stamp = (warp == 0 && lane == 0 && use <= 2);
+        if (stamp) TC_STAMP(use == 1 ? 8 : 12);
+        // B: rows [half*BN/2, +BN/2) of hi and lo, straight to swizzled smem with cp.async
+#pragma unroll 4
+        for (int q = 0; q < (BN / WS_PW) * 8 / 32; ++q) {
+          const int idx = lane + q * 32;
+          const int r = part * (BN / WS_PW) + (idx >> 3), ch = idx & 7;
+          const uint32_t off = swz(r, ch);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sBhi + off)),
+                       "l"(Bh + (long long)r * g.K + k0 + ch * 4));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sBlo + off)),
+                       "l"(Bl + (long long)r * g.K + k0 + ch * 4));
         }
-        // hi = RN_tf32(x), lo = RN_tf32(x - hi): both exactly representable, so the tensor core's
-        // operand truncation is a no-op and the split error is unbiased (~2^-22 relative)
-        float4 hi, lo;
-        hi.x = tf32_rn(x.x); lo.x = tf32_rn(x.x - hi.x);
-        hi.y = tf32_rn(x.y); lo.y = tf32_rn(x.y - hi.y);
-        hi.z = tf32_rn(x.z); lo.z = tf32_rn(x.z - hi.z);
-        hi.w = tf32_rn(x.w); lo.w = tf32_rn(x.w - hi.w);
-        const uint32_t off = swz(r, ch);
-        *reinterpret_cast<float4*>(sAhi + off) = hi;
-        *reinterpret_cast<float4*>(sAlo + off) = lo;
-      }
-      // ---- stage B (pre-split weights, K-major) ----
-#pragma unroll
-      for (int q = 0; q < (BN * 8) / THREADS; ++q) {
-        const int idx = tid + q * THREADS;
-        const int r = idx >> 3, ch = idx & 7;
-        const float4 h = __ldg(reinterpret_cast<const float4*>(Bh + (long long)r * g.K + k0) + ch);
-        const float4 l = __ldg(reinterpret_cast<const float4*>(Bl + (long long)r * g.K + k0) + ch);
-        const uint32_t off = swz(r, ch);
-        *reinterpret_cast<float4*>(sBhi + off) = h;
-        *reinterpret_cast<float4*>(sBlo + off) = l;
-      }
-      fence_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      __syncthreads();
-      if (tid == 0) {
-        fence_after();
-        const uint64_t dAh = make_desc(smem_u32(sAhi)), dAl = make_desc(smem_u32(sAlo));
-        const uint64_t dBh = make_desc(smem_u32(sBhi)), dBl = make_desc(smem_u32(sBlo));
-#pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint64_t adv = (uint64_t)(kk * 32 >> 4);   // 8 fp32 = 32 bytes along K inside the swizzle row
-          // main product into columns [0,BN); the two small correction products into their own
-          // accumulator [BN,2BN): the tensor core truncates on every accumulate, so keeping the
-          // 2^-11-sized terms away from the large running sum cuts that bias 3x
-          const uint32_t first = (c | kk) ? 1u : 0u;
-          mma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, first);
-          if (p.mode != 1) {          // mode 1 = plain TF32 (accuracy studies only)
-            mma_tf32(tmem_d + BN, dAl + adv, dBh + adv, idesc, first);
-            mma_tf32(tmem_d + BN, dAh + adv, dBl + adv, idesc, 1u);
-          }
-        }
-        mma_commit(&bar);
-      }
-      mbar_wait(&bar, phase);   // MMAs of this chunk retired: smem reusable, accumulator current
-      phase ^= 1;
-    }
-    fence_after();
-
-    // ---- epilogue: TMEM -> registers -> fused op -> global; thread owns row m0 + 32*warp + lane ----
-    const int r = m0 + warp * 32 + lane;
-    const float* __restrict__ bias = EPI == 1 ? g.bias + (long long)model * g.sBias : nullptr;
-    const float* __restrict__ aux = EPI == 2 ? g.aux + (long long)model * g.sAux : nullptr;
-    float* __restrict__ C = g.C + (long long)model * g.sC;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (stamp) TC_STAMP(use == 1 ? 9 : 13);
+        // A: rows [half*64, +64): registers -> transform -> TF32 split -> swizzled smem
 #pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      float v[32], vc[32];
-      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
-      if (p.mode != 1) {
-        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(BN + cb), vc);
+        for (int q0 = 0; q0 < (BM / WS_PW) * 8 / 32; q0 += 8) {
+          float4 x[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += vc[j];
-      }
-      if (r < g.M) {
-        float* crow = C + (long long)r * g.ldc + n0 + cb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (EPI == 1) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cb + j));
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-          } else if (EPI == 2) {
-            const float4 x = *reinterpret_cast<const float4*>(aux + (long long)r * g.ldaux + n0 + cb + j);
-            o.x *= dswishf_(x.x); o.y *= dswishf_(x.y); o.z *= dswishf_(x.z); o.w *= dswishf_(x.w);
-          } else if (EPI == 3) {
-            const float4 x = *reinterpret_cast<const float4*>(crow + j);
-            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+          for (int u = 0; u < 8; ++u) {
+            const int idx = lane + (q0 + u) * 32;
+            const int r = part * (BM / WS_PW) + (idx >> 3), ch = idx & 7;
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < g.M) x[u] = __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * g.lda + k0) + ch);
           }
-          *reinterpret_cast<float4*>(crow + j) = o;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = lane + (q0 + u) * 32;
+            const int r = part * (BM / WS_PW) + (idx >> 3), ch = idx & 7;
+            float4 v = x[u];
+            if (AMODE == 1) {
+              v.x = swishf_(v.x); v.y = swishf_(v.y); v.z = swishf_(v.z); v.w = swishf_(v.w);
+            } else if (AMODE == 2) {
+              const float4 av = __ldg(reinterpret_cast<const float4*>(avec + k0) + ch);
+              v.x = dswishf_(v.x) * av.x; v.y = dswishf_(v.y) * av.y; v.z = dswishf_(v.z) * av.z; v.w = dswishf_(v.w) * av.w;
+            }
+            float4 hi, lo;
+            hi.x = tf32_rn(v.x); lo.x = tf32_rn(v.x - hi.x);
+            hi.y = tf32_rn(v.y); lo.y = tf32_rn(v.y - hi.y);
+            hi.z = tf32_rn(v.z); lo.z = tf32_rn(v.z - hi.z);
+            hi.w = tf32_rn(v.w); lo.w = tf32_rn(v.w - hi.w);
+            const uint32_t off = swz(r, ch);
+            *reinterpret_cast<float4*>(sAhi + off) = hi;
+            *reinterpret_cast<float4*>(sAlo + off) = lo;
+          }
         }
+        if (stamp) TC_STAMP(use == 1 ? 10 : 14);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (stamp) TC_STAMP(use == 1 ? 11 : 15);
       }
     }
-    fence_before();
-    __syncthreads();   // every warp has drained its TMEM lanes before the next tile overwrites them
-    fence_after();
+  } else if (warp == WS_MMA_WARP) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int gchunk = 0, it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t d_main = tmem0 + acc * 2 * BN, d_corr = d_main + BN;
+        mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        fence_after();
+        for (int c = 0; c < nchunks; ++c, ++gchunk) {
+          const int s = gchunk % WS_STAGES;
+          mbar_wait(&full_bar[s], (gchunk / WS_STAGES) & 1);
+          if (gchunk == 0) TC_STAMP(2);
+          fence_after();
+          uint8_t* st = base + s * STAGE_BYTES;
+          const uint64_t dAh = make_desc(smem_u32(st)), dAl = make_desc(smem_u32(st + A_BYTES));
+          const uint64_t dBh = make_desc(smem_u32(st + 2 * A_BYTES)), dBl = make_desc(smem_u32(st + 2 * A_BYTES + B_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+            const uint32_t first = (c | kk) ? 1u : 0u;
+            mma_tf32(d_main, dAh + adv, dBh + adv, idesc, first);
+            if (p.mode != 1) {
+              mma_tf32(d_corr, dAl + adv, dBh + adv, idesc, first);
+              mma_tf32(d_corr, dAh + adv, dBl + adv, idesc, 1u);
+            }
+          }
+          mma_commit(&empty_bar[s]);
+        }
+        mma_commit(&tfull_bar[acc]);
+        TC_STAMP(3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue =================
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int model = t / (m_tiles * n_tiles);
+      const int rem = t % (m_tiles * n_tiles);
+      const int m0 = (rem / n_tiles) * BM, n0 = (rem % n_tiles) * BN;
+      const uint32_t d_main = tmem0 + acc * 2 * BN + ((uint32_t)(quarter * 32) << 16);
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      if (it == 0 && warp == WS_EPI_WARP0 && lane == 0) TC_STAMP(4);
+      fence_after();
+      const float* __restrict__ bias = (EPI == 1 || EPI == 4) ? g.bias + (long long)model * g.sBias : nullptr;
+      const float* __restrict__ aux = EPI == 2 ? g.aux + (long long)model * g.sAux : nullptr;
+      float* __restrict__ C = g.C + (long long)model * g.sC;
+      const int r = m0 + quarter * 32 + lane;   // TMEM lane == output row: each thread owns one row
+      float* __restrict__ C2 = EPI == 4 ? g.C2 + (long long)model * g.sC : nullptr;
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        float v[32], vc[32];
+        tmem_ld32(d_main + (uint32_t)cb, v);
+        if (p.mode != 1) {
+          tmem_ld32(d_main + (uint32_t)(BN + cb), vc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += vc[j];
+        }
+        if (r < g.M) {
+          float* crow = C + (long long)r * g.ldc + n0 + cb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (EPI == 1 || EPI == 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cb + j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            } else if (EPI == 2) {
+              const float4 x = *reinterpret_cast<const float4*>(aux + (long long)r * g.ldaux + n0 + cb + j);
+              o.x *= dswishf_(x.x); o.y *= dswishf_(x.y); o.z *= dswishf_(x.z); o.w *= dswishf_(x.w);
+            } else if (EPI == 3) {
+              const float4 x = *reinterpret_cast<const float4*>(crow + j);
+              o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+            }
+            *reinterpret_cast<float4*>(crow + j) = o;
+            if (EPI == 4) {   // activation for the next GEMM, computed once per element here
+              const float4 a = make_float4(swishf_(o.x), swishf_(o.y), swishf_(o.z), swishf_(o.w));
+              *reinterpret_cast<float4*>(C2 + (long long)r * g.ldc + n0 + cb + j) = a;
+            }
+          }
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (warp == WS_EPI_WARP0 && lane == 0) TC_STAMP(5);
+    }
   }
-
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * BN));
+  fence_before();
+  __syncthreads();
+  if (tid == 0) TC_STAMP(6);
+  if (warp == WS_MMA_WARP) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(4 * BN));
   }
 }
 
 template <int BN>
-constexpr size_t smem_bytes() { return (size_t)(2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024; }
+constexpr size_t ws_smem_bytes() { return (size_t)WS_STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024; }
 
 }  // namespace tc
 
 template <int BN, int AMODE, int EPI>
 int launch_gemm_tc(const GemmArgs& g, const float* Bhi, const float* Blo, long long sBw, int n_models, cudaStream_t st) {
-  static bool configured = false;
-  constexpr size_t smem = tc::smem_bytes<BN>();
-  if (!configured) {
-    VSSR_CUDA(cudaFuncSetAttribute(tc::gemm_tc_kernel<BN, AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   static int mode = -1;
   if (mode < 0) { const char* e = getenv("VSSR_TC_MODE"); mode = e ? atoi(e) : 0; }
-  tc::TcArgs p{g, Bhi, Blo, sBw, n_models, mode};
+  static int dbg_on = -1;
+  static unsigned long long* dbg = nullptr;
+  static int dbg_left = 12, dbg_skip = -1;
+  if (dbg_skip < 0) { const char* e = getenv("VSSR_TC_DEBUG_SKIP"); dbg_skip = e ? atoi(e) : 0; }
+  if (dbg_on && dbg_skip > 0) --dbg_skip;
+  if (dbg_on < 0) { const char* e = getenv("VSSR_TC_DEBUG"); dbg_on = e ? atoi(e) : 0; if (dbg_on) cudaMalloc(&dbg, 148 * 16 * 8); }
+  tc::TcArgs p{g, Bhi, Blo, sBw, n_models, mode, (dbg_on && dbg_left > 0 && dbg_skip == 0) ? dbg : nullptr};
   const int total = ceil_div(g.M, tc::BM) * (g.N / BN) * n_models;
-  const int grid = total < 148 * 2 ? total : 148 * 2;   // 2 CTAs/SM: 256 TMEM columns each
-  VSSR_PROF(VSSR_K_GEMM, st, (tc::gemm_tc_kernel<BN, AMODE, EPI><<<grid, tc::THREADS, smem, st>>>(p)));
+  {
+    static bool configured = false;
+    constexpr size_t smem = tc::ws_smem_bytes<BN>();
+    if (!configured) {
+      VSSR_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws_kernel<BN, AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    const int grid = total < 148 ? total : 148;
+    VSSR_PROF(VSSR_K_GEMM, st, (tc::gemm_tc_ws_kernel<BN, AMODE, EPI><<<grid, tc::WS_THREADS, smem, st>>>(p)));
+    if (p.dbg) {
+      --dbg_left;
+      unsigned long long h[148 * 16];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull, t6 = 0;
+      for (int b = 0; b < grid; ++b) { if (h[b * 16] < t0) t0 = h[b * 16]; if (h[b * 16 + 6] > t6) t6 = h[b * 16 + 6]; }
+      const int b = grid - 1;
+      printf("[tc] BN=%d A=%d E=%d M=%d N=%d K=%d tiles=%d grid=%d span=%.1fus | cta%d: init=%.1f first_full=%.1f last_commit=%.1f first_tfull=%.1f last_epi=%.1f end=%.1f | prod use1: wait=%.2f issuedB=%.2f Adone=%.2f arrived=%.2f ; use2: wait=%.2f issuedB=%.2f Adone=%.2f arrived=%.2f\n", BN, AMODE, EPI, g.M, g.N, g.K, total, grid, (t6 - t0) * 1e-3, b,
+             (h[b*16+1]-h[b*16])*1e-3, (h[b*16+2]-h[b*16])*1e-3, (h[b*16+3]-h[b*16])*1e-3, (h[b*16+4]-h[b*16])*1e-3, (h[b*16+5]-h[b*16])*1e-3, (h[b*16+6]-h[b*16])*1e-3,
+             (h[b*16+8]-h[b*16])*1e-3, (h[b*16+9]-h[b*16])*1e-3, (h[b*16+10]-h[b*16])*1e-3, (h[b*16+11]-h[b*16])*1e-3, (h[b*16+12]-h[b*16])*1e-3, (h[b*16+13]-h[b*16])*1e-3, (h[b*16+14]-h[b*16])*1e-3, (h[b*16+15]-h[b*16])*1e-3);
+    }
+    return 0;
+  }
   return 0;
 }

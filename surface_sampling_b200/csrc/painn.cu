@@ -18,6 +18,7 @@
 //
 // Vector features are stored [A,3,128] (Cartesian-major) so U/V act as plain row GEMMs.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -36,7 +37,8 @@ __device__ __forceinline__ float dswishf_(float x) {
 // ------------------------------------------------------------------------------------------
 // SGEMM (fp32 FMA):  C[M,N] (op)= T(A)[M,K] . B[K,N],  batched over models on blockIdx.z.
 //   AMODE 0: A as is; 1: swish(A); 2: dswish(A) * avec[k]
-//   EPI   0: C = acc; 1: C = acc + bias[n]; 2: C = acc * dswish(aux[m,n]); 3: C += acc
+//   EPI   0: C = acc; 1: C = acc + bias[n]; 2: C = acc * dswish(aux[m,n]); 3: C += acc;
+//         4: C = acc + bias[n] and C2 = swish(C)  (activation for the next GEMM, computed once)
 // Tile 128 x BN x 16, 256 threads, 8 x (BN/16) outputs per thread, register-prefetch pipeline.
 // ------------------------------------------------------------------------------------------
 struct GemmArgs {
@@ -47,6 +49,7 @@ struct GemmArgs {
   const float* avec; long long sAvec;
   float* C; int ldc; long long sC;
   int M, N, K;
+  float* C2;   // EPI 4 only: second output swish(C) with C's leading dimension and model stride
 };
 
 template <int BN, int AMODE, int EPI>
@@ -145,8 +148,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
   }
 
   // epilogue
-  const float* __restrict__ bias = EPI == 1 ? g.bias + (long long)model * g.sBias : nullptr;
+  const float* __restrict__ bias = (EPI == 1 || EPI == 4) ? g.bias + (long long)model * g.sBias : nullptr;
   const float* __restrict__ aux = EPI == 2 ? g.aux + (long long)model * g.sAux : nullptr;
+  float* __restrict__ C2 = EPI == 4 ? g.C2 + (long long)model * g.sC : nullptr;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     for (int h = 0; h < TN / 4; ++h) {
       const int c = n0 + (h == 0 ? tx * 4 : (BN / 2) + tx * 4);
       float4 v = make_float4(acc[i][h * 2].x, acc[i][h * 2].y, acc[i][h * 2 + 1].x, acc[i][h * 2 + 1].y);
-      if (EPI == 1) {
+      if (EPI == 1 || EPI == 4) {
         const float4 bb = *reinterpret_cast<const float4*>(bias + c);
         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
       } else if (EPI == 2) {
@@ -166,6 +170,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
         v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
       }
       *reinterpret_cast<float4*>(C + (long long)r * g.ldc + c) = v;
+      if (EPI == 4)
+        *reinterpret_cast<float4*>(C2 + (long long)r * g.ldc + c) = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
     }
   }
 }
@@ -641,7 +647,7 @@ struct Workspace {
   float* v[NCONV + 1];      // [M,A,3,128]  (v[0] unused: zeros)
   float* h1[NCONV]; float* phi[NCONV]; float* cat[NCONV]; float* vmid[NCONV]; float* UV[NCONV];
   float* h3[NCONV]; float* a[NCONV];
-  float* h5; float* e_atom;
+  float* h5; float* e_atom; float* act;   // act: swish(h1)/swish(h3) scratch [M,A,128]
   // gradients
   float* ds; float* dvA; float* dvB; float* dphi; float* dh1; float* da; float* dh3; float* dcat; float* dUV;
   size_t bytes;
@@ -668,7 +674,7 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
     w.h1[l] = take(MA * F); w.phi[l] = take(MA * F3); w.cat[l] = take(MA * 2 * F); w.vmid[l] = take(MA * 3 * F);
     w.UV[l] = take(MA * 6 * F); w.h3[l] = take(MA * F); w.a[l] = take(MA * F3);
   }
-  w.h5 = take(MA * FH); w.e_atom = take(MA);
+  w.h5 = take(MA * FH); w.e_atom = take(MA); w.act = take(MA * F);
   w.ds = take(MA * F); w.dvA = take(MA * 3 * F); w.dvB = take(MA * 3 * F); w.dphi = take(MA * F3);
   w.dh1 = take(MA * F); w.da = take(MA * F3); w.dh3 = take(MA * F); w.dcat = take(MA * 2 * F);
   w.dUV = take(MA * 6 * F);
@@ -727,12 +733,12 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     GemmArgs g{};
     // F1
     g = GemmArgs{w.s[l], F, MA_F, wl + L_W1T, F, W_STRIDE, wl + L_B1, W_STRIDE, nullptr, 0, 0, nullptr, 0,
-                 w.h1[l], F, MA_F, A, F, F};
-    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W1T, F, wl + L_W1, M, st))) return rc;
+                 w.h1[l], F, MA_F, A, F, F, w.act};
+    if ((rc = run_gemm<128, 0, 4>(g, wl + L_W1T, F, wl + L_W1, M, st))) return rc;
     // F2
-    g = GemmArgs{w.h1[l], F, MA_F, wl + L_W2T, F3, W_STRIDE, wl + L_B2, W_STRIDE, nullptr, 0, 0, nullptr, 0,
+    g = GemmArgs{w.act, F, MA_F, wl + L_W2T, F3, W_STRIDE, wl + L_B2, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.phi[l], F3, (long long)A * F3, A, F3, F};
-    if ((rc = run_gemm<128, 1, 1>(g, wl + L_W2T, F3, wl + L_W2, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W2T, F3, wl + L_W2, M, st))) return rc;
     // F3
     if (staged) {
       if (l == 0)
@@ -759,12 +765,12 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     VSSR_PROF(VSSR_K_ELEMWISE, st, nrm_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], A, w.cat[l]));
     // F6
     g = GemmArgs{w.cat[l], 2 * F, (long long)A * 2 * F, wl + L_W3T, F, W_STRIDE, wl + L_B3, W_STRIDE, nullptr, 0, 0,
-                 nullptr, 0, w.h3[l], F, MA_F, A, F, 2 * F};
-    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W3T, F, wl + L_W3, M, st))) return rc;
+                 nullptr, 0, w.h3[l], F, MA_F, A, F, 2 * F, w.act};
+    if ((rc = run_gemm<128, 0, 4>(g, wl + L_W3T, F, wl + L_W3, M, st))) return rc;
     // F7
-    g = GemmArgs{w.h3[l], F, MA_F, wl + L_W4T, F3, W_STRIDE, wl + L_B4, W_STRIDE, nullptr, 0, 0, nullptr, 0,
+    g = GemmArgs{w.act, F, MA_F, wl + L_W4T, F3, W_STRIDE, wl + L_B4, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.a[l], F3, (long long)A * F3, A, F3, F};
-    if ((rc = run_gemm<128, 1, 1>(g, wl + L_W4T, F3, wl + L_W4, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W4T, F3, wl + L_W4, M, st))) return rc;
     // F8
     VSSR_PROF(VSSR_K_ELEMWISE, st, update_fwd_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], w.a[l], w.cat[l], w.vmid[l], A,
                                                                            w.s[l + 1], w.v[l + 1]));
