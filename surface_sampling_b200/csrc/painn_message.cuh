@@ -111,15 +111,18 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
       const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
       const float4 ev = r4[10];  // (env,env,denv,denv)
       const float2 env2 = make_float2(ev.x, ev.y);
+      // two independent partial sums per filter (even / odd rbf index): 6 FFMA2 chains in flight
       float2 w0 = __fmul2_rn(bd0, env2), w1 = __fmul2_rn(bd1, env2), w2 = __fmul2_rn(bd2, env2);
+      float2 w0b = dup2(0.f), w1b = dup2(0.f), w2b = dup2(0.f);
 #pragma unroll
       for (int q = 0; q < NRBF / 2; ++q) {
         const float4 t = r4[q];
         const float2 ra = make_float2(t.x, t.y), rb = make_float2(t.z, t.w);
         w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);
-        w0 = __ffma2_rn(wd0[2 * q + 1], rb, w0); w1 = __ffma2_rn(wd1[2 * q + 1], rb, w1);
-        w2 = __ffma2_rn(wd2[2 * q + 1], rb, w2);
+        w0b = __ffma2_rn(wd0[2 * q + 1], rb, w0b); w1b = __ffma2_rn(wd1[2 * q + 1], rb, w1b);
+        w2b = __ffma2_rn(wd2[2 * q + 1], rb, w2b);
       }
+      w0 = __fadd2_rn(w0, w0b); w1 = __fadd2_rn(w1, w1b); w2 = __fadd2_rn(w2, w2b);
       const float2 x0 = __fmul2_rn(p0, w0), x1 = __fmul2_rn(p1, w1), x2 = __fmul2_rn(p2, w2);
       ds = __fadd2_rn(ds, x1);
       dvx = __ffma2_rn(x2, dup2(g.x), dvx);

@@ -79,3 +79,50 @@ def test_manual_backward_matches_autograd(structures, sto_weights):
         e2, g2 = energy_and_grad_manual(st, pos, s["numbers"], i, j, off)
         assert abs(float(e) - float(e2)) < 1e-9
         assert float((g - g2).abs().max()) < 1e-8
+
+
+def test_eam_au_golden(structures, golden_values):
+    """tests/test_Au.py:19 of the reference: min over the 28 canonical states (6 of 8 adatoms)."""
+    import itertools
+    from pathlib import Path
+    from oracle.eam import EAMFuncfl
+    z = np.load(Path(__file__).resolve().parent / "golden" / "eam_funcfl.npz")
+    au = EAMFuncfl({k.split("/")[1]: z[k] for k in z.files if k.startswith("Au/")})
+    slab = structures["Au_110_2x2"]
+    ads = structures["Au_110_2x2_proper_adsorbed"]["positions"][16:24]
+    best = min(au.energy_forces(np.concatenate([slab["positions"], ads[list(keep)]]), slab["cell"], slab["pbc"])[0]
+               for keep in itertools.combinations(range(8), 6))
+    assert abs(best - golden_values["eam_au"]["energy"]) < 1e-5     # CIF adatoms carry 5 decimals
+    cu = EAMFuncfl({k.split("/")[1]: z[k] for k in z.files if k.startswith("Cu/")})
+    a = 3.615
+    e, f = cu.energy_forces(np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]]) * a, np.eye(3) * a, [True] * 3)
+    assert abs(e / 4 + 3.54) < 1e-6 and np.abs(f).max() < 1e-10   # Foiles-86 Cu: E_coh = 3.54 eV by construction
+
+
+def test_pourbaix_formula_product_vs_oracle():
+    """H7: the host-side scalar of NFFPourbaix against the oracle restatement (no GPU needed: the slab
+    energy is injected)."""
+    from oracle.pourbaix import pourbaix_potential
+    from surface_sampling_b200.atoms import Atoms
+    from surface_sampling_b200.calculators import NFFPourbaix, PourbaixAtom
+    table = {   # Sr / O literals: reference tests/pourbaix/test_pourbaix_atoms.py:44-86; Ti, H synthetic
+        "Sr": dict(E_std=-1.6895, dG2_std=-5.798, n_e=2, n_H=0, conc=1e-6),
+        "O": dict(E_std=-4.9480, dG2_std=2.46, n_e=-2, n_H=-2, conc=1.0),
+        "Ti": dict(E_std=-7.8955, dG2_std=-9.20, n_e=4, n_H=4, conc=1e-6),
+        "H": dict(E_std=-3.3927, dG2_std=0.0, n_e=1, n_H=1, conc=1.0),
+    }
+    calc = NFFPourbaix.__new__(NFFPourbaix)   # host-only use: no engine, no device
+    calc.parameters, calc.results, calc.atoms, calc._cache_key = {}, {}, None, None
+    calc.pourbaix_atoms = {k: PourbaixAtom(k, species_conc=v["conc"], num_e=v["n_e"], num_H=v["n_H"],
+                                           atom_std_state_energy=v["E_std"], delta_G2_std=v["dG2_std"])
+                           for k, v in table.items()}
+    for symbols, corr in ((["Sr"] * 4 + ["Ti"] * 4 + ["O"] * 13, {}),
+                          (["Sr"] * 2 + ["Ti"] * 2 + ["O"] * 8 + ["H"] * 3, {"HO": 0.23}),
+                          (["Sr"] * 2 + ["Ti"] * 2 + ["O"] * 7 + ["H"] * 9, {"HO": 0.23})):   # excess-H water rule
+        atoms = Atoms(symbols=symbols, positions=np.zeros((len(symbols), 3)))
+        for phi, pH in ((0.0, 0.0), (1.0, 7.0), (-0.5, 14.0)):
+            calc.phi, calc.pH, calc.temp, calc.adsorbate_corrections = phi, pH, 0.0257, corr
+            e_slab = -123.456
+            got = -(calc.get_delta_G1(atoms, slab_energy=e_slab) + calc.get_delta_G2(atoms))
+            ref = pourbaix_potential(symbols, e_slab, table, phi, pH, 0.0257, corr)
+            assert abs(got - ref) < 1e-10, (symbols, phi, pH, got, ref)
