@@ -211,63 +211,83 @@ __device__ __forceinline__ void ters_zeta_term(const TersP& p, double rij, doubl
   dz_dcos = fc * dg * ex;
 }
 
+constexpr int MAXACT = 16;   // neighbours inside the largest potential cutoff (<= slots inside cutoff+skin)
+
+// compact the skin list of atom i to the slots that are inside rcut right now
+struct Active {
+  int slot[MAXACT];
+  double x[MAXACT], y[MAXACT], z[MAXACT], r[MAXACT];
+  int n;
+};
+__device__ __forceinline__ void gather_active(const Smem& s, const Cell64& ci, int i, int max_nbr, double rcut, Active& a,
+                                              int32_t* status) {
+  a.n = 0;
+  const int cn = s.cnt[i];
+  for (int t = 0; t < cn; ++t) {
+    double x, y, z;
+    edge_vec(s, ci, i, s.nj[i * max_nbr + t], s.ns[i * max_nbr + t], x, y, z);
+    const double r = sqrt(x * x + y * y + z * z);
+    if (r < rcut) {
+      if (a.n < MAXACT) {
+        a.slot[a.n] = t; a.x[a.n] = x; a.y[a.n] = y; a.z[a.n] = z; a.r[a.n] = r;
+        ++a.n;
+      } else {
+        atomicOr(status, VSSR_STATUS_SLOT_OVERFLOW);
+      }
+    }
+  }
+}
+
 __device__ void tersoff_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, const double* __restrict__ params,
-                               int ntypes) {
+                               int ntypes, double rcut, int32_t* status) {
   for (int i = threadIdx.x; i < n; i += NT) {
     const int ti = s.type[i], ci_n = s.cnt[i];
     double gix = 0.0, giy = 0.0, giz = 0.0, ei = 0.0;
     double* Gi = s.G + (size_t)i * max_nbr * 3;
     for (int t = 0; t < ci_n; ++t) { Gi[3 * t] = 0.0; Gi[3 * t + 1] = 0.0; Gi[3 * t + 2] = 0.0; }
-    for (int t = 0; t < ci_n; ++t) {
-      const int j = s.nj[i * max_nbr + t];
-      const int tj = s.type[j];
+    Active a;
+    gather_active(s, ci, i, max_nbr, rcut, a, status);
+    for (int p = 0; p < a.n; ++p) {
+      const int t = a.slot[p];
+      const int tj = s.type[s.nj[i * max_nbr + t]];
       const TersP pij = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + tj) * 14);
-      double jx, jy, jz;
-      edge_vec(s, ci, i, j, s.ns[i * max_nbr + t], jx, jy, jz);
-      const double rij = sqrt(jx * jx + jy * jy + jz * jz);
+      const double jx = a.x[p], jy = a.y[p], jz = a.z[p], rij = a.r[p];
       if (rij >= pij.R + pij.D) continue;
       const double irij = 1.0 / rij;
       const double ux = jx * irij, uy = jy * irij, uz = jz * irij;
       double zeta = 0.0;
-      for (int u = 0; u < ci_n; ++u) {
-        if (u == t) continue;
-        const int k = s.nj[i * max_nbr + u];
-        const TersP pk = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + s.type[k]) * 14);
-        double kx, ky, kz;
-        edge_vec(s, ci, i, k, s.ns[i * max_nbr + u], kx, ky, kz);
-        const double rik = sqrt(kx * kx + ky * ky + kz * kz);
+      for (int q = 0; q < a.n; ++q) {
+        if (q == p) continue;
+        const TersP pk = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + s.type[s.nj[i * max_nbr + a.slot[q]]]) * 14);
+        const double rik = a.r[q];
         if (rik >= pk.R + pk.D) continue;
-        const double cs = (jx * kx + jy * ky + jz * kz) * irij / rik;
+        const double cs = (jx * a.x[q] + jy * a.y[q] + jz * a.z[q]) * irij / rik;
         double z, a1, a2, a3;
         ters_zeta_term(pk, rij, rik, cs, z, a1, a2, a3);
         zeta += z;
       }
-      double fc, dfc, b, db;
+      double fc, dfc, bb, db;
       ters_fc(rij, pij.R, pij.D, fc, dfc);
-      ters_bij(zeta, pij, b, db);
+      ters_bij(zeta, pij, bb, db);
       const double er = pij.A * exp(-pij.lam1 * rij), ea = -pij.B * exp(-pij.lam2 * rij);
       const double fR = fc * er, dfR = er * (dfc - pij.lam1 * fc);
       const double fA = fc * ea, dfA = ea * (dfc - pij.lam2 * fc);
-      ei += 0.5 * (fR + b * fA);
-      const double dEdr = 0.5 * (dfR + b * dfA);
+      ei += 0.5 * (fR + bb * fA);
+      const double dEdr = 0.5 * (dfR + bb * dfA);
       const double pref = 0.5 * fA * db;
-      // explicit pair part: gradient w.r.t. x_j is +dEdr*u, w.r.t. x_i is -dEdr*u
       double gjx = dEdr * ux, gjy = dEdr * uy, gjz = dEdr * uz;
       if (pref != 0.0) {
-        for (int u = 0; u < ci_n; ++u) {
-          if (u == t) continue;
-          const int k = s.nj[i * max_nbr + u];
-          const TersP pk = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + s.type[k]) * 14);
-          double kx, ky, kz;
-          edge_vec(s, ci, i, k, s.ns[i * max_nbr + u], kx, ky, kz);
-          const double rik = sqrt(kx * kx + ky * ky + kz * kz);
+        for (int q = 0; q < a.n; ++q) {
+          if (q == p) continue;
+          const int u = a.slot[q];
+          const TersP pk = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + s.type[s.nj[i * max_nbr + u]]) * 14);
+          const double rik = a.r[q];
           if (rik >= pk.R + pk.D) continue;
           const double irik = 1.0 / rik;
-          const double wx = kx * irik, wy = ky * irik, wz = kz * irik;
+          const double wx = a.x[q] * irik, wy = a.y[q] * irik, wz = a.z[q] * irik;
           const double cs = ux * wx + uy * wy + uz * wz;
           double z, dzj, dzk, dzc;
           ters_zeta_term(pk, rij, rik, cs, z, dzj, dzk, dzc);
-          // dcos/dr_ij_vec = (w - cs u)/rij ; dcos/dr_ik_vec = (u - cs w)/rik
           const double djx = pref * (dzj * ux + dzc * (wx - cs * ux) * irij);
           const double djy = pref * (dzj * uy + dzc * (wy - cs * uy) * irij);
           const double djz = pref * (dzj * uz + dzc * (wz - cs * uz) * irij);
@@ -299,25 +319,24 @@ __device__ __forceinline__ SWP load_sw(const double* __restrict__ p) {
 }
 
 __device__ void sw_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, const double* __restrict__ params,
-                          int ntypes) {
+                          int ntypes, double rcut, int32_t* status) {
   for (int i = threadIdx.x; i < n; i += NT) {
     const int ti = s.type[i], ci_n = s.cnt[i];
     double gix = 0.0, giy = 0.0, giz = 0.0, ei = 0.0;
     double* Gi = s.G + (size_t)i * max_nbr * 3;
     for (int t = 0; t < ci_n; ++t) { Gi[3 * t] = 0.0; Gi[3 * t + 1] = 0.0; Gi[3 * t + 2] = 0.0; }
-    for (int t = 0; t < ci_n; ++t) {
-      const int j = s.nj[i * max_nbr + t];
-      const int tj = s.type[j];
+    Active a;
+    gather_active(s, ci, i, max_nbr, rcut, a, status);
+    for (int p = 0; p < a.n; ++p) {
+      const int t = a.slot[p];
+      const int tj = s.type[s.nj[i * max_nbr + t]];
       const SWP pij = load_sw(params + (size_t)((ti * ntypes + tj) * ntypes + tj) * 10);
       const double cutij = pij.a * pij.sigma;
-      double jx, jy, jz;
-      edge_vec(s, ci, i, j, s.ns[i * max_nbr + t], jx, jy, jz);
-      const double rij = sqrt(jx * jx + jy * jy + jz * jz);
+      const double jx = a.x[p], jy = a.y[p], jz = a.z[p], rij = a.r[p];
       if (rij >= cutij) continue;
       const double irij = 1.0 / rij;
       const double ux = jx * irij, uy = jy * irij, uz = jz * irij;
-      // two-body (half per direction)
-      {
+      {   // two-body (half per direction)
         const double sr = pij.sigma * irij;
         const double srp = pow(sr, pij.p), srq = pow(sr, pij.q);
         const double rc = rij - cutij;
@@ -335,19 +354,17 @@ __device__ void sw_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, c
       const double gsij = pij.gamma * pij.sigma;
       const double rcij = rij - cutij;
       const double exij = exp(gsij / rcij);
-      const double dexij = -gsij / (rcij * rcij);  // d ln(exij)/d rij
-      for (int u = t + 1; u < ci_n; ++u) {
-        const int k = s.nj[i * max_nbr + u];
-        const int tk = s.type[k];
+      const double dexij = -gsij / (rcij * rcij);
+      for (int q = p + 1; q < a.n; ++q) {
+        const int u = a.slot[q];
+        const int tk = s.type[s.nj[i * max_nbr + u]];
         const SWP pik = load_sw(params + (size_t)((ti * ntypes + tk) * ntypes + tk) * 10);
         const SWP pijk = load_sw(params + (size_t)((ti * ntypes + tj) * ntypes + tk) * 10);
         const double cutik = pik.a * pik.sigma;
-        double kx, ky, kz;
-        edge_vec(s, ci, i, k, s.ns[i * max_nbr + u], kx, ky, kz);
-        const double rik = sqrt(kx * kx + ky * ky + kz * kz);
+        const double rik = a.r[q];
         if (rik >= cutik) continue;
         const double irik = 1.0 / rik;
-        const double wx = kx * irik, wy = ky * irik, wz = kz * irik;
+        const double wx = a.x[q] * irik, wy = a.y[q] * irik, wz = a.z[q] * irik;
         const double cs = ux * wx + uy * wy + uz * wz;
         const double gsik = pik.gamma * pik.sigma;
         const double rcik = rik - cutik;
@@ -377,9 +394,9 @@ __device__ void sw_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, c
 
 // phase 1 (centre terms) + phase 2 (gather through reverse map) -> s.f = -dE/dx ; returns E (all threads)
 __device__ double eval_forces(int kind, const Smem& s, const Cell64& ci, int n, int max_nbr,
-                              const double* __restrict__ params, int ntypes) {
-  if (kind == VSSR_POT_TERSOFF) tersoff_phase1(s, ci, n, max_nbr, params, ntypes);
-  else sw_phase1(s, ci, n, max_nbr, params, ntypes);
+                              const double* __restrict__ params, int ntypes, double rcut, int32_t* status) {
+  if (kind == VSSR_POT_TERSOFF) tersoff_phase1(s, ci, n, max_nbr, params, ntypes, rcut, status);
+  else sw_phase1(s, ci, n, max_nbr, params, ntypes, rcut, status);
   __syncthreads();
   double e = 0.0, z0 = 0.0, z1 = 0.0;
   for (int j = threadIdx.x; j < n; j += NT) {
@@ -466,11 +483,20 @@ __global__ void __launch_bounds__(NT) classical_kernel(int kind, const double* _
     s.fixed[i] = RELAX ? fixed[a0 + i] : 0;
   }
   __syncthreads();
-  const double rcut = max_cut(kind, params, ntypes);
+  // potential parameters: shared-memory copy when they fit (ntypes <= 3)
+  __shared__ double sprm_buf[27 * 14];
+  const int nprm = ntypes * ntypes * ntypes * (kind == VSSR_POT_TERSOFF ? 14 : 10);
+  const double* sprm = params;
+  if (nprm <= 27 * 14) {
+    for (int q = threadIdx.x; q < nprm; q += NT) sprm_buf[q] = params[q];
+    sprm = sprm_buf;
+    __syncthreads();
+  }
+  const double rcut = max_cut(kind, sprm, ntypes);
   const double rl = rcut + (RELAX ? skin : 0.0);
   build_list(s, ci, n, max_nbr, rl, status);
 
-  double energy = eval_forces(kind, s, ci, n, max_nbr, params, ntypes);
+  double energy = eval_forces(kind, s, ci, n, max_nbr, sprm, ntypes, rcut, status);
   if (!RELAX) {
     for (int i = threadIdx.x; i < n; i += NT) {
       for (int c = 0; c < 3; ++c) out_forces[3 * (a0 + i) + c] = s.f[3 * i + c];
@@ -549,7 +575,7 @@ __global__ void __launch_bounds__(NT) classical_kernel(int kind, const double* _
     }
     nsteps += 1;
     if (__syncthreads_or(moved)) build_list(s, ci, n, max_nbr, rl, status);
-    energy = eval_forces(kind, s, ci, n, max_nbr, params, ntypes);
+    energy = eval_forces(kind, s, ci, n, max_nbr, sprm, ntypes, rcut, status);
   }
   for (int i = threadIdx.x; i < n; i += NT)
     for (int c = 0; c < 3; ++c) {
