@@ -259,6 +259,8 @@ def main():
         eng = engine.PainnEngine([init_random_weights(s) for s in (0, 1, 2)], pots["offset_data"])
         e_cap = C * 72 * 96
         to_species = lambda zz: zz
+        if not os.environ.get("VSSR_NO_FILTER_MEMO"):
+            eng.set_framework(pos, cell, pbc, fixed)     # radial-filter memo for the frozen bulk (one-time, untimed)
 
         def relax_batch(b, zh):
             return eng.relax(b, relax_steps=steps_relax, fmax=0.01, z_host=zh, want_std=False, e_cap=e_cap)

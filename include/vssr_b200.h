@@ -85,10 +85,27 @@ int vssr_painn_energy_grad(const float* weights, int32_t n_models,
                               -> global-gather kernels */,
                            const int32_t* rowptr, const int32_t* col,
                            const int8_t* shift, int64_t e_cap, float cutoff,
+                           const void* filter_cache /* from vssr_painn_filter_cache_build, or NULL */,
+                           int32_t fc_n0, int64_t fc_e_cap0,
                            void* workspace, size_t workspace_bytes,
                            double* energy /*[M,B]*/, float* grad /*[M,A,3]*/,
                            float* embedding /*[M,A,128] or NULL: final scalar features*/,
                            void* stream);
+
+/* Radial-filter memo for frozen pairs.  In VSSR-MC every chain shares one frozen bulk framework (the
+ * first n0 atoms of every structure, FixAtoms / `group bulk`), so most edges keep a bit-identical
+ * distance in every chain and at every FIRE step.  Their per-model, per-layer filter rows w(d) and
+ * dw/dd are computed ONCE here from the framework alone; the evaluation kernels look an edge up by
+ * (j_local, lattice shift) in the framework's CSR row and use the memo only when its fp32 distance is
+ * bitwise equal, so the result never depends on a promise by the caller.  Synchronises the stream.
+ * (No counterpart in the reference: it re-evaluates every filter on every call.)                     */
+size_t vssr_painn_filter_cache_bytes(int32_t n_models, int32_t n0, int64_t e_cap0);
+int vssr_painn_filter_cache_build(const float* weights, int32_t n_models, const float* pos0 /*[n0,3]*/,
+                                  const float* cell /*[3,3]*/, const uint8_t* pbc /*[3]*/,
+                                  const uint8_t* fixed0 /*[n0]*/, int32_t n0, float cutoff, float skin,
+                                  int64_t e_cap0, void* cache, size_t cache_bytes, void* workspace,
+                                  size_t workspace_bytes, int32_t* nslots_out /* host, may be NULL */,
+                                  void* stream);
 
 /* EnsembleNFF semantics: per model E_eV = E_kcal/23.06052 + offset_ev[b]; mean and population std
  * over models; forces = -mean(grad)/23.06052, forces_std = std(grad)/23.06052.               */
@@ -129,7 +146,8 @@ int vssr_painn_relax(const float* weights, int32_t n_models, double* pos /*[A,3]
                      const int32_t* z, const uint8_t* fixed, const int32_t* atom_ptr,
                      const float* cell, const uint8_t* pbc, const double* offset_ev,
                      int32_t n_struct, int32_t n_atoms, int32_t max_atoms_per_struct, float cutoff, float skin,
-                     int32_t relax_steps, double fmax, int64_t e_cap, void* workspace,
+                     int32_t relax_steps, double fmax, int64_t e_cap,
+                     const void* filter_cache, int32_t fc_n0, int64_t fc_e_cap0, void* workspace,
                      size_t workspace_bytes, double* out /*[B,8]*/, float* forces /*[A,3]*/,
                      float* forces_std /*[A,3] or NULL*/, int32_t* status, void* stream);
 

@@ -305,8 +305,9 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
                                 const uint8_t* fixed, const int32_t* atom_ptr, const float* cell, const uint8_t* pbc,
                                 const double* offset_ev, int32_t n_struct, int32_t n_atoms,
                                 int32_t max_atoms_per_struct, float cutoff, float skin,
-                                int32_t relax_steps, double fmax, int64_t e_cap, void* workspace,
-                                size_t workspace_bytes, double* out, float* forces, float* forces_std,
+                                int32_t relax_steps, double fmax, int64_t e_cap, const void* filter_cache,
+                                int32_t fc_n0, int64_t fc_e_cap0, void* workspace, size_t workspace_bytes,
+                                double* out, float* forces, float* forces_std,
                                 int32_t* status, void* stream) {
   if (!weights || !pos || !z || !fixed || !atom_ptr || !cell || !pbc || !workspace || !out || !forces || !status)
     return VSSR_ERR_ARG;
@@ -324,7 +325,8 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
   for (int it = 0; it <= relax_steps; ++it) {
     if ((rc = vssr_painn_energy_grad(weights, n_models, w.pos32, z, atom_ptr, cell, n_struct, n_atoms,
                                      max_atoms_per_struct, w.rowptr,
-                                     w.col, w.shift, e_cap, cutoff, w.painn, w.painn_bytes, w.energy, w.grad, nullptr,
+                                     w.col, w.shift, e_cap, cutoff, filter_cache, fc_n0, fc_e_cap0, w.painn, w.painn_bytes, w.energy,
+                                     w.grad, nullptr,
                                      stream)))
       return rc;
     const bool last = it == relax_steps;

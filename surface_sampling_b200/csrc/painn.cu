@@ -209,24 +209,45 @@ int run_gemm(GemmArgs g, const float* Bkn, int ldb_kn, const float* Bnk, int n_m
 // One warp per receiver atom; lanes over the row in chunks of 32.  Edges inside the model cutoff
 // are COMPACTED to the front of the row (order preserved: ballot + popc), nvalid[i] of them:
 // one 384-byte record per edge, erec[e][96 floats]:
-//   [0..3]   (ux,uy,uz,d)        [4] sender (global atom index, int bits)   [5..7] pad
+//   [0..3]   (ux,uy,uz,d)   [4] sender (global atom index)  [5] filter-memo slot or -1  [6] (j_local,S) key  [7] pad
 //   [8..51]  (rbf_n*env) duplicated as pairs (v,v) for n=1..20, then (env,env),(denv,denv)
 //   [52..91] d(rbf_n*env)/dd duplicated as pairs                              [92..95] pad
 // (a record is what one warp prefetches with a single cp.async per lane)
 // The pair duplication feeds the packed FFMA2 path (sm_100 fma.rn.f32x2) without register moves.
 // grad0[a] = excluded-volume gradient (same for every model); evex[a] its energy.
 // ------------------------------------------------------------------------------------------
-constexpr int REC = 96, REC_EJ = 4, REC_RE = 8, REC_DRE = 52;
+constexpr int REC = 96, REC_EJ = 4, REC_SLOT = 5, REC_RE = 8, REC_DRE = 52;
+
+// Radial-filter memo ("frozen-pair cache").  The filter w(d) = Wd.(rbf(d)*env(d)) + bd*env(d) and its
+// derivative q(d) depend on the edge only through the scalar d.  In VSSR-MC every chain shares the same
+// frozen bulk framework, so ~3/4 of all edges have, in every chain and at every FIRE step, bit-identical
+// d.  Their w and q (per model and layer, 384 floats each) are computed once (vssr_painn_filter_cache_build)
+// and looked up by exact distance match: an edge (i_local, j_local, S) of a chain is resolved to the
+// framework edge with the same key by binary search in the framework's CSR row and uses the memo only if
+// its fp32 d is bitwise equal to the framework's.  No promise from the caller is needed.
+struct FilterCacheView {
+  int n0;                    // framework atoms (0 = no cache)
+  int nslots_cap;            // slot capacity (row stride of wc/qc per model-layer)
+  const int32_t* rowptr;     // [n0+1] framework CSR (cutoff+skin list); row i holds nvalid[i] compacted edges
+  const int32_t* nvalid;     // [n0]
+  const int32_t* key;        // [E0] j_local*125 + (S0+2)*25 + (S1+2)*5 + (S2+2), ascending within a row
+  const int32_t* slot;       // [E0] memo slot or -1
+  const float* d;            // [E0] fp32 distance of the framework edge
+  const float* wc;           // [M*3][nslots_cap][384]
+  const float* qc;           // [M*3][nslots_cap][384]
+};
 
 __global__ void __launch_bounds__(128) edge_geometry_kernel(
     const float* __restrict__ pos, const int32_t* __restrict__ atom_ptr, const float* __restrict__ cell, int n_struct,
     int n_atoms, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-    const int8_t* __restrict__ shift, long long e_cap, float cutoff, int32_t* __restrict__ nvalid,
-    float* __restrict__ erec, float* __restrict__ evex, float* __restrict__ grad0) {
+    const int8_t* __restrict__ shift, long long e_cap, float cutoff, FilterCacheView fc,
+    int32_t* __restrict__ nvalid, float* __restrict__ erec, int32_t* __restrict__ eslot, float* __restrict__ evex,
+    float* __restrict__ grad0) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n_atoms) return;
   const int b = struct_of_atom(atom_ptr, n_struct, i);
+  const int a0 = __ldg(atom_ptr + b);
   float c[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) c[k] = __ldg(cell + 9 * b + k);
@@ -234,17 +255,22 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
   long long e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
   if (e1 > e_cap) e1 = e_cap;
   if (e0 > e_cap) e0 = e_cap;
+  // framework row of this atom (if it is one of the first n0 atoms of its structure)
+  int f0 = 0, f1 = 0;
+  if (i - a0 < fc.n0) { f0 = __ldg(fc.rowptr + (i - a0)); f1 = f0 + __ldg(fc.nvalid + (i - a0)); }
   const float pi_over_rc = 3.14159265358979323846f / cutoff;
   float ev = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
   int nv = 0;
   for (long long base = e0; base < e1; base += 32) {
     const long long e = base + lane;
     bool valid = false;
-    int j = 0;
+    int j = 0, key = -1;
     float rx = 0.f, ry = 0.f, rz = 0.f, dp = 0.f;
     if (e < e1) {
       j = __ldg(col + e);
       const char4 s = reinterpret_cast<const char4*>(shift)[e];
+      if (s.x >= -2 && s.x <= 2 && s.y >= -2 && s.y <= 2 && s.z >= -2 && s.z <= 2)
+        key = (j - a0) * 125 + (s.x + 2) * 25 + (s.y + 2) * 5 + (s.z + 2);
       const float f0 = (float)s.x, f1 = (float)s.y, f2 = (float)s.z;
       // same fp32 offset arithmetic as the neighbour list
       const float ox = __fadd_rn(__fadd_rn(__fmul_rn(f0, c[0]), __fmul_rn(f1, c[3])), __fmul_rn(f2, c[6]));
@@ -264,10 +290,22 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
       const float inv_d = 1.0f / d;
       const float ux = rx * inv_d, uy = ry * inv_d, uz = rz * inv_d;
       float* rec = erec + w * REC;
+      // filter memo lookup: same (j_local, S) in the framework row AND bit-identical distance
+      int slot = -1;
+      if (key >= 0 && j - a0 < fc.n0) {
+        int lo = f0, hi = f1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(fc.key + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        if (lo < f1 && __ldg(fc.key + lo) == key && __float_as_int(__ldg(fc.d + lo)) == __float_as_int(d))
+          slot = __ldg(fc.slot + lo);
+      }
+      eslot[w] = slot;
       *reinterpret_cast<float4*>(rec) = make_float4(ux, uy, uz, d);
-      *reinterpret_cast<float4*>(rec + 4) = make_float4(__int_as_float(j), 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(rec + 4) = make_float4(__int_as_float(j), __int_as_float(slot), __int_as_float(key), 0.f);
       float env = 0.f, denv = 0.f;
-      const bool inside = d < cutoff;
+      const bool inside = d < cutoff && slot < 0;   // memoised edges never read their rbf rows
       if (inside) {
         float sn, cs;
         sincosf(pi_over_rc * d, &sn, &cs);
@@ -639,9 +677,89 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
 
 #include "painn_message.cuh"
 
+// ---- filter memo construction (one-time per framework + weights) ----
+struct CacheBlob {
+  int32_t* rowptr; int32_t* nvalid; int32_t* key; int32_t* slot; float* d; float* wc; float* qc; int32_t* counter;
+  size_t bytes;
+};
+CacheBlob carve_cache(void* base, int M, int n0, long long e_cap0) {
+  CacheBlob c;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) -> void* {
+    void* p = base ? reinterpret_cast<char*>(base) + off : nullptr;
+    off += ((nbytes + 255) / 256) * 256;
+    return p;
+  };
+  c.rowptr = (int32_t*)take((size_t)(n0 + 1) * 4);
+  c.nvalid = (int32_t*)take((size_t)n0 * 4);
+  c.key = (int32_t*)take((size_t)e_cap0 * 4);
+  c.slot = (int32_t*)take((size_t)e_cap0 * 4);
+  c.d = (float*)take((size_t)e_cap0 * 4);
+  c.counter = (int32_t*)take(4);
+  c.wc = (float*)take((size_t)M * NCONV * e_cap0 * F3 * 4);
+  c.qc = (float*)take((size_t)M * NCONV * e_cap0 * F3 * 4);
+  c.bytes = off;
+  return c;
+}
+FilterCacheView cache_view(const void* blob, int M, int n0, long long e_cap0) {
+  FilterCacheView v{};
+  if (!blob || n0 <= 0) return v;
+  CacheBlob c = carve_cache(const_cast<void*>(blob), M, n0, e_cap0);
+  v.n0 = n0; v.nslots_cap = (int)e_cap0; v.rowptr = c.rowptr; v.nvalid = c.nvalid; v.key = c.key; v.slot = c.slot;
+  v.d = c.d; v.wc = c.wc; v.qc = c.qc;
+  return v;
+}
+
+// one thread: number the framework edges whose two atoms are both frozen (their d never changes)
+__global__ void cache_slot_kernel(const float* __restrict__ erec, const int32_t* __restrict__ rowptr,
+                                  const int32_t* __restrict__ nvalid, const uint8_t* __restrict__ fixed0, int n0,
+                                  int32_t* __restrict__ key, int32_t* __restrict__ slot, float* __restrict__ d,
+                                  int32_t* __restrict__ counter) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int n = 0;
+  for (int i = 0; i < n0; ++i) {
+    const int e0 = rowptr[i];
+    for (int w = e0; w < e0 + nvalid[i]; ++w) {
+      const float* rec = erec + (long long)w * REC;
+      const int j = __float_as_int(rec[REC_EJ]);
+      key[w] = __float_as_int(rec[6]);
+      d[w] = rec[3];
+      slot[w] = (fixed0[i] && fixed0[j] && __float_as_int(rec[6]) >= 0) ? n++ : -1;
+    }
+  }
+  *counter = n;
+}
+
+// grid (e_cap0, M*NCONV), 128 threads (feature f): w_k, q_k of memoised edges, same FMA order as the
+// message kernels' direct evaluation
+__global__ void __launch_bounds__(128) cache_fill_kernel(const float* __restrict__ weights, const float* __restrict__ erec,
+                                                         const int32_t* __restrict__ slot, int e_cap0,
+                                                         float* __restrict__ wc, float* __restrict__ qc) {
+  const int w = blockIdx.x, ml = blockIdx.y, f = threadIdx.x;
+  const int sl = slot[w];
+  if (sl < 0) return;
+  const int m = ml / NCONV, layer = ml % NCONV;
+  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
+  const float* rec = erec + (long long)w * REC;
+  const float env = rec[REC_RE + 40], denv = rec[REC_RE + 42];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float bd = wl[L_BD + k * F + f];
+    float wv = bd * env, qv = bd * denv;
+    for (int n = 0; n < NRBF; ++n) {
+      const float wd = wl[L_WDT + n * F3 + k * F + f];
+      wv = fmaf(wd, rec[REC_RE + 2 * n], wv);
+      qv = fmaf(wd, rec[REC_DRE + 2 * n], qv);
+    }
+    wc[((long long)ml * e_cap0 + sl) * F3 + k * F + f] = wv;
+    qc[((long long)ml * e_cap0 + sl) * F3 + k * F + f] = qv;
+  }
+}
+
+
 struct Workspace {
   // edge records (compacted per row by edge_geometry_kernel)
-  int32_t* nvalid; float* erec; float* evex; float* grad0; float* gradp;
+  int32_t* nvalid; float* erec; int32_t* eslot; float* evex; float* grad0; float* gradp;
   // activations
   float* s[NCONV + 1];      // [M,A,128]
   float* v[NCONV + 1];      // [M,A,3,128]  (v[0] unused: zeros)
@@ -664,6 +782,7 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
   const size_t MA = (size_t)M * (size_t)A;
   w.nvalid = reinterpret_cast<int32_t*>(take(A));
   w.erec = take((size_t)e_cap * REC);
+  w.eslot = reinterpret_cast<int32_t*>(take((size_t)e_cap));
   w.evex = take(A);
   w.grad0 = take((size_t)A * 3);
   w.gradp = take(MA * 2 * 3);
@@ -693,9 +812,9 @@ extern "C" size_t vssr_painn_workspace_bytes(int32_t n_models, int32_t n_atoms, 
 extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, const float* pos, const int32_t* z,
                                       const int32_t* atom_ptr, const float* cell, int32_t n_struct, int32_t n_atoms,
                                       int32_t max_atoms_per_struct, const int32_t* rowptr, const int32_t* col,
-                                      const int8_t* shift, int64_t e_cap, float cutoff, void* workspace,
-                                      size_t workspace_bytes, double* energy, float* grad, float* embedding,
-                                      void* stream) {
+                                      const int8_t* shift, int64_t e_cap, float cutoff, const void* filter_cache,
+                                      int32_t fc_n0, int64_t fc_e_cap0, void* workspace, size_t workspace_bytes,
+                                      double* energy, float* grad, float* embedding, void* stream) {
   if (!weights || !pos || !z || !atom_ptr || !cell || !rowptr || !col || !shift || !workspace || !energy || !grad)
     return VSSR_ERR_ARG;
   if (n_models <= 0 || n_struct <= 0 || n_atoms <= 0) return VSSR_ERR_ARG;
@@ -709,8 +828,9 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
 
   // message kernels: shared-memory staged FFMA2 path when every structure fits, else global-gather path
   const int nmax = max_atoms_per_struct;
-  const size_t smem_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4 + MSG_PIPE_BYTES, smem_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4 + MSG_PIPE_BYTES;
-  const size_t smem_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4 + MSG_PIPE_BYTES, smem_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4 + MSG_PIPE_BYTES;
+  const FilterCacheView fc = cache_view(filter_cache, n_models, fc_n0, fc_e_cap0);
+  const size_t smem_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4 + MSG_PIPE_BYTES_FWD, smem_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4 + MSG_PIPE_BYTES_FWD;
+  const size_t smem_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4 + MSG_PIPE_BYTES_BWD, smem_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4 + MSG_PIPE_BYTES_BWD;
   const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
   const int n_chunks = 2;
   const dim3 v2_grid(n_struct * n_chunks, F / MSG_FC, M);
@@ -723,8 +843,8 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   }
 
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(
-      pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, w.nvalid, w.erec, w.evex,
-      w.grad0));
+      pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, staged ? fc : FilterCacheView{},
+      w.nvalid, w.erec, w.eslot, w.evex, w.grad0));
   VSSR_PROF(VSSR_K_ELEMWISE, st, embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]));
 
   int rc;
@@ -743,11 +863,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if (staged) {
       if (l == 0)
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.eslot, fc, w.phi[l], w.s[l], nullptr,
             w.cat[l], w.vmid[l]));
       else
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.eslot, fc, w.phi[l], w.s[l], w.v[l],
             w.cat[l], w.vmid[l]));
     } else {
       if (l == 0)
@@ -821,11 +941,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if (staged) {
       if (l == 0)
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.eslot, fc, w.phi[l], nullptr, w.ds,
             dv_cur, nullptr, nullptr, w.gradp));
       else
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.eslot, fc, w.phi[l], w.v[l], w.ds,
             dv_cur, w.dphi, dv_nxt, w.gradp));
       VSSR_PROF(VSSR_K_ELEMWISE, st, grad_accum_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.gradp, 3 * A, grad));
     } else {
@@ -850,5 +970,51 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       float* t = dv_cur; dv_cur = dv_nxt; dv_nxt = t;
     }
   }
+  return VSSR_OK;
+}
+
+extern "C" size_t vssr_painn_filter_cache_bytes(int32_t n_models, int32_t n0, int64_t e_cap0) {
+  return carve_cache(nullptr, n_models, n0, e_cap0).bytes;
+}
+
+extern "C" int vssr_painn_filter_cache_build(const float* weights, int32_t n_models, const float* pos0, const float* cell,
+                                             const uint8_t* pbc, const uint8_t* fixed0, int32_t n0, float cutoff,
+                                             float skin, int64_t e_cap0, void* cache, size_t cache_bytes, void* workspace,
+                                             size_t workspace_bytes, int32_t* nslots_out, void* stream) {
+  if (!weights || !pos0 || !cell || !pbc || !fixed0 || !cache || !workspace || n0 <= 0 || n_models <= 0) return VSSR_ERR_ARG;
+  CacheBlob c = carve_cache(cache, n_models, n0, e_cap0);
+  if (c.bytes > cache_bytes) return VSSR_ERR_WORKSPACE;
+  // scratch: atom_ptr[2], deg[n0], col[e_cap0], shift[e_cap0*4], status, erec[e_cap0*REC], eslot, evex, grad0
+  size_t off = 0;
+  auto take = [&](size_t nbytes) -> void* { void* p = reinterpret_cast<char*>(workspace) + off; off += ((nbytes + 255) / 256) * 256; return p; };
+  int32_t* atom_ptr = (int32_t*)take(8);
+  int32_t* deg = (int32_t*)take((size_t)n0 * 4);
+  int32_t* col = (int32_t*)take((size_t)e_cap0 * 4);
+  int8_t* shift = (int8_t*)take((size_t)e_cap0 * 4);
+  int32_t* status = (int32_t*)take(4);
+  float* erec = (float*)take((size_t)e_cap0 * REC * 4);
+  int32_t* eslot = (int32_t*)take((size_t)e_cap0 * 4);
+  float* evex = (float*)take((size_t)n0 * 4);
+  float* grad0 = (float*)take((size_t)n0 * 12);
+  if (off > workspace_bytes) return VSSR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int32_t ptr_h[2] = {0, n0};
+  VSSR_CUDA(cudaMemcpyAsync(atom_ptr, ptr_h, 8, cudaMemcpyHostToDevice, st));
+  VSSR_CUDA(cudaMemsetAsync(status, 0, 4, st));
+  VSSR_CUDA(cudaMemsetAsync(c.slot, 0xFF, (size_t)e_cap0 * 4, st));
+  int rc = vssr_nbr_build(pos0, atom_ptr, cell, pbc, 1, n0, cutoff + skin, deg, c.rowptr, col, shift, e_cap0, status, stream);
+  if (rc) return rc;
+  VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(n0, 4), 128, 0, st>>>(
+      pos0, atom_ptr, cell, 1, n0, c.rowptr, col, shift, (long long)e_cap0, cutoff, FilterCacheView{}, c.nvalid, erec, eslot,
+      evex, grad0));
+  VSSR_PROF(VSSR_K_GEOM, st, cache_slot_kernel<<<1, 32, 0, st>>>(erec, c.rowptr, c.nvalid, fixed0, n0, c.key, c.slot, c.d, c.counter));
+  VSSR_PROF(VSSR_K_GEOM, st, cache_fill_kernel<<<dim3((unsigned)e_cap0, n_models * NCONV), 128, 0, st>>>(
+      weights, erec, c.slot, (int)e_cap0, c.wc, c.qc));
+  int32_t host[2] = {0, 0};
+  VSSR_CUDA(cudaMemcpyAsync(&host[0], c.counter, 4, cudaMemcpyDeviceToHost, st));
+  VSSR_CUDA(cudaMemcpyAsync(&host[1], status, 4, cudaMemcpyDeviceToHost, st));
+  VSSR_CUDA(cudaStreamSynchronize(st));
+  if (host[1] & VSSR_STATUS_EDGE_OVERFLOW) return VSSR_ERR_WORKSPACE;
+  if (nslots_out) *nslots_out = host[0];
   return VSSR_OK;
 }

@@ -18,7 +18,10 @@ constexpr int MSG_FC = 64;        // features per CTA
 constexpr int MSG_THREADS = 256;  // 8 warps
 constexpr int MSG_WARPS = MSG_THREADS / 32;
 constexpr int MSG_STAGES = 3;     // cp.async ring depth per warp
-constexpr int MSG_PIPE_BYTES = MSG_WARPS * MSG_STAGES * REC * 4;
+constexpr int MSG_RS_FWD = REC + 3 * MSG_FC;   // ring stage floats: edge record + memoised w rows of the chunk
+constexpr int MSG_RS_BWD = REC + 6 * MSG_FC;   // ... + memoised q rows
+constexpr int MSG_PIPE_BYTES_FWD = MSG_WARPS * MSG_STAGES * MSG_RS_FWD * 4;
+constexpr int MSG_PIPE_BYTES_BWD = MSG_WARPS * MSG_STAGES * MSG_RS_BWD * 4;
 
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
@@ -41,14 +44,40 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ dst_atom0, int pe
   }
 }
 
-// one 16-byte cp.async per lane for the first n16*16 bytes of a record, then commit (always commits,
-// so group accounting stays uniform even past the end of the row)
-__device__ __forceinline__ void prefetch_record(float* dst, const float* src, int lane, int n16, bool live) {
-  if (live && lane < n16) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + lane * 4);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + lane * 4));
+// one 16-byte cp.async per lane for the first n16*16 bytes of a record; if the edge's filter is
+// memoised (slot >= 0) each lane also pulls its feature pair of the NK cached rows (8 bytes each)
+// behind the record; then commit (always commits, so group accounting stays uniform past the row end)
+template <int NK>
+__device__ __forceinline__ void prefetch_record(float* dst, const float* src, int lane, int n16, bool live, int slot,
+                                                const float* __restrict__ wrow, const float* __restrict__ qrow) {
+  if (live) {
+    if (lane < n16) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + lane * 4);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + lane * 4));
+    }
+    if (slot >= 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + REC + (k * 32 + lane) * 2);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(wrow + (long long)slot * F3 + k * F + 2 * lane));
+      }
+      if (NK == 6) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const unsigned d = (unsigned)__cvta_generic_to_shared(dst + REC + 3 * MSG_FC + (k * 32 + lane) * 2);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(qrow + (long long)slot * F3 + k * F + 2 * lane));
+        }
+      }
+    }
   }
   asm volatile("cp.async.commit_group;\n" ::);
+}
+// memo slot of the e-th valid edge of the current row: lanes hold edges [0,64) in two registers
+__device__ __forceinline__ int row_slot(int s0, int s1, const int32_t* __restrict__ eslot_row, int e, int ne) {
+  if (e >= ne) return -1;
+  if (e < 32) return __shfl_sync(0xffffffffu, s0, e);
+  if (e < 64) return __shfl_sync(0xffffffffu, s1, e - 32);
+  return __ldg(eslot_row + e);
 }
 __device__ __forceinline__ void wait_record() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(MSG_STAGES - 2));
@@ -59,14 +88,16 @@ template <bool FIRST>
 __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid, const float* __restrict__ erec,
-    const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
-    float* __restrict__ cat, float* __restrict__ v_mid) {
+    const int32_t* __restrict__ eslot, FilterCacheView fc, const float* __restrict__ phi,
+    const float* __restrict__ s_in, const float* __restrict__ v_in, float* __restrict__ cat,
+    float* __restrict__ v_mid) {
   extern __shared__ __align__(16) float smem_all[];
   constexpr int PER = MsgFwdLayout<FIRST>::PER;
   constexpr int N16 = (REC_RE + 44) / 4;  // 13 x 16 B: geometry + rbf rows
+  constexpr int RS = MSG_RS_FWD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* ring = smem_all + warp * MSG_STAGES * REC;
-  float* smem = smem_all + MSG_WARPS * MSG_STAGES * REC;
+  float* ring = smem_all + warp * MSG_STAGES * RS;
+  float* smem = smem_all + MSG_WARPS * MSG_STAGES * RS;
   const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
   const int h = blockIdx.y, m = blockIdx.z;
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
@@ -82,6 +113,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
 
   const int f0 = h * MSG_FC + 2 * lane;  // first feature of this lane's pair
   const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
+  // memoised filter rows of this (model, layer), pre-offset to this CTA's feature half
+  const float* __restrict__ wrow = fc.wc ? fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC : nullptr;
   float2 wd0[NRBF], wd1[NRBF], wd2[NRBF];
 #pragma unroll
   for (int q = 0; q < NRBF; ++q) {
@@ -94,35 +127,42 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
 
   for (int il = ch + n_chunks * warp; il < n; il += n_chunks * MSG_WARPS) {
     const int i = a0 + il;
-    const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
+    const long long e0 = __ldg(rowptr + i);
+    const float* rec0 = erec + e0 * REC;
     const int ne = __ldg(nvalid + i);
+    const int32_t* srow = eslot + e0;
+    const int s0r = lane < ne ? __ldg(srow + lane) : -1, s1r = lane + 32 < ne ? __ldg(srow + lane + 32) : -1;
     float2 ds = dup2(0.f), dvx = dup2(0.f), dvy = dup2(0.f), dvz = dup2(0.f);
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < MSG_STAGES - 1; ++s) prefetch_record(ring + s * REC, rec0 + (long long)s * REC, lane, N16, s < ne);
+    for (int s = 0; s < MSG_STAGES - 1; ++s)
+      prefetch_record<3>(ring + s * RS, rec0 + (long long)s * REC, lane, N16, s < ne, row_slot(s0r, s1r, srow, s, ne), wrow, nullptr);
     for (int e = 0; e < ne; ++e) {
       wait_record();
       const int nx = e + MSG_STAGES - 1;
-      prefetch_record(ring + (nx % MSG_STAGES) * REC, rec0 + (long long)nx * REC, lane, N16, nx < ne);
-      const float* rec = ring + (e % MSG_STAGES) * REC;
+      prefetch_record<3>(ring + (nx % MSG_STAGES) * RS, rec0 + (long long)nx * REC, lane, N16, nx < ne,
+                         row_slot(s0r, s1r, srow, nx, ne), wrow, nullptr);
+      const float* rec = ring + (e % MSG_STAGES) * RS;
       const float4 g = *reinterpret_cast<const float4*>(rec);
       const float* sj = smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane;
       const float2 p0 = ld2(sj), p1 = ld2(sj + MSG_FC), p2 = ld2(sj + 2 * MSG_FC);
-      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
-      const float4 ev = r4[10];  // (env,env,denv,denv)
-      const float2 env2 = make_float2(ev.x, ev.y);
-      // two independent partial sums per filter (even / odd rbf index): 6 FFMA2 chains in flight
-      float2 w0 = __fmul2_rn(bd0, env2), w1 = __fmul2_rn(bd1, env2), w2 = __fmul2_rn(bd2, env2);
-      float2 w0b = dup2(0.f), w1b = dup2(0.f), w2b = dup2(0.f);
+      float2 w0, w1, w2;
+      if (__float_as_int(rec[REC_SLOT]) >= 0) {   // memoised filter (warp-uniform branch)
+        w0 = ld2(rec + REC + 2 * lane); w1 = ld2(rec + REC + MSG_FC + 2 * lane); w2 = ld2(rec + REC + 2 * MSG_FC + 2 * lane);
+      } else {
+        const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
+        const float4 ev = r4[10];  // (env,env,denv,denv)
+        const float2 env2 = make_float2(ev.x, ev.y);
+        w0 = __fmul2_rn(bd0, env2); w1 = __fmul2_rn(bd1, env2); w2 = __fmul2_rn(bd2, env2);
 #pragma unroll
-      for (int q = 0; q < NRBF / 2; ++q) {
-        const float4 t = r4[q];
-        const float2 ra = make_float2(t.x, t.y), rb = make_float2(t.z, t.w);
-        w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);
-        w0b = __ffma2_rn(wd0[2 * q + 1], rb, w0b); w1b = __ffma2_rn(wd1[2 * q + 1], rb, w1b);
-        w2b = __ffma2_rn(wd2[2 * q + 1], rb, w2b);
+        for (int q = 0; q < NRBF / 2; ++q) {
+          const float4 t = r4[q];
+          const float2 ra = make_float2(t.x, t.y), rb = make_float2(t.z, t.w);
+          w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);
+          w0 = __ffma2_rn(wd0[2 * q + 1], rb, w0); w1 = __ffma2_rn(wd1[2 * q + 1], rb, w1);
+          w2 = __ffma2_rn(wd2[2 * q + 1], rb, w2);
+        }
       }
-      w0 = __fadd2_rn(w0, w0b); w1 = __fadd2_rn(w1, w1b); w2 = __fadd2_rn(w2, w2b);
       const float2 x0 = __fmul2_rn(p0, w0), x1 = __fmul2_rn(p1, w1), x2 = __fmul2_rn(p2, w2);
       ds = __fadd2_rn(ds, x1);
       dvx = __ffma2_rn(x2, dup2(g.x), dvx);
@@ -155,17 +195,19 @@ template <bool FIRST>
 __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid, const float* __restrict__ erec,
-    const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
-    const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in, float* __restrict__ gradp) {
+    const int32_t* __restrict__ eslot, FilterCacheView fc, const float* __restrict__ phi,
+    const float* __restrict__ v_in, const float* __restrict__ ds, const float* __restrict__ dv,
+    float* __restrict__ dphi, float* __restrict__ dv_in, float* __restrict__ gradp) {
   extern __shared__ __align__(16) float smem_all[];
   constexpr int PER = MsgBwdLayout<FIRST>::PER;
   constexpr int O_V = 3 * MSG_FC;                          // only when !FIRST
   constexpr int O_DS = FIRST ? 3 * MSG_FC : 6 * MSG_FC;
   constexpr int O_DV = O_DS + MSG_FC;
   constexpr int N16 = (REC_DRE + 40) / 4;                  // 23 x 16 B: whole record
+  constexpr int RS = MSG_RS_BWD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* ring = smem_all + warp * MSG_STAGES * REC;
-  float* smem = smem_all + MSG_WARPS * MSG_STAGES * REC;
+  float* ring = smem_all + warp * MSG_STAGES * RS;
+  float* smem = smem_all + MSG_WARPS * MSG_STAGES * RS;
   const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
   const int h = blockIdx.y, m = blockIdx.z;
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
@@ -185,6 +227,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
 
   const int f0 = h * MSG_FC + 2 * lane;
   const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
+  const float* __restrict__ wrow = fc.wc ? fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC : nullptr;
+  const float* __restrict__ qrow = fc.qc ? fc.qc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC : nullptr;
   float2 wd0[NRBF], wd1[NRBF], wd2[NRBF];
 #pragma unroll
   for (int q = 0; q < NRBF; ++q) {
@@ -197,8 +241,11 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
 
   for (int il = ch + n_chunks * warp; il < n; il += n_chunks * MSG_WARPS) {
     const int i = a0 + il;
-    const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
+    const long long e0 = __ldg(rowptr + i);
+    const float* rec0 = erec + e0 * REC;
     const int ne = __ldg(nvalid + i);
+    const int32_t* srow = eslot + e0;
+    const int s0r = lane < ne ? __ldg(srow + lane) : -1, s1r = lane + 32 < ne ? __ldg(srow + lane + 32) : -1;
     const float* si = smem + il * PER + 2 * lane;
     const float2 pi0 = ld2(si), pi1 = ld2(si + MSG_FC), pi2 = ld2(si + 2 * MSG_FC);
     const float2 gsi = ld2(si + O_DS);
@@ -210,35 +257,44 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     float2 gnx = dup2(0.f), gny = dup2(0.f), gnz = dup2(0.f);    // -(per-feature dE/dx_i)
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < MSG_STAGES - 1; ++s) prefetch_record(ring + s * REC, rec0 + (long long)s * REC, lane, N16, s < ne);
+    for (int s = 0; s < MSG_STAGES - 1; ++s)
+      prefetch_record<6>(ring + s * RS, rec0 + (long long)s * REC, lane, N16, s < ne, row_slot(s0r, s1r, srow, s, ne), wrow, qrow);
     for (int e = 0; e < ne; ++e) {
       wait_record();
       const int nx = e + MSG_STAGES - 1;
-      prefetch_record(ring + (nx % MSG_STAGES) * REC, rec0 + (long long)nx * REC, lane, N16, nx < ne);
-      const float* rec = ring + (e % MSG_STAGES) * REC;
+      prefetch_record<6>(ring + (nx % MSG_STAGES) * RS, rec0 + (long long)nx * REC, lane, N16, nx < ne,
+                         row_slot(s0r, s1r, srow, nx, ne), wrow, qrow);
+      const float* rec = ring + (e % MSG_STAGES) * RS;
       const float4 g = *reinterpret_cast<const float4*>(rec);
       const float* sj = smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane;
       const float2 pj0 = ld2(sj), pj1 = ld2(sj + MSG_FC), pj2 = ld2(sj + 2 * MSG_FC);
       const float2 gsj = ld2(sj + O_DS);
       const float2 gvjx = ld2(sj + O_DV), gvjy = ld2(sj + O_DV + MSG_FC), gvjz = ld2(sj + O_DV + 2 * MSG_FC);
-      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
-      const float4* d4 = reinterpret_cast<const float4*>(rec + REC_DRE);
-      const float4 ev = r4[10];
-      const float2 env2 = make_float2(ev.x, ev.y), denv2 = make_float2(ev.z, ev.w);
-      float2 w0 = __fmul2_rn(bd0, env2), w1 = __fmul2_rn(bd1, env2), w2 = __fmul2_rn(bd2, env2);
-      float2 q0 = __fmul2_rn(bd0, denv2), q1 = __fmul2_rn(bd1, denv2), q2 = __fmul2_rn(bd2, denv2);
+      float2 w0, w1, w2, q0, q1, q2;
+      if (__float_as_int(rec[REC_SLOT]) >= 0) {   // memoised filter and derivative (warp-uniform branch)
+        const float* mw = rec + REC + 2 * lane;
+        w0 = ld2(mw); w1 = ld2(mw + MSG_FC); w2 = ld2(mw + 2 * MSG_FC);
+        q0 = ld2(mw + 3 * MSG_FC); q1 = ld2(mw + 4 * MSG_FC); q2 = ld2(mw + 5 * MSG_FC);
+      } else {
+        const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
+        const float4* d4 = reinterpret_cast<const float4*>(rec + REC_DRE);
+        const float4 ev = r4[10];
+        const float2 env2 = make_float2(ev.x, ev.y), denv2 = make_float2(ev.z, ev.w);
+        w0 = __fmul2_rn(bd0, env2); w1 = __fmul2_rn(bd1, env2); w2 = __fmul2_rn(bd2, env2);
+        q0 = __fmul2_rn(bd0, denv2); q1 = __fmul2_rn(bd1, denv2); q2 = __fmul2_rn(bd2, denv2);
 #pragma unroll
-      for (int q = 0; q < NRBF / 2; ++q) {
-        const float4 t = r4[q];
-        const float4 u = d4[q];
-        const float2 ra = make_float2(t.x, t.y), rb = make_float2(t.z, t.w);
-        const float2 da = make_float2(u.x, u.y), db = make_float2(u.z, u.w);
-        w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);
-        q0 = __ffma2_rn(wd0[2 * q], da, q0); q1 = __ffma2_rn(wd1[2 * q], da, q1); q2 = __ffma2_rn(wd2[2 * q], da, q2);
-        w0 = __ffma2_rn(wd0[2 * q + 1], rb, w0); w1 = __ffma2_rn(wd1[2 * q + 1], rb, w1);
-        w2 = __ffma2_rn(wd2[2 * q + 1], rb, w2);
-        q0 = __ffma2_rn(wd0[2 * q + 1], db, q0); q1 = __ffma2_rn(wd1[2 * q + 1], db, q1);
-        q2 = __ffma2_rn(wd2[2 * q + 1], db, q2);
+        for (int q = 0; q < NRBF / 2; ++q) {
+          const float4 t = r4[q];
+          const float4 u = d4[q];
+          const float2 ra = make_float2(t.x, t.y), rb = make_float2(t.z, t.w);
+          const float2 da = make_float2(u.x, u.y), db = make_float2(u.z, u.w);
+          w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);
+          q0 = __ffma2_rn(wd0[2 * q], da, q0); q1 = __ffma2_rn(wd1[2 * q], da, q1); q2 = __ffma2_rn(wd2[2 * q], da, q2);
+          w0 = __ffma2_rn(wd0[2 * q + 1], rb, w0); w1 = __ffma2_rn(wd1[2 * q + 1], rb, w1);
+          w2 = __ffma2_rn(wd2[2 * q + 1], rb, w2);
+          q0 = __ffma2_rn(wd0[2 * q + 1], db, q0); q1 = __ffma2_rn(wd1[2 * q + 1], db, q1);
+          q2 = __ffma2_rn(wd2[2 * q + 1], db, q2);
+        }
       }
       const float2 ux = dup2(g.x), uy = dup2(g.y), uz = dup2(g.z);
       // edge A (i receives from j): dxA1 = gsi, dxA2 = gvi.u, dxA0 = gvi.vj

@@ -211,6 +211,44 @@ class PainnEngine:
         self.edges_per_atom = edges_per_atom
         self._ws = _Workspace()
         self._ws_relax = _Workspace()
+        self._fc = None          # (blob tensor, n0, e_cap0, nslots) of the frozen-pair filter memo
+
+    def set_framework(self, pos0, cell, pbc, fixed0) -> int:
+        """Build the radial-filter memo for a frozen framework shared by every structure (its atoms must
+        be the FIRST n0 atoms of each structure, as in VSSR-MC where adsorbates are appended).  Edges
+        whose distance is bitwise equal to a framework edge between two frozen atoms reuse the memoised
+        filter rows instead of re-evaluating 2x60 FMAs per feature; anything else is computed as usual,
+        so correctness never depends on this call.  Returns the number of memoised pairs."""
+        lib, dev = self.lib, self.device
+        pos0 = np.ascontiguousarray(pos0, dtype=np.float32)
+        n0 = len(pos0)
+        b = Batch.from_arrays([pos0], [np.zeros(n0, np.int32)], [cell], [pbc])
+        rowptr, col, _ = neighbor_list(b, self.cutoff + self.skin)
+        e_cap0 = int(col.numel()) + 8
+        nbytes = int(lib.vssr_painn_filter_cache_bytes(self.n_models, n0, e_cap0))
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = torch.empty(e_cap0 * (96 * 4 + 16) + n0 * 64 + 8192, dtype=torch.uint8, device=dev)
+        d_pos = torch.from_numpy(pos0).to(dev)
+        d_cell = torch.from_numpy(np.ascontiguousarray(cell, dtype=np.float32)).to(dev)
+        d_pbc = torch.from_numpy(np.ascontiguousarray(pbc).astype(np.uint8)).to(dev)
+        d_fix = torch.from_numpy(np.ascontiguousarray(fixed0).astype(np.uint8)).to(dev)
+        import ctypes
+        nslots = ctypes.c_int32(0)
+        _lib.check(lib.vssr_painn_filter_cache_build(_ptr(self.weights), self.n_models, _ptr(d_pos), _ptr(d_cell),
+                                                     _ptr(d_pbc), _ptr(d_fix), n0, self.cutoff, self.skin, e_cap0,
+                                                     _ptr(blob), blob.numel(), _ptr(ws), ws.numel(),
+                                                     ctypes.addressof(nslots), _stream()),
+                   "vssr_painn_filter_cache_build")
+        self._fc = (blob, n0, e_cap0, int(nslots.value))
+        return int(nslots.value)
+
+    def clear_framework(self):
+        self._fc = None
+
+    def _fc_args(self):
+        if self._fc is None:
+            return None, 0, 0
+        return self._fc[0].data_ptr(), self._fc[1], self._fc[2]
 
     # -- H5 stoichiometric offset (per structure, host, exact fp64) ---------------------------
     def offsets_ev(self, z_host: np.ndarray, atom_ptr: np.ndarray) -> np.ndarray | None:
@@ -250,7 +288,7 @@ class PainnEngine:
         emb = torch.empty((M, A, F), dtype=torch.float32, device=dev) if want_embedding else None
         _lib.check(lib.vssr_painn_energy_grad(_ptr(self.weights), M, _ptr(pos32), _ptr(batch.z), _ptr(batch.atom_ptr),
                                               _ptr(cell32), B, A, batch.max_atoms, _ptr(rowptr), _ptr(col), _ptr(shift), e_cap,
-                                              self.cutoff, _ptr(ws), ws.numel(), _ptr(energy), _ptr(grad), _ptr(emb),
+                                              self.cutoff, *self._fc_args(), _ptr(ws), ws.numel(), _ptr(energy), _ptr(grad), _ptr(emb),
                                               _stream()), "vssr_painn_energy_grad")
         off = None
         if self.offset_data is not None:
@@ -286,8 +324,8 @@ class PainnEngine:
         cell32 = batch.cell32.contiguous()
         _lib.check(lib.vssr_painn_relax(_ptr(self.weights), M, _ptr(batch.pos), _ptr(batch.z), _ptr(batch.fixed),
                                         _ptr(batch.atom_ptr), _ptr(cell32), _ptr(batch.pbc), _ptr(off), B, A,
-                                        batch.max_atoms, self.cutoff, self.skin, int(relax_steps), float(fmax), cap, _ptr(ws),
-                                        ws.numel(), _ptr(out), _ptr(forces), _ptr(fstd), _ptr(status), _stream()),
+                                        batch.max_atoms, self.cutoff, self.skin, int(relax_steps), float(fmax), cap,
+                                        *self._fc_args(), _ptr(ws), ws.numel(), _ptr(out), _ptr(forces), _ptr(fstd), _ptr(status), _stream()),
                    "vssr_painn_relax")
         return {"out": out, "forces": forces, "forces_std": fstd, "status": status}
 

@@ -156,3 +156,40 @@ def test_uncertainty_reductions(structures, potentials, sto_weights):
         v = np.linalg.norm(fs[k], axis=1)
         ref = [v.sum(), v.max(), v.min(), v.mean(), (v ** 2).mean(), np.sqrt((v ** 2).mean())]
         assert np.allclose(red[k], ref, rtol=1e-5)
+
+
+def test_frozen_pair_filter_memo(structures, potentials, sto_weights):
+    """The radial-filter memo (vssr_painn_filter_cache_build) changes nothing but speed: with the frozen
+    framework registered, energies/forces agree with the un-memoised evaluation to fp32 round-off, the
+    oracle tolerances still hold, and the relaxation makes the same decisions."""
+    from surface_sampling_b200 import engine
+    od = potentials["offset_data"]
+    base = structures["SrTiO3_001_2x2"]
+    fixed0 = orelax.fixed_mask_from_surface_depth(base["positions"], base["cell"], 1)
+    rng = np.random.default_rng(21)
+    structs, fixed = [], []
+    for k in (0, 2, 5):
+        s = with_adsorbates(base, rng, k, [8, 38, 22]) if k else dict(base)
+        s["positions"] = s["positions"].copy()
+        s["positions"][~np.concatenate([fixed0, np.zeros(k, bool)])] += rng.normal(0, 0.03, (int((~fixed0).sum()) + k, 3))
+        structs.append(s)
+        fixed.append(np.concatenate([fixed0, np.zeros(k, bool)]))
+    plain = engine.PainnEngine(sto_weights, od)
+    memo = engine.PainnEngine(sto_weights, od)
+    nslots = memo.set_framework(base["positions"], base["cell"], PBC3, fixed0)
+    assert nslots > 1500          # ~(52/60)^2 of the 2504 edges connect two frozen atoms
+    r0 = plain.energy_forces(_batch(structs))
+    r1 = memo.energy_forces(_batch(structs))
+    assert (r0["energy"] - r1["energy"]).abs().max().item() < 2e-6 * 60
+    assert (r0["forces"] - r1["forces"]).abs().max().item() < 2e-5
+    _compare(memo, EnsembleOracle(sto_weights, od, dtype=torch.float64), structs)
+    b0, b1 = _batch(structs, fixed), _batch(structs, fixed)
+    o0 = plain.relax(b0, relax_steps=10)["out"].cpu().numpy()
+    o1 = memo.relax(b1, relax_steps=10)["out"].cpu().numpy()
+    assert np.array_equal(o0[:, 4:], o1[:, 4:]) and np.abs(o0[:, 0] - o1[:, 0]).max() < 1e-4
+    assert (b0.pos - b1.pos).abs().max().item() < 1e-5
+    # a framework that does not match the batch (shifted atoms) silently disables the memo: same answers
+    other = engine.PainnEngine(sto_weights, od)
+    other.set_framework(base["positions"] + 0.123, base["cell"], PBC3, fixed0)
+    r2 = other.energy_forces(_batch(structs))
+    assert torch.equal(r2["forces"], r0["forces"]) or (r2["forces"] - r0["forces"]).abs().max().item() < 2e-5
