@@ -86,7 +86,7 @@ int vssr_painn_energy_grad(const float* weights, int32_t n_models,
                            const int32_t* rowptr, const int32_t* col,
                            const int8_t* shift, int64_t e_cap, float cutoff,
                            const void* filter_cache /* from vssr_painn_filter_cache_build, or NULL */,
-                           int32_t fc_n0, int64_t fc_e_cap0,
+                           int32_t fc_n0, int64_t fc_e_cap0, int32_t fc_flags /* VSSR_FC_* */,
                            void* workspace, size_t workspace_bytes,
                            double* energy /*[M,B]*/, float* grad /*[M,A,3]*/,
                            float* embedding /*[M,A,128] or NULL: final scalar features*/,
@@ -98,8 +98,17 @@ int vssr_painn_energy_grad(const float* weights, int32_t n_models,
  * dw/dd are computed ONCE here from the framework alone; the evaluation kernels look an edge up by
  * (j_local, lattice shift) in the framework's CSR row and use the memo only when its fp32 distance is
  * bitwise equal, so the result never depends on a promise by the caller.  Synchronises the stream.
- * (No counterpart in the reference: it re-evaluates every filter on every call.)                     */
+ * (No counterpart in the reference: it re-evaluates every filter on every call.)
+ *
+ * fc_flags of the evaluation calls:
+ *   VSSR_FC_CONSTRAINED_GRAD  the caller applies FixAtoms to the framework's frozen atoms (ASE zeroes
+ *       their forces before any optimiser sees them, ase Atoms.get_forces(apply_constraint=True) as used
+ *       by mcmc/dynamics.py:25-141), so dE/dx of those atoms is not computed: a memoised edge joins two
+ *       frozen atoms and its whole position-gradient branch is skipped.  Energies, and the gradient rows
+ *       of every other atom, are unchanged; gradient rows of frozen framework atoms are returned as 0. */
+#define VSSR_FC_CONSTRAINED_GRAD 1
 size_t vssr_painn_filter_cache_bytes(int32_t n_models, int32_t n0, int64_t e_cap0);
+size_t vssr_painn_filter_cache_workspace_bytes(int32_t n0, int64_t e_cap0);   /* scratch for the build */
 int vssr_painn_filter_cache_build(const float* weights, int32_t n_models, const float* pos0 /*[n0,3]*/,
                                   const float* cell /*[3,3]*/, const uint8_t* pbc /*[3]*/,
                                   const uint8_t* fixed0 /*[n0]*/, int32_t n0, float cutoff, float skin,
@@ -147,8 +156,8 @@ int vssr_painn_relax(const float* weights, int32_t n_models, double* pos /*[A,3]
                      const float* cell, const uint8_t* pbc, const double* offset_ev,
                      int32_t n_struct, int32_t n_atoms, int32_t max_atoms_per_struct, float cutoff, float skin,
                      int32_t relax_steps, double fmax, int64_t e_cap,
-                     const void* filter_cache, int32_t fc_n0, int64_t fc_e_cap0, void* workspace,
-                     size_t workspace_bytes, double* out /*[B,8]*/, float* forces /*[A,3]*/,
+                     const void* filter_cache, int32_t fc_n0, int64_t fc_e_cap0, int32_t fc_flags,
+                     void* workspace, size_t workspace_bytes, double* out /*[B,8]*/, float* forces /*[A,3]*/,
                      float* forces_std /*[A,3] or NULL*/, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -31,10 +31,11 @@ SIGNATURES = {
     "vssr_painn_weight_floats": (c_i64, []),
     "vssr_painn_workspace_bytes": (c_size_t, [c_int, c_int, c_i64]),
     "vssr_painn_filter_cache_bytes": (c_size_t, [c_int, c_int, c_i64]),
+    "vssr_painn_filter_cache_workspace_bytes": (c_size_t, [c_int, c_i64]),
     "vssr_painn_filter_cache_build": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                               c_float, c_i64, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p]),
     "vssr_painn_energy_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                       c_void_p, c_void_p, c_void_p, c_i64, c_float, c_void_p, c_int, c_i64, c_void_p, c_size_t,
+                                       c_void_p, c_void_p, c_void_p, c_i64, c_float, c_void_p, c_int, c_i64, c_int, c_void_p, c_size_t,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "vssr_ensemble_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -46,7 +47,7 @@ SIGNATURES = {
     "vssr_painn_relax_workspace_bytes": (c_size_t, [c_int, c_int, c_i64]),
     "vssr_painn_relax": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_double, c_i64, c_void_p, c_int,
-                                 c_i64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_i64, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vssr_classical_smem_bytes": (c_size_t, [c_int, c_int]),
     "vssr_classical_energy_forces": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

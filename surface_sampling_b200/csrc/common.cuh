@@ -10,7 +10,7 @@ extern long long g_vssr_launches;  // defined in api.cu
 // Kernel classes for the optional per-class CUDA-event profile (bench.py roofline).
 enum VssrKernelClass {
   VSSR_K_NBR = 0, VSSR_K_GEOM, VSSR_K_GEMM, VSSR_K_MSG_FWD, VSSR_K_MSG_BWD, VSSR_K_ELEMWISE, VSSR_K_READOUT,
-  VSSR_K_ENSEMBLE, VSSR_K_FIRE, VSSR_K_CLASSICAL, VSSR_K_NCLASS
+  VSSR_K_ENSEMBLE, VSSR_K_FIRE, VSSR_K_CLASSICAL, VSSR_K_MSG_FWD_MEMO, VSSR_K_MSG_BWD_MEMO, VSSR_K_NCLASS
 };
 void vssr_prof_begin(int cls, cudaStream_t st);  // no-ops unless vssr_profile_enable(1)
 void vssr_prof_end(int cls, cudaStream_t st);

@@ -203,13 +203,16 @@ __global__ void to_float_kernel(const double* __restrict__ src, long long n, flo
 }
 
 // out[b] = [E (clamped), E_std, raw E, max|F|, nsteps, converged, oob, n_evals]
+// max|F| is taken over ALL atoms of the last evaluation's raw forces (calc.results["forces"], mcmc/dynamics.py:155)
 __global__ void relax_finalize_kernel(const double* __restrict__ e_mean, const double* __restrict__ e_std,
-                                      const double* __restrict__ state, int B, double* __restrict__ out) {
+                                      const double* __restrict__ state, const float* __restrict__ forces,
+                                      const int32_t* __restrict__ atom_ptr, int B, double* __restrict__ out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const double* s = state + 8 * b;
   const double e = e_mean[b];
-  const double fmx = s[7];
+  double fmx = 0.0;
+  for (int k = 3 * atom_ptr[b]; k < 3 * atom_ptr[b + 1]; ++k) fmx = fmax(fmx, fabs((double)forces[k]));
   const bool oob = fabs(e) > 1000.0 || fmx > 1000.0;  // mcmc/dynamics.py:159
   double* o = out + 8 * b;
   o[0] = oob ? 1000.0 : e;
@@ -306,7 +309,8 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
                                 const double* offset_ev, int32_t n_struct, int32_t n_atoms,
                                 int32_t max_atoms_per_struct, float cutoff, float skin,
                                 int32_t relax_steps, double fmax, int64_t e_cap, const void* filter_cache,
-                                int32_t fc_n0, int64_t fc_e_cap0, void* workspace, size_t workspace_bytes,
+                                int32_t fc_n0, int64_t fc_e_cap0, int32_t fc_flags, void* workspace,
+                                size_t workspace_bytes,
                                 double* out, float* forces, float* forces_std,
                                 int32_t* status, void* stream) {
   if (!weights || !pos || !z || !fixed || !atom_ptr || !cell || !pbc || !workspace || !out || !forces || !status)
@@ -323,9 +327,12 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
     return rc;
   if ((rc = vssr_fire_init(w.state, w.vel, n_struct, n_atoms, stream))) return rc;
   for (int it = 0; it <= relax_steps; ++it) {
+    // the last evaluation is the one whose raw forces on ALL atoms feed the out-of-bounds test
+    // (mcmc/dynamics.py:155-159): it always computes the full gradient
+    const int32_t flags_it = it == relax_steps ? (fc_flags & ~VSSR_FC_CONSTRAINED_GRAD) : fc_flags;
     if ((rc = vssr_painn_energy_grad(weights, n_models, w.pos32, z, atom_ptr, cell, n_struct, n_atoms,
                                      max_atoms_per_struct, w.rowptr,
-                                     w.col, w.shift, e_cap, cutoff, filter_cache, fc_n0, fc_e_cap0, w.painn, w.painn_bytes, w.energy,
+                                     w.col, w.shift, e_cap, cutoff, filter_cache, fc_n0, fc_e_cap0, flags_it, w.painn, w.painn_bytes, w.energy,
                                      w.grad, nullptr,
                                      stream)))
       return rc;
@@ -337,6 +344,6 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
                              stream)))
       return rc;
   }
-  VSSR_PROF(VSSR_K_FIRE, st, relax_finalize_kernel<<<ceil_div(n_struct, 128), 128, 0, st>>>(w.e_mean, w.e_std, w.state, n_struct, out));
+  VSSR_PROF(VSSR_K_FIRE, st, relax_finalize_kernel<<<ceil_div(n_struct, 128), 128, 0, st>>>(w.e_mean, w.e_std, w.state, forces, atom_ptr, n_struct, out));
   return VSSR_OK;
 }

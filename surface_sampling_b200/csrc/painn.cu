@@ -209,14 +209,16 @@ int run_gemm(GemmArgs g, const float* Bkn, int ldb_kn, const float* Bnk, int n_m
 // One warp per receiver atom; lanes over the row in chunks of 32.  Edges inside the model cutoff
 // are COMPACTED to the front of the row (order preserved: ballot + popc), nvalid[i] of them:
 // one 384-byte record per edge, erec[e][96 floats]:
-//   [0..3]   (ux,uy,uz,d)   [4] sender (global atom index)  [5] filter-memo slot or -1  [6] (j_local,S) key  [7] pad
+//   [0..3]   (ux,uy,uz,d)   [4] sender (global atom index)  [5] -1  [6] (j_local,S) key  [7] 1/d
 //   [8..51]  (rbf_n*env) duplicated as pairs (v,v) for n=1..20, then (env,env),(denv,denv)
 //   [52..91] d(rbf_n*env)/dd duplicated as pairs                              [92..95] pad
-// (a record is what one warp prefetches with a single cp.async per lane)
+// (a record is what one warp prefetches with a single cp.async per lane).  Edges whose filter is memoised
+// (see FilterCacheView) go to a second compact list of 32-byte records mrec[e][8], nmemo[i] per row.
 // The pair duplication feeds the packed FFMA2 path (sm_100 fma.rn.f32x2) without register moves.
 // grad0[a] = excluded-volume gradient (same for every model); evex[a] its energy.
 // ------------------------------------------------------------------------------------------
 constexpr int REC = 96, REC_EJ = 4, REC_SLOT = 5, REC_RE = 8, REC_DRE = 52;
+constexpr int MREC = 8;   // memoised-edge record: (ux,uy,uz,d), sender, slot, 1/d, pad
 
 // Radial-filter memo ("frozen-pair cache").  The filter w(d) = Wd.(rbf(d)*env(d)) + bd*env(d) and its
 // derivative q(d) depend on the edge only through the scalar d.  In VSSR-MC every chain shares the same
@@ -235,14 +237,15 @@ struct FilterCacheView {
   const float* d;            // [E0] fp32 distance of the framework edge
   const float* wc;           // [M*3][nslots_cap][384]
   const float* qc;           // [M*3][nslots_cap][384]
+  const uint8_t* frozen;     // [n0] framework atoms flagged frozen (FixAtoms)
 };
 
 __global__ void __launch_bounds__(128) edge_geometry_kernel(
     const float* __restrict__ pos, const int32_t* __restrict__ atom_ptr, const float* __restrict__ cell, int n_struct,
     int n_atoms, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const int8_t* __restrict__ shift, long long e_cap, float cutoff, FilterCacheView fc,
-    int32_t* __restrict__ nvalid, float* __restrict__ erec, int32_t* __restrict__ eslot, float* __restrict__ evex,
-    float* __restrict__ grad0) {
+    int32_t* __restrict__ nvalid, float* __restrict__ erec, int32_t* __restrict__ nmemo, float* __restrict__ mrec,
+    float* __restrict__ evex, float* __restrict__ grad0) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n_atoms) return;
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
   if (i - a0 < fc.n0) { f0 = __ldg(fc.rowptr + (i - a0)); f1 = f0 + __ldg(fc.nvalid + (i - a0)); }
   const float pi_over_rc = 3.14159265358979323846f / cutoff;
   float ev = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-  int nv = 0;
+  int nv = 0, nm = 0;   // direct / memoised edges of this row
   for (long long base = e0; base < e1; base += 32) {
     const long long e = base + lane;
     bool valid = false;
@@ -283,15 +286,11 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
       dp = sqrtf(d2p);
       valid = dp <= cutoff;
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    // filter memo lookup: same (j_local, S) in the framework row AND bit-identical distance
+    float d = 0.f;
+    int slot = -1;
     if (valid) {
-      const long long w = e0 + nv + __popc(mask & ((1u << lane) - 1u));
-      const float d = sqrtf((rx * rx + 1e-10f) + (ry * ry + 1e-10f) + (rz * rz + 1e-10f));
-      const float inv_d = 1.0f / d;
-      const float ux = rx * inv_d, uy = ry * inv_d, uz = rz * inv_d;
-      float* rec = erec + w * REC;
-      // filter memo lookup: same (j_local, S) in the framework row AND bit-identical distance
-      int slot = -1;
+      d = sqrtf((rx * rx + 1e-10f) + (ry * ry + 1e-10f) + (rz * rz + 1e-10f));
       if (key >= 0 && j - a0 < fc.n0) {
         int lo = f0, hi = f1;
         while (lo < hi) {
@@ -301,35 +300,50 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
         if (lo < f1 && __ldg(fc.key + lo) == key && __float_as_int(__ldg(fc.d + lo)) == __float_as_int(d))
           slot = __ldg(fc.slot + lo);
       }
-      eslot[w] = slot;
-      *reinterpret_cast<float4*>(rec) = make_float4(ux, uy, uz, d);
-      *reinterpret_cast<float4*>(rec + 4) = make_float4(__int_as_float(j), __int_as_float(slot), __int_as_float(key), 0.f);
-      float env = 0.f, denv = 0.f;
-      const bool inside = d < cutoff && slot < 0;   // memoised edges never read their rbf rows
-      if (inside) {
-        float sn, cs;
-        sincosf(pi_over_rc * d, &sn, &cs);
-        env = 0.5f * (cs + 1.0f);
-        denv = -0.5f * pi_over_rc * sn;
-      }
-      float2* rrow = reinterpret_cast<float2*>(rec + REC_RE);
-      float2* drow = reinterpret_cast<float2*>(rec + REC_DRE);
-#pragma unroll
-      for (int n = 0; n < NRBF; ++n) {
-        float r = 0.f, dr = 0.f;
+    }
+    const bool is_memo = valid && slot >= 0, is_direct = valid && slot < 0;
+    const unsigned mask_m = __ballot_sync(0xffffffffu, is_memo), mask_d = __ballot_sync(0xffffffffu, is_direct);
+    if (valid) {
+      const float inv_d = 1.0f / d;
+      const float ux = rx * inv_d, uy = ry * inv_d, uz = rz * inv_d;
+      if (is_memo) {
+        // memoised edges: 32-byte record (unit, d, sender, slot), own compact list
+        const long long w = e0 + nm + __popc(mask_m & ((1u << lane) - 1u));
+        float4* mr = reinterpret_cast<float4*>(mrec + w * MREC);
+        mr[0] = make_float4(ux, uy, uz, d);
+        mr[1] = make_float4(__int_as_float(j), __int_as_float(slot), inv_d, 0.f);
+      } else {
+        const long long w = e0 + nv + __popc(mask_d & ((1u << lane) - 1u));
+        float* rec = erec + w * REC;
+        *reinterpret_cast<float4*>(rec) = make_float4(ux, uy, uz, d);
+        *reinterpret_cast<float4*>(rec + 4) = make_float4(__int_as_float(j), __int_as_float(-1), __int_as_float(key), inv_d);
+        float env = 0.f, denv = 0.f;
+        const bool inside = d < cutoff;
         if (inside) {
-          const float coef = (float)(n + 1) * pi_over_rc;
           float sn, cs;
-          sincosf(coef * d, &sn, &cs);
-          r = sn * inv_d;
-          dr = (coef * cs - r) * inv_d;
+          sincosf(pi_over_rc * d, &sn, &cs);
+          env = 0.5f * (cs + 1.0f);
+          denv = -0.5f * pi_over_rc * sn;
         }
-        const float a = r * env, bq = dr * env + r * denv;
-        rrow[n] = make_float2(a, a);
-        drow[n] = make_float2(bq, bq);
+        float2* rrow = reinterpret_cast<float2*>(rec + REC_RE);
+        float2* drow = reinterpret_cast<float2*>(rec + REC_DRE);
+#pragma unroll
+        for (int n = 0; n < NRBF; ++n) {
+          float r = 0.f, dr = 0.f;
+          if (inside) {
+            const float coef = (float)(n + 1) * pi_over_rc;
+            float sn, cs;
+            sincosf(coef * d, &sn, &cs);
+            r = sn * inv_d;
+            dr = (coef * cs - r) * inv_d;
+          }
+          const float a = r * env, bq = dr * env + r * denv;
+          rrow[n] = make_float2(a, a);
+          drow[n] = make_float2(bq, bq);
+        }
+        rrow[20] = make_float2(env, env);
+        rrow[21] = make_float2(denv, denv);
       }
-      rrow[20] = make_float2(env, env);
-      rrow[21] = make_float2(denv, denv);
       // excluded volume (sigma/d)^12 on the plain distance
       const float q = 1.5f / dp;
       const float q2 = q * q, q4 = q2 * q2;
@@ -338,11 +352,13 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
       const float gg = 24.0f * vex / dp;      // -2 * dvex/dd : edge A and its reverse B
       gx += gg * ux; gy += gg * uy; gz += gg * uz;
     }
-    nv += __popc(mask);
+    nv += __popc(mask_d);
+    nm += __popc(mask_m);
   }
   ev = warp_sum(ev); gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
   if (lane == 0) {
     nvalid[i] = nv;
+    nmemo[i] = nm;
     evex[i] = ev;
     grad0[3 * i] = gx; grad0[3 * i + 1] = gy; grad0[3 * i + 2] = gz;
   }
@@ -680,6 +696,7 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
 // ---- filter memo construction (one-time per framework + weights) ----
 struct CacheBlob {
   int32_t* rowptr; int32_t* nvalid; int32_t* key; int32_t* slot; float* d; float* wc; float* qc; int32_t* counter;
+  uint8_t* frozen;   // [n0] copy of fixed0
   size_t bytes;
 };
 CacheBlob carve_cache(void* base, int M, int n0, long long e_cap0) {
@@ -696,6 +713,7 @@ CacheBlob carve_cache(void* base, int M, int n0, long long e_cap0) {
   c.slot = (int32_t*)take((size_t)e_cap0 * 4);
   c.d = (float*)take((size_t)e_cap0 * 4);
   c.counter = (int32_t*)take(4);
+  c.frozen = (uint8_t*)take((size_t)n0);
   c.wc = (float*)take((size_t)M * NCONV * e_cap0 * F3 * 4);
   c.qc = (float*)take((size_t)M * NCONV * e_cap0 * F3 * 4);
   c.bytes = off;
@@ -706,7 +724,7 @@ FilterCacheView cache_view(const void* blob, int M, int n0, long long e_cap0) {
   if (!blob || n0 <= 0) return v;
   CacheBlob c = carve_cache(const_cast<void*>(blob), M, n0, e_cap0);
   v.n0 = n0; v.nslots_cap = (int)e_cap0; v.rowptr = c.rowptr; v.nvalid = c.nvalid; v.key = c.key; v.slot = c.slot;
-  v.d = c.d; v.wc = c.wc; v.qc = c.qc;
+  v.d = c.d; v.wc = c.wc; v.qc = c.qc; v.frozen = c.frozen;
   return v;
 }
 
@@ -759,7 +777,7 @@ __global__ void __launch_bounds__(128) cache_fill_kernel(const float* __restrict
 
 struct Workspace {
   // edge records (compacted per row by edge_geometry_kernel)
-  int32_t* nvalid; float* erec; int32_t* eslot; float* evex; float* grad0; float* gradp;
+  int32_t* nvalid; float* erec; int32_t* nmemo; float* mrec; float* evex; float* grad0; float* gradp;
   // activations
   float* s[NCONV + 1];      // [M,A,128]
   float* v[NCONV + 1];      // [M,A,3,128]  (v[0] unused: zeros)
@@ -782,7 +800,8 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
   const size_t MA = (size_t)M * (size_t)A;
   w.nvalid = reinterpret_cast<int32_t*>(take(A));
   w.erec = take((size_t)e_cap * REC);
-  w.eslot = reinterpret_cast<int32_t*>(take((size_t)e_cap));
+  w.nmemo = reinterpret_cast<int32_t*>(take(A));
+  w.mrec = take((size_t)e_cap * MREC);
   w.evex = take(A);
   w.grad0 = take((size_t)A * 3);
   w.gradp = take(MA * 2 * 3);
@@ -813,8 +832,9 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
                                       const int32_t* atom_ptr, const float* cell, int32_t n_struct, int32_t n_atoms,
                                       int32_t max_atoms_per_struct, const int32_t* rowptr, const int32_t* col,
                                       const int8_t* shift, int64_t e_cap, float cutoff, const void* filter_cache,
-                                      int32_t fc_n0, int64_t fc_e_cap0, void* workspace, size_t workspace_bytes,
-                                      double* energy, float* grad, float* embedding, void* stream) {
+                                      int32_t fc_n0, int64_t fc_e_cap0, int32_t fc_flags, void* workspace,
+                                      size_t workspace_bytes, double* energy, float* grad, float* embedding,
+                                      void* stream) {
   if (!weights || !pos || !z || !atom_ptr || !cell || !rowptr || !col || !shift || !workspace || !energy || !grad)
     return VSSR_ERR_ARG;
   if (n_models <= 0 || n_struct <= 0 || n_atoms <= 0) return VSSR_ERR_ARG;
@@ -829,22 +849,46 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   // message kernels: shared-memory staged FFMA2 path when every structure fits, else global-gather path
   const int nmax = max_atoms_per_struct;
   const FilterCacheView fc = cache_view(filter_cache, n_models, fc_n0, fc_e_cap0);
-  const size_t smem_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4 + MSG_PIPE_BYTES_FWD, smem_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4 + MSG_PIPE_BYTES_FWD;
-  const size_t smem_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4 + MSG_PIPE_BYTES_BWD, smem_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4 + MSG_PIPE_BYTES_BWD;
+  // staged rows of one structure (memo pass) + the per-warp record rings (direct pass)
+  const size_t st_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4, st_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4;
+  const size_t st_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4, st_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4;
+  const size_t smem_fwd0 = st_fwd0 + MSG_PIPE_BYTES, smem_fwd = st_fwd + MSG_PIPE_BYTES;
+  const size_t smem_bwd0 = st_bwd0 + MSG_PIPE_BYTES, smem_bwd = st_bwd + MSG_PIPE_BYTES;
   const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
+  const bool memo = staged && fc.n0 > 0;   // two passes: memoised edges (light kernels), then direct edges
+  const bool constrained = memo && (fc_flags & VSSR_FC_CONSTRAINED_GRAD);   // no dE/dx wanted on frozen atoms
   const int n_chunks = 2;
   const dim3 v2_grid(n_struct * n_chunks, F / MSG_FC, M);
+  const dim3 memo_grid(n_struct, F / MSG_FC, M);
+  const size_t memo_ring = (size_t)(MEMO_THREADS_FWD / 32) * MEMO_RING_BYTES_PER_WARP;
+  const size_t sm_fwd0 = st_fwd0 + memo_ring, sm_fwd = st_fwd + memo_ring;
+  const size_t sm_state = (size_t)nmax * MEMO_STATE_PER * 4 + memo_ring;
   if (staged) {
-    static size_t cfg[4] = {0, 0, 0, 0};
-    if (smem_fwd0 > cfg[0]) { VSSR_CUDA(cudaFuncSetAttribute(message_fwd_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd0)); cfg[0] = smem_fwd0; }
-    if (smem_fwd > cfg[1]) { VSSR_CUDA(cudaFuncSetAttribute(message_fwd_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd)); cfg[1] = smem_fwd; }
-    if (smem_bwd0 > cfg[2]) { VSSR_CUDA(cudaFuncSetAttribute(message_bwd_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd0)); cfg[2] = smem_bwd0; }
-    if (smem_bwd > cfg[3]) { VSSR_CUDA(cudaFuncSetAttribute(message_bwd_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd)); cfg[3] = smem_bwd; }
+    static size_t cfg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto want = [&](int k, const void* fn, size_t bytes) -> int {
+      if (bytes > cfg[k]) {
+        VSSR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cfg[k] = bytes;
+      }
+      return VSSR_OK;
+    };
+    int rc0;
+    if ((rc0 = want(0, (const void*)message_fwd_v2<true>, smem_fwd0))) return rc0;
+    if ((rc0 = want(1, (const void*)message_fwd_v2<false>, smem_fwd))) return rc0;
+    if ((rc0 = want(2, (const void*)message_bwd_v2<true>, smem_bwd0))) return rc0;
+    if ((rc0 = want(3, (const void*)message_bwd_v2<false>, smem_bwd))) return rc0;
+    if (memo) {
+      if ((rc0 = want(4, (const void*)message_fwd_memo<true>, sm_fwd0))) return rc0;
+      if ((rc0 = want(5, (const void*)message_fwd_memo<false>, sm_fwd))) return rc0;
+      if ((rc0 = want(6, (const void*)message_bwd_memo<true>, st_bwd0))) return rc0;
+      if ((rc0 = want(7, (const void*)message_bwd_memo<false>, st_bwd))) return rc0;
+      if ((rc0 = want(8, (const void*)message_bwd_memo_state, sm_state))) return rc0;
+    }
   }
 
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(
       pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, staged ? fc : FilterCacheView{},
-      w.nvalid, w.erec, w.eslot, w.evex, w.grad0));
+      w.nvalid, w.erec, w.nmemo, w.mrec, w.evex, w.grad0));
   VSSR_PROF(VSSR_K_ELEMWISE, st, embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]));
 
   int rc;
@@ -861,14 +905,21 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if ((rc = run_gemm<128, 0, 1>(g, wl + L_W2T, F3, wl + L_W2, M, st))) return rc;
     // F3
     if (staged) {
-      if (l == 0)
+      if (l == 0) {
+        if (memo)
+          VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<true><<<memo_grid, MEMO_THREADS_FWD, sm_fwd0, st>>>(
+              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.eslot, fc, w.phi[l], w.s[l], nullptr,
-            w.cat[l], w.vmid[l]));
-      else
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
+            w.cat[l], w.vmid[l], memo ? 1 : 0));
+      } else {
+        if (memo)
+          VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<false><<<memo_grid, MEMO_THREADS_FWD, sm_fwd, st>>>(
+              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.eslot, fc, w.phi[l], w.s[l], w.v[l],
-            w.cat[l], w.vmid[l]));
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
+            w.cat[l], w.vmid[l], memo ? 1 : 0));
+      }
     } else {
       if (l == 0)
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<true><<<msg_grid, 128, 0, st>>>(
@@ -939,14 +990,25 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if ((rc = run_gemm<128, 0, 3>(g, wl + L_UV, F, wl + L_UVT, M, st))) return rc;
     // B3
     if (staged) {
-      if (l == 0)
+      // accum bit 0: dphi/dv_in were started by a memo pass; bit 1: so was gradp
+      if (l == 0) {
+        if (memo && !constrained)
+          VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<true><<<memo_grid, MEMO_THREADS_BWD, st_bwd0, st>>>(
+              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp));
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.eslot, fc, w.phi[l], nullptr, w.ds,
-            dv_cur, nullptr, nullptr, w.gradp));
-      else
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
+            dv_cur, nullptr, nullptr, w.gradp, (memo && !constrained) ? 3 : 0));
+      } else {
+        if (constrained)
+          VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo_state<<<memo_grid, MEMO_THREADS_FWD, sm_state, st>>>(
+              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt));
+        else if (memo)
+          VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<false><<<memo_grid, MEMO_THREADS_BWD, st_bwd, st>>>(
+              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.eslot, fc, w.phi[l], w.v[l], w.ds,
-            dv_cur, w.dphi, dv_nxt, w.gradp));
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
+            dv_cur, w.dphi, dv_nxt, w.gradp, constrained ? 1 : (memo ? 3 : 0)));
+      }
       VSSR_PROF(VSSR_K_ELEMWISE, st, grad_accum_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.gradp, 3 * A, grad));
     } else {
       if (l == 0)
@@ -970,11 +1032,45 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       float* t = dv_cur; dv_cur = dv_nxt; dv_nxt = t;
     }
   }
+  if (constrained)
+    VSSR_PROF(VSSR_K_ELEMWISE, st, zero_frozen_grad_kernel<<<dim3(ceil_div(A, 256), M), 256, 0, st>>>(
+        atom_ptr, n_struct, A, fc.n0, fc.frozen, grad));
   return VSSR_OK;
 }
 
 extern "C" size_t vssr_painn_filter_cache_bytes(int32_t n_models, int32_t n0, int64_t e_cap0) {
   return carve_cache(nullptr, n_models, n0, e_cap0).bytes;
+}
+
+namespace {
+// scratch of the memo build: one-structure neighbour list + the geometry kernel's outputs
+struct CacheScratch {
+  int32_t *atom_ptr, *deg, *col, *status, *nmemo;
+  int8_t* shift;
+  float *erec, *mrec, *evex, *grad0;
+  size_t bytes;
+};
+CacheScratch carve_cache_scratch(void* base, int n0, long long e_cap0) {
+  size_t off = 0;
+  auto take = [&](size_t nbytes) -> void* { void* p = reinterpret_cast<char*>(base) + off; off += ((nbytes + 255) / 256) * 256; return p; };
+  CacheScratch s;
+  s.atom_ptr = (int32_t*)take(8);
+  s.deg = (int32_t*)take((size_t)n0 * 4);
+  s.col = (int32_t*)take((size_t)e_cap0 * 4);
+  s.shift = (int8_t*)take((size_t)e_cap0 * 4);
+  s.status = (int32_t*)take(4);
+  s.erec = (float*)take((size_t)e_cap0 * REC * 4);
+  s.nmemo = (int32_t*)take((size_t)n0 * 4);
+  s.mrec = (float*)take((size_t)e_cap0 * MREC * 4);
+  s.evex = (float*)take((size_t)n0 * 4);
+  s.grad0 = (float*)take((size_t)n0 * 12);
+  s.bytes = off;
+  return s;
+}
+}  // namespace
+
+extern "C" size_t vssr_painn_filter_cache_workspace_bytes(int32_t n0, int64_t e_cap0) {
+  return carve_cache_scratch(nullptr, n0, e_cap0).bytes;
 }
 
 extern "C" int vssr_painn_filter_cache_build(const float* weights, int32_t n_models, const float* pos0, const float* cell,
@@ -984,28 +1080,21 @@ extern "C" int vssr_painn_filter_cache_build(const float* weights, int32_t n_mod
   if (!weights || !pos0 || !cell || !pbc || !fixed0 || !cache || !workspace || n0 <= 0 || n_models <= 0) return VSSR_ERR_ARG;
   CacheBlob c = carve_cache(cache, n_models, n0, e_cap0);
   if (c.bytes > cache_bytes) return VSSR_ERR_WORKSPACE;
-  // scratch: atom_ptr[2], deg[n0], col[e_cap0], shift[e_cap0*4], status, erec[e_cap0*REC], eslot, evex, grad0
-  size_t off = 0;
-  auto take = [&](size_t nbytes) -> void* { void* p = reinterpret_cast<char*>(workspace) + off; off += ((nbytes + 255) / 256) * 256; return p; };
-  int32_t* atom_ptr = (int32_t*)take(8);
-  int32_t* deg = (int32_t*)take((size_t)n0 * 4);
-  int32_t* col = (int32_t*)take((size_t)e_cap0 * 4);
-  int8_t* shift = (int8_t*)take((size_t)e_cap0 * 4);
-  int32_t* status = (int32_t*)take(4);
-  float* erec = (float*)take((size_t)e_cap0 * REC * 4);
-  int32_t* eslot = (int32_t*)take((size_t)e_cap0 * 4);
-  float* evex = (float*)take((size_t)n0 * 4);
-  float* grad0 = (float*)take((size_t)n0 * 12);
-  if (off > workspace_bytes) return VSSR_ERR_WORKSPACE;
+  const CacheScratch sc = carve_cache_scratch(workspace, n0, e_cap0);
+  if (sc.bytes > workspace_bytes) return VSSR_ERR_WORKSPACE;
+  int32_t *atom_ptr = sc.atom_ptr, *deg = sc.deg, *col = sc.col, *status = sc.status, *nmemo = sc.nmemo;
+  int8_t* shift = sc.shift;
+  float *erec = sc.erec, *mrec = sc.mrec, *evex = sc.evex, *grad0 = sc.grad0;
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t ptr_h[2] = {0, n0};
   VSSR_CUDA(cudaMemcpyAsync(atom_ptr, ptr_h, 8, cudaMemcpyHostToDevice, st));
   VSSR_CUDA(cudaMemsetAsync(status, 0, 4, st));
   VSSR_CUDA(cudaMemsetAsync(c.slot, 0xFF, (size_t)e_cap0 * 4, st));
+  VSSR_CUDA(cudaMemcpyAsync(c.frozen, fixed0, (size_t)n0, cudaMemcpyDeviceToDevice, st));
   int rc = vssr_nbr_build(pos0, atom_ptr, cell, pbc, 1, n0, cutoff + skin, deg, c.rowptr, col, shift, e_cap0, status, stream);
   if (rc) return rc;
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(n0, 4), 128, 0, st>>>(
-      pos0, atom_ptr, cell, 1, n0, c.rowptr, col, shift, (long long)e_cap0, cutoff, FilterCacheView{}, c.nvalid, erec, eslot,
+      pos0, atom_ptr, cell, 1, n0, c.rowptr, col, shift, (long long)e_cap0, cutoff, FilterCacheView{}, c.nvalid, erec, nmemo, mrec,
       evex, grad0));
   VSSR_PROF(VSSR_K_GEOM, st, cache_slot_kernel<<<1, 32, 0, st>>>(erec, c.rowptr, c.nvalid, fixed0, n0, c.key, c.slot, c.d, c.counter));
   VSSR_PROF(VSSR_K_GEOM, st, cache_fill_kernel<<<dim3((unsigned)e_cap0, n_models * NCONV), 128, 0, st>>>(

@@ -112,6 +112,7 @@ class Batch:
     n_struct: int
     n_atoms: int
     atom_ptr_host: np.ndarray
+    fixed_host: np.ndarray | None = None   # host copy of `fixed` (contract checks only)
 
     @property
     def cell32(self):
@@ -149,7 +150,8 @@ class Batch:
         ptr = np.asarray(ptr, dtype=np.int32)
         return Batch(pos=up(pos, torch.float64), z=up(z, torch.int32), fixed=up(fixed, torch.uint8),
                      atom_ptr=up(ptr, torch.int32), cell=up(cell, torch.float64), pbc=up(pbc, torch.uint8),
-                     n_struct=len(ptr) - 1, n_atoms=int(ptr[-1]), atom_ptr_host=ptr.copy())
+                     n_struct=len(ptr) - 1, n_atoms=int(ptr[-1]), atom_ptr_host=ptr.copy(),
+                     fixed_host=np.asarray(fixed).astype(bool))
 
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.pos, self.z, self.fixed, self.atom_ptr, self.cell, self.pbc))
@@ -213,12 +215,18 @@ class PainnEngine:
         self._ws_relax = _Workspace()
         self._fc = None          # (blob tensor, n0, e_cap0, nslots) of the frozen-pair filter memo
 
-    def set_framework(self, pos0, cell, pbc, fixed0) -> int:
+    def set_framework(self, pos0, cell, pbc, fixed0, constrained_forces: bool = False) -> int:
         """Build the radial-filter memo for a frozen framework shared by every structure (its atoms must
         be the FIRST n0 atoms of each structure, as in VSSR-MC where adsorbates are appended).  Edges
         whose distance is bitwise equal to a framework edge between two frozen atoms reuse the memoised
         filter rows instead of re-evaluating 2x60 FMAs per feature; anything else is computed as usual,
-        so correctness never depends on this call.  Returns the number of memoised pairs."""
+        so correctness never depends on this call.  Returns the number of memoised pairs.
+
+        constrained_forces=True (VSSR_FC_CONSTRAINED_GRAD) additionally declares that the frozen atoms
+        carry FixAtoms, as in every VSSR-MC relaxation (mcmc/dynamics.py:25-141 -> ASE zeroes their
+        forces): dE/dx of those atoms is then not computed at all (their force rows come back as 0),
+        which removes the whole position-gradient branch of every memoised edge.  Energies and the
+        forces of all other atoms are unchanged."""
         lib, dev = self.lib, self.device
         pos0 = np.ascontiguousarray(pos0, dtype=np.float32)
         n0 = len(pos0)
@@ -227,7 +235,7 @@ class PainnEngine:
         e_cap0 = int(col.numel()) + 8
         nbytes = int(lib.vssr_painn_filter_cache_bytes(self.n_models, n0, e_cap0))
         blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        ws = torch.empty(e_cap0 * (96 * 4 + 16) + n0 * 64 + 8192, dtype=torch.uint8, device=dev)
+        ws = torch.empty(int(lib.vssr_painn_filter_cache_workspace_bytes(n0, e_cap0)), dtype=torch.uint8, device=dev)
         d_pos = torch.from_numpy(pos0).to(dev)
         d_cell = torch.from_numpy(np.ascontiguousarray(cell, dtype=np.float32)).to(dev)
         d_pbc = torch.from_numpy(np.ascontiguousarray(pbc).astype(np.uint8)).to(dev)
@@ -239,7 +247,8 @@ class PainnEngine:
                                                      _ptr(blob), blob.numel(), _ptr(ws), ws.numel(),
                                                      ctypes.addressof(nslots), _stream()),
                    "vssr_painn_filter_cache_build")
-        self._fc = (blob, n0, e_cap0, int(nslots.value))
+        self._fc = (blob, n0, e_cap0, int(nslots.value), 1 if constrained_forces else 0,
+                    np.ascontiguousarray(fixed0).astype(bool))
         return int(nslots.value)
 
     def clear_framework(self):
@@ -247,8 +256,8 @@ class PainnEngine:
 
     def _fc_args(self):
         if self._fc is None:
-            return None, 0, 0
-        return self._fc[0].data_ptr(), self._fc[1], self._fc[2]
+            return None, 0, 0, 0
+        return self._fc[0].data_ptr(), self._fc[1], self._fc[2], self._fc[4]
 
     # -- H5 stoichiometric offset (per structure, host, exact fp64) ---------------------------
     def offsets_ev(self, z_host: np.ndarray, atom_ptr: np.ndarray) -> np.ndarray | None:
@@ -310,6 +319,13 @@ class PainnEngine:
         updated in place.  Returns dict(out[B,8], forces, forces_std, status)."""
         lib, dev = self.lib, self.device
         A, B, M = batch.n_atoms, batch.n_struct, self.n_models
+        if self._fc is not None and self._fc[4] and batch.fixed_host is not None:
+            # VSSR_FC_CONSTRAINED_GRAD contract: the framework's frozen atoms are FixAtoms in every structure
+            frozen = np.flatnonzero(self._fc[5])
+            idx = (batch.atom_ptr_host[:-1, None] + frozen[None, :]).reshape(-1)
+            if (np.diff(batch.atom_ptr_host) < self._fc[1]).any() or not batch.fixed_host[idx].all():
+                raise _lib.VssrError("set_framework(constrained_forces=True): a structure does not hold the framework's "
+                                     "frozen atoms fixed; use constrained_forces=False")
         cap = int(e_cap) if e_cap else A * self.edges_per_atom
         nbytes = int(lib.vssr_painn_relax_workspace_bytes(M, A, cap))
         ws = self._ws_relax.get(nbytes, dev)

@@ -188,6 +188,23 @@ def test_frozen_pair_filter_memo(structures, potentials, sto_weights):
     o1 = memo.relax(b1, relax_steps=10)["out"].cpu().numpy()
     assert np.array_equal(o0[:, 4:], o1[:, 4:]) and np.abs(o0[:, 0] - o1[:, 0]).max() < 1e-4
     assert (b0.pos - b1.pos).abs().max().item() < 1e-5
+    # VSSR_FC_CONSTRAINED_GRAD: no dE/dx for the frozen atoms (FixAtoms discards it anyway); energies and
+    # the force rows of every free atom are the same bits, frozen rows come back as zero, and the
+    # relaxation (which only ever sees constrained forces) is bit-identical
+    cons = engine.PainnEngine(sto_weights, od)
+    cons.set_framework(base["positions"], base["cell"], PBC3, fixed0, constrained_forces=True)
+    b3 = _batch(structs)
+    r3 = cons.energy_forces(b3)
+    assert torch.equal(r3["energy"], r1["energy"])
+    frozen = torch.from_numpy(np.concatenate(fixed)).cuda()
+    assert torch.equal(r3["forces"][~frozen], r1["forces"][~frozen])
+    assert r3["forces"][frozen].abs().max().item() == 0.0 and r3["forces_std"][frozen].abs().max().item() == 0.0
+    b2 = _batch(structs, fixed)
+    o2 = cons.relax(b2, relax_steps=10)["out"].cpu().numpy()
+    assert np.array_equal(o2, o1), (o2 - o1)
+    assert torch.equal(b2.pos, b1.pos), (b2.pos - b1.pos).abs().max().item()
+    with pytest.raises(Exception):          # contract check: the batch must hold the frozen atoms fixed
+        cons.relax(_batch(structs), relax_steps=1)
     # a framework that does not match the batch (shifted atoms) silently disables the memo: same answers
     other = engine.PainnEngine(sto_weights, od)
     other.set_framework(base["positions"] + 0.123, base["cell"], PBC3, fixed0)
