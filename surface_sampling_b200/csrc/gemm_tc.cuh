@@ -185,11 +185,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc_ws_kernel(TcArgs p) {
       for (int c = 0; c < nchunks; ++c, ++gchunk) {
         if (gchunk % WS_STAGES != s) continue;
         const int k0 = c * BK;
+        // A (global -> registers) is requested BEFORE waiting for the stage to drain: the loads need no
+        // shared memory, so their latency overlaps the MMAs still reading this stage
+        constexpr int NQ = (BM / WS_PW) * 8 / 32;   // float4 per lane and chunk (8)
+        float4 x[NQ];
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+          const int idx = lane + u * 32;
+          const int r = part * (BM / WS_PW) + (idx >> 3), ch = idx & 7;
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + r < g.M) x[u] = __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * g.lda + k0) + ch);
+        }
+        float4 av[AMODE == 2 ? 1 : 1];
+        if (AMODE == 2) av[0] = __ldg(reinterpret_cast<const float4*>(avec + k0) + (lane & 7));
         mbar_wait(&empty_bar[s], (use & 1) ^ 1);
         ++use;
         const bool stamp = (warp == 0 && lane == 0 && use <= 2);
         if (stamp) TC_STAMP(use == 1 ? 8 : 12);
-        // B: rows [half*BN/2, +BN/2) of hi and lo, straight to swizzled smem with cp.async
+        // B: rows [part*BN/4, +BN/4) of hi and lo, straight to swizzled smem with cp.async
 #pragma unroll 4
         for (int q = 0; q < (BN / WS_PW) * 8 / 32; ++q) {
           const int idx = lane + q * 32;
@@ -197,42 +210,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc_ws_kernel(TcArgs p) {
           const uint32_t off = swz(r, ch);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sBhi + off)),
                        "l"(Bh + (long long)r * g.K + k0 + ch * 4));
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sBlo + off)),
-                       "l"(Bl + (long long)r * g.K + k0 + ch * 4));
+          if (p.mode != 2)   // mode 2: timing experiment only (wrong results): B_lo not fetched
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sBlo + off)),
+                         "l"(Bl + (long long)r * g.K + k0 + ch * 4));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (stamp) TC_STAMP(use == 1 ? 9 : 13);
-        // A: rows [half*64, +64): registers -> transform -> TF32 split -> swizzled smem
-#pragma unroll 1
-        for (int q0 = 0; q0 < (BM / WS_PW) * 8 / 32; q0 += 8) {
-          float4 x[8];
+        // A: registers -> transform -> TF32 split -> swizzled smem
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int idx = lane + (q0 + u) * 32;
-            const int r = part * (BM / WS_PW) + (idx >> 3), ch = idx & 7;
-            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + r < g.M) x[u] = __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * g.lda + k0) + ch);
+        for (int u = 0; u < NQ; ++u) {
+          const int idx = lane + u * 32;
+          const int r = part * (BM / WS_PW) + (idx >> 3), ch = idx & 7;   // ch == lane & 7
+          float4 v = x[u];
+          if (AMODE == 1) {
+            v.x = swishf_(v.x); v.y = swishf_(v.y); v.z = swishf_(v.z); v.w = swishf_(v.w);
+          } else if (AMODE == 2) {
+            v.x = dswishf_(v.x) * av[0].x; v.y = dswishf_(v.y) * av[0].y; v.z = dswishf_(v.z) * av[0].z; v.w = dswishf_(v.w) * av[0].w;
           }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int idx = lane + (q0 + u) * 32;
-            const int r = part * (BM / WS_PW) + (idx >> 3), ch = idx & 7;
-            float4 v = x[u];
-            if (AMODE == 1) {
-              v.x = swishf_(v.x); v.y = swishf_(v.y); v.z = swishf_(v.z); v.w = swishf_(v.w);
-            } else if (AMODE == 2) {
-              const float4 av = __ldg(reinterpret_cast<const float4*>(avec + k0) + ch);
-              v.x = dswishf_(v.x) * av.x; v.y = dswishf_(v.y) * av.y; v.z = dswishf_(v.z) * av.z; v.w = dswishf_(v.w) * av.w;
-            }
-            float4 hi, lo;
-            hi.x = tf32_rn(v.x); lo.x = tf32_rn(v.x - hi.x);
-            hi.y = tf32_rn(v.y); lo.y = tf32_rn(v.y - hi.y);
-            hi.z = tf32_rn(v.z); lo.z = tf32_rn(v.z - hi.z);
-            hi.w = tf32_rn(v.w); lo.w = tf32_rn(v.w - hi.w);
-            const uint32_t off = swz(r, ch);
-            *reinterpret_cast<float4*>(sAhi + off) = hi;
-            *reinterpret_cast<float4*>(sAlo + off) = lo;
-          }
+          float4 hi, lo;
+          hi.x = tf32_rn(v.x); lo.x = tf32_rn(v.x - hi.x);
+          hi.y = tf32_rn(v.y); lo.y = tf32_rn(v.y - hi.y);
+          hi.z = tf32_rn(v.z); lo.z = tf32_rn(v.z - hi.z);
+          hi.w = tf32_rn(v.w); lo.w = tf32_rn(v.w - hi.w);
+          const uint32_t off = swz(r, ch);
+          *reinterpret_cast<float4*>(sAhi + off) = hi;
+          *reinterpret_cast<float4*>(sAlo + off) = lo;
         }
         if (stamp) TC_STAMP(use == 1 ? 10 : 14);
         asm volatile("cp.async.wait_group 0;" ::: "memory");

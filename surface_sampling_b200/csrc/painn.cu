@@ -778,6 +778,7 @@ __global__ void __launch_bounds__(128) cache_fill_kernel(const float* __restrict
 struct Workspace {
   // edge records (compacted per row by edge_geometry_kernel)
   int32_t* nvalid; float* erec; int32_t* nmemo; float* mrec; float* evex; float* grad0; float* gradp;
+  int32_t* order_d; int32_t* order_m;   // per-structure row order, most direct / memoised edges first
   // activations
   float* s[NCONV + 1];      // [M,A,128]
   float* v[NCONV + 1];      // [M,A,3,128]  (v[0] unused: zeros)
@@ -801,6 +802,8 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
   w.nvalid = reinterpret_cast<int32_t*>(take(A));
   w.erec = take((size_t)e_cap * REC);
   w.nmemo = reinterpret_cast<int32_t*>(take(A));
+  w.order_d = reinterpret_cast<int32_t*>(take(A));
+  w.order_m = reinterpret_cast<int32_t*>(take(A));
   w.mrec = take((size_t)e_cap * MREC);
   w.evex = take(A);
   w.grad0 = take((size_t)A * 3);
@@ -889,6 +892,9 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(
       pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, staged ? fc : FilterCacheView{},
       w.nvalid, w.erec, w.nmemo, w.mrec, w.evex, w.grad0));
+  if (staged)
+    VSSR_PROF(VSSR_K_GEOM, st, row_order_kernel<<<n_struct, 128, (size_t)2 * nmax * sizeof(int32_t), st>>>(
+        atom_ptr, w.nvalid, w.nmemo, w.order_d, w.order_m));
   VSSR_PROF(VSSR_K_ELEMWISE, st, embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]));
 
   int rc;
@@ -908,16 +914,16 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       if (l == 0) {
         if (memo)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<true><<<memo_grid, MEMO_THREADS_FWD, sm_fwd0, st>>>(
-              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
+              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
             w.cat[l], w.vmid[l], memo ? 1 : 0));
       } else {
         if (memo)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<false><<<memo_grid, MEMO_THREADS_FWD, sm_fwd, st>>>(
-              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
+              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
             w.cat[l], w.vmid[l], memo ? 1 : 0));
       }
     } else {
@@ -994,19 +1000,19 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       if (l == 0) {
         if (memo && !constrained)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<true><<<memo_grid, MEMO_THREADS_BWD, st_bwd0, st>>>(
-              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp));
+              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp));
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
             dv_cur, nullptr, nullptr, w.gradp, (memo && !constrained) ? 3 : 0));
       } else {
         if (constrained)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo_state<<<memo_grid, MEMO_THREADS_FWD, sm_state, st>>>(
-              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt));
+              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt));
         else if (memo)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<false><<<memo_grid, MEMO_THREADS_BWD, st_bwd, st>>>(
-              l, A, atom_ptr, rowptr, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));
+              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
+            weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
             dv_cur, w.dphi, dv_nxt, w.gradp, constrained ? 1 : (memo ? 3 : 0)));
       }
       VSSR_PROF(VSSR_K_ELEMWISE, st, grad_accum_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.gradp, 3 * A, grad));

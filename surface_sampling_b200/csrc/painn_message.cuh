@@ -63,6 +63,34 @@ __device__ __forceinline__ void wait_record() {
   __syncwarp();
 }
 
+// Rows (receivers) are handed to warps dynamically, most expensive first (row_order_kernel sorts each
+// structure's rows by edge count): longest-processing-time-first scheduling.  A row is always computed
+// whole by one warp, so the result does not depend on which warp takes it.
+__device__ __forceinline__ int next_row(int* ctr, int lane) {
+  int t = 0;
+  if (lane == 0) t = atomicAdd(ctr, 1);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+// order[a0 + rank] = local index of the row with that rank (cost descending, index ascending on ties)
+__global__ void __launch_bounds__(128) row_order_kernel(const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ cost_a,
+                                                        const int32_t* __restrict__ cost_b, int32_t* __restrict__ order_a,
+                                                        int32_t* __restrict__ order_b) {
+  extern __shared__ int32_t costs[];   // [2][n]
+  const int b = blockIdx.x;
+  const int a0 = atom_ptr[b], n = atom_ptr[b + 1] - a0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) { costs[k] = cost_a[a0 + k]; costs[n + k] = cost_b[a0 + k]; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 2 * n; k += blockDim.x) {
+    const int which = k >= n, il = which ? k - n : k;
+    const int32_t* c = costs + which * n;
+    const int mine = c[il];
+    int rank = 0;
+    for (int o = 0; o < n; ++o) rank += (c[o] > mine) || (c[o] == mine && o < il);
+    (which ? order_b : order_a)[a0 + rank] = il;
+  }
+}
+
 // Walk the memoised edges of one receiver.  Lane l loads record base+l (32 records per sweep, coalesced)
 // and the per-edge fields are broadcast by shuffle; the NK filter-row pairs of an edge are fetched into
 // registers MEMO_DEPTH edges ahead, so the L2 latency of the row gather overlaps the arithmetic of the
@@ -166,10 +194,12 @@ __device__ __forceinline__ void fwd_edge(const float4 g, const float* __restrict
 template <bool FIRST>
 __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
     int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
+    const int32_t* __restrict__ order, const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
     const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
     float* __restrict__ cat, float* __restrict__ v_mid) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ int row_ctr;
+  if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MsgFwdLayout<FIRST>::PER;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, h = blockIdx.y, m = blockIdx.z;
@@ -186,7 +216,8 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
   const int f0 = h * MSG_FC + 2 * lane;
   const float* __restrict__ wbase = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC;
   __syncthreads();
-  for (int il = warp; il < n; il += MEMO_THREADS_FWD / 32) {
+  for (int t = next_row(&row_ctr, lane); t < n; t = next_row(&row_ctr, lane)) {
+    const int il = __ldg(order + a0 + t);
     const int i = a0 + il;
     const float4* mr = reinterpret_cast<const float4*>(mrec + (long long)__ldg(rowptr + i) * MREC);
     const int ne = __ldg(nmemo + i);
@@ -214,10 +245,13 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
 template <bool FIRST>
 __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid, const float* __restrict__ erec,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order, const int32_t* __restrict__ nvalid,
+    const float* __restrict__ erec,
     const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
     float* __restrict__ cat, float* __restrict__ v_mid, int accum) {
   extern __shared__ __align__(16) float smem_all[];
+  __shared__ int row_ctr;
+  if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MsgFwdLayout<FIRST>::PER;
   constexpr int N16 = (REC_RE + 44) / 4;  // 13 x 16 B: geometry + rbf rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -248,7 +282,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
   const float2 bd0 = ld2(wl + L_BD + f0), bd1 = ld2(wl + L_BD + F + f0), bd2 = ld2(wl + L_BD + 2 * F + f0);
   __syncthreads();
 
-  for (int il = ch + n_chunks * warp; il < n; il += n_chunks * MSG_WARPS) {
+  for (int t = ch + n_chunks * next_row(&row_ctr, lane); t < n; t = ch + n_chunks * next_row(&row_ctr, lane)) {
+    const int il = __ldg(order + a0 + t);
     const int i = a0 + il;
     const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
     const int ne = __ldg(nvalid + i);
@@ -416,10 +451,12 @@ __device__ __forceinline__ void bwd_stage(float* smem, const float* phi, const f
 template <bool FIRST>
 __global__ void __launch_bounds__(MEMO_THREADS_BWD, 1) message_bwd_memo(
     int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
+    const int32_t* __restrict__ order, const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
     const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
     const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in, float* __restrict__ gradp) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ int row_ctr;
+  if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MsgBwdLayout<FIRST>::PER;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, h = blockIdx.y, m = blockIdx.z;
@@ -439,7 +476,8 @@ __global__ void __launch_bounds__(MEMO_THREADS_BWD, 1) message_bwd_memo(
   const float* __restrict__ wrow = fc.wc + ml;
   const float* __restrict__ qrow = fc.qc + ml;
   __syncthreads();
-  for (int il = warp; il < n; il += MEMO_THREADS_BWD / 32) {
+  for (int t = next_row(&row_ctr, lane); t < n; t = next_row(&row_ctr, lane)) {
+    const int il = __ldg(order + a0 + t);
     const int i = a0 + il;
     const float4* mr = reinterpret_cast<const float4*>(mrec + (long long)__ldg(rowptr + i) * MREC);
     const int ne = __ldg(nmemo + i);
@@ -471,10 +509,12 @@ __global__ void __launch_bounds__(MEMO_THREADS_BWD, 1) message_bwd_memo(
 constexpr int MEMO_STATE_PER = 4 * MSG_FC;
 __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_bwd_memo_state(
     int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
+    const int32_t* __restrict__ order, const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
     const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
     const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ int row_ctr;
+  if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MEMO_STATE_PER;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, h = blockIdx.y, m = blockIdx.z;
@@ -492,7 +532,8 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_bwd_memo_state(
   stage_rows(smem, PER, MSG_FC, dv, 3 * F, F, 3, n, tid, MEMO_THREADS_FWD);
   const float* __restrict__ wbase = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC;
   __syncthreads();
-  for (int il = warp; il < n; il += MEMO_THREADS_FWD / 32) {
+  for (int t = next_row(&row_ctr, lane); t < n; t = next_row(&row_ctr, lane)) {
+    const int il = __ldg(order + a0 + t);
     const int i = a0 + il;
     const float4* mr = reinterpret_cast<const float4*>(mrec + (long long)__ldg(rowptr + i) * MREC);
     const int ne = __ldg(nmemo + i);
@@ -529,11 +570,14 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_bwd_memo_state(
 template <bool FIRST>
 __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid, const float* __restrict__ erec,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order, const int32_t* __restrict__ nvalid,
+    const float* __restrict__ erec,
     const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
     const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in, float* __restrict__ gradp,
     int accum) {
   extern __shared__ __align__(16) float smem_all[];
+  __shared__ int row_ctr;
+  if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MsgBwdLayout<FIRST>::PER;
   constexpr int N16 = (REC_DRE + 40) / 4;                  // 23 x 16 B: whole record
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -565,7 +609,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
   const float2 bd0 = ld2(wl + L_BD + f0), bd1 = ld2(wl + L_BD + F + f0), bd2 = ld2(wl + L_BD + 2 * F + f0);
   __syncthreads();
 
-  for (int il = ch + n_chunks * warp; il < n; il += n_chunks * MSG_WARPS) {
+  for (int t = ch + n_chunks * next_row(&row_ctr, lane); t < n; t = ch + n_chunks * next_row(&row_ctr, lane)) {
+    const int il = __ldg(order + a0 + t);
     const int i = a0 + il;
     const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
     const int ne = __ldg(nvalid + i);
