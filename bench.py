@@ -193,7 +193,9 @@ def workload_config(args, chains):
     return {"workload": WORKLOADS[args.workload]["desc"], "chains_per_gpu": chains,
             "l2": "per-evaluation working set (activations ~48 KB/atom/model, >1 GB) exceeds the 126 MB L2; no explicit flush"
                   if args.workload == "sto_painn" else "whole relaxation is shared-memory resident; L2 is not on the path",
-            "parallelism": f"chains sharded, {args.gpus} rank(s), no data-path collective"}
+            "parallelism": f"chains sharded, {args.gpus} rank(s), no data-path collective",
+            "e2e_pipeline": f"{max(1, args.groups)} interleaved chain groups per GPU (host MC logic of one group overlaps the "
+                            "relaxation of the other); value = one batch of all chains per step"}
 
 
 def run_reference(args):
@@ -230,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sto_painn", choices=list(WORKLOADS))
     ap.add_argument("--chains-per-gpu", type=int, default=0)
+    ap.add_argument("--groups", type=int, default=2, help="interleaved chain groups of the e2e pipeline")
     ap.add_argument("--cpu-baseline-proposals", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -279,13 +282,26 @@ def main():
         def relax_batch(b, zh):
             return eng.relax(b, relax_steps=steps_relax, fmax=0.01, check=False)
 
+    class Pending:
+        """Asynchronous engine call: the 8 scalars per chain are copied to pinned host memory behind the
+        relaxation on the same stream; result() waits for that copy only."""
+
+        def __init__(self, out_dev):
+            self.host = torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
+            self.host.copy_(out_dev, non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record()
+
+        def result(self):
+            self.done.synchronize()
+            return self.host.numpy()
+
     def relax_fn(pos_l, num_l, fix_l):
         b = engine.Batch.from_arrays(pos_l, [to_species(zz) for zz in num_l], [cell] * len(pos_l), [pbc] * len(pos_l), fix_l)
         r = relax_batch(b, np.concatenate(num_l))
-        out = r["out"].cpu().numpy()          # D2H of 8 scalars per chain (synchronises)
-        io["h2d"] = b.h2d_bytes() + 8 * b.n_struct
-        io["d2h"] = out.nbytes
-        return out
+        io["h2d"] += b.h2d_bytes() + 8 * b.n_struct
+        io["d2h"] += r["out"].numel() * 8
+        return Pending(r["out"])
 
     drv = build_driver(name, relax_fn, [rank * C + c for c in range(C)])
     if w["canonical"]:
@@ -298,20 +314,26 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------ e2e: public API, host buffers
+    # The chains run as `--groups` interleaved groups (MultiChainMC.pipeline): while the GPU relaxes one group,
+    # the host applies Metropolis to / proposes for the other.  One step = one iteration of EVERY chain.
+    pipe = drv.pipeline(n_groups=max(1, args.groups))
     for _ in range(args.warmup):
-        drv.step()
+        pipe.advance()
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = int(lib.vssr_launch_count())
+    io["h2d"] = io["d2h"] = 0
     ev0.record()
     for _ in range(args.steps):
-        drv.step()
+        pipe.advance()
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
     e2e_launches = int(lib.vssr_launch_count()) - l0
+    io = {k: v // args.steps for k, v in io.items()}
+    pipe.drain()
 
     # ------------------------------------------------------------ device-resident: relax call only
     # stage the proposal batches (current chain states + one fresh proposal each) in HBM beforehand

@@ -17,9 +17,16 @@
 // gradients and the position gradient of atom i are produced by atom i's CTA: no atomics.
 //
 // Vector features are stored [A,3,128] (Cartesian-major) so U/V act as plain row GEMMs.
+#include <cuda.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+
+#include <initializer_list>
+#include <mutex>
+#include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "painn_layout.h"

@@ -207,17 +207,27 @@ class MultiChainMC:
         self.decisions = [[] for _ in seeds]        # per chain: (accept, curr, prev, u)
 
     # -- hot path call ------------------------------------------------------------------------
-    def _energies(self, chains):
+    # relax_fn may return out[C,8] directly, or a handle with .result() -> out[C,8] when the engine call is
+    # asynchronous (the relaxation is enqueued on the GPU and only result() waits for the 8 scalars per chain)
+    def _launch(self, chains):
         pos, num, fix = [], [], []
         for c in chains:
             p, z = c.arrays()
             pos.append(p)
             num.append(z)
             fix.append(np.concatenate([self.fixed0, np.zeros(len(z) - len(self.fixed0), dtype=bool)]))
-        out = self.relax_fn(pos, num, fix)
+        handle = self.relax_fn(pos, num, fix)
         self.n_relaxed += len(chains)
+        return handle, num
+
+    def _collect(self, launched):
+        handle, num = launched
+        out = handle.result() if hasattr(handle, "result") else handle
         # the OOB clamp of optimize_slab is invisible to Metropolis (system.py:466-469): raw energy is used
-        return [self.surface_energy_fn(float(out[k, 2]), [SYMBOLS[int(q)] for q in num[k]]) for k in range(len(chains))]
+        return [self.surface_energy_fn(float(out[k, 2]), [SYMBOLS[int(q)] for q in num[k]]) for k in range(len(num))]
+
+    def _energies(self, chains):
+        return self._collect(self._launch(chains))
 
     def _ensure_prev(self, chains):
         missing = [c for c in chains if "surface_energy" not in c.results]
@@ -225,8 +235,11 @@ class MultiChainMC:
             for c, e in zip(missing, self._energies(missing)):
                 c.results["surface_energy"] = e
 
-    def step(self, active=None, force_semigrand=None):
-        """One MC iteration for the chains in `active` (default all). Returns accept flags."""
+    def step_begin(self, active=None, force_semigrand=None):
+        """First half of an MC iteration for the chains in `active` (default all): propose, apply and
+        enqueue the relaxation.  Returns a ticket for step_end; nothing here waits for the GPU (unless a
+        chain has no current energy yet), so the host work of one chain group overlaps the relaxation of
+        another (run_pipelined)."""
         idx = list(range(len(self.chains))) if active is None else list(active)
         chains = [self.chains[i] for i in idx]
         snaps, actions = [], []
@@ -240,12 +253,17 @@ class MultiChainMC:
         prev = [c.results["surface_energy"] for c in chains]
         for c, a in zip(chains, actions):
             c.apply(a)
-        curr = self._energies(chains)
+        return idx, chains, snaps, prev, self._launch(chains), self.temp
+
+    def step_end(self, ticket):
+        """Second half: read the relaxed energies back and apply Metropolis. Returns accept flags."""
+        idx, chains, snaps, prev, launched, temp = ticket
+        curr = self._collect(launched)
         accepts = []
         for k, c in enumerate(chains):
             diff = float(curr[k] - prev[k])
             with np.errstate(over="ignore"):
-                base_prob = np.exp(-diff / self.temp)
+                base_prob = np.exp(-diff / temp)
             u = c.np_rng.rand()
             acc = bool(u < base_prob)
             if acc:
@@ -258,6 +276,17 @@ class MultiChainMC:
             self.decisions[idx[k]].append((acc, curr[k], prev[k], u))
             accepts.append(acc)
         return accepts
+
+    def step(self, active=None, force_semigrand=None):
+        """One MC iteration for the chains in `active` (default all). Returns accept flags."""
+        return self.step_end(self.step_begin(active, force_semigrand))
+
+    def pipeline(self, n_groups=2):
+        """Software pipeline over `n_groups` interleaved chain groups: `advance()` completes one MC iteration
+        of EVERY chain while the next iteration of each group is already enqueued, so the GPU never waits for
+        the host-side Metropolis / proposal logic.  Chains are independent and the engine is batch-invariant,
+        so every chain makes exactly the decisions it makes under step()."""
+        return _Pipeline(self, n_groups)
 
     def prepare_canonical(self):
         """MCMC.prepare_canonical (mcmc.py:150-188): semigrand steps until num_ads_atoms adsorbed."""
@@ -296,3 +325,32 @@ class MultiChainMC:
             if gather is not None:
                 gather(i, energy_hist[:, i], frac_accept[:, i], ads_count[:, i])
         return {"energy_hist": energy_hist, "frac_accept_hist": frac_accept, "adsorption_count_hist": ads_count}
+
+
+class _Pipeline:
+    def __init__(self, drv: MultiChainMC, n_groups: int):
+        C = len(drv.chains)
+        self.drv = drv
+        self.groups = [list(range(g, C, n_groups)) for g in range(n_groups) if g < C]
+        self.tickets = [None] * len(self.groups)
+
+    def advance(self, last=False):
+        """One iteration of every chain. Returns the accept flags in chain order."""
+        drv = self.drv
+        acc = [False] * len(drv.chains)
+        for gi, g in enumerate(self.groups):
+            if self.tickets[gi] is None:
+                self.tickets[gi] = drv.step_begin(g)
+        for gi, g in enumerate(self.groups):
+            flags = drv.step_end(self.tickets[gi])
+            self.tickets[gi] = None if last else drv.step_begin(g)
+            for i, f in zip(g, flags):
+                acc[i] = f
+        return acc
+
+    def drain(self):
+        """Finish the iterations that are still in flight."""
+        for gi in range(len(self.groups)):
+            if self.tickets[gi] is not None:
+                self.drv.step_end(self.tickets[gi])
+                self.tickets[gi] = None

@@ -75,3 +75,38 @@ def test_sharded_statistics_gather_gloo_world2(tmp_path):
     drv, _ = _driver(list(range(6)))
     ref = drv.run(total_sweeps=2, sweep_size=4, start_temp=0.5, perform_annealing=False)
     assert np.array_equal(got[0], ref["energy_hist"]) and np.array_equal(got[2], ref["adsorption_count_hist"])
+
+
+def test_pipelined_groups_make_the_same_decisions():
+    """MultiChainMC.pipeline (host logic of one chain group overlapped with the relaxation of the other,
+    asynchronous relax handles) leaves every chain's accept/reject sequence and occupancy unchanged."""
+    seeds = list(range(7))
+    ref, _ = _driver(seeds)
+    for _ in range(12):
+        ref.step()
+    drv, _ = _driver(seeds)
+    sync_fn = drv.relax_fn
+
+    class Handle:          # asynchronous engine call: the result is only read back in step_end
+        def __init__(self, out):
+            self._out, self.read = out, 0
+
+        def result(self):
+            self.read += 1
+            return self._out
+
+    handles = []
+
+    def async_fn(pos_l, num_l, fix_l):
+        handles.append(Handle(sync_fn(pos_l, num_l, fix_l)))
+        return handles[-1]
+
+    drv.relax_fn = async_fn
+    pipe = drv.pipeline(n_groups=3)
+    flags = [pipe.advance(last=(k == 11)) for k in range(12)]
+    pipe.drain()
+    assert all(h.read == 1 for h in handles)
+    assert drv.decisions == ref.decisions
+    for a, b in zip(drv.chains, ref.chains):
+        assert np.array_equal(a.occ, b.occ) and np.array_equal(a.arrays()[0], b.arrays()[0])
+    assert [f[3] for f in flags] == [d[0] for d in ref.decisions[3]]
