@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
 
   const GemmArgs& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) TC_STAMP(0);
   if (warp == TM_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(4 * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
   __syncthreads();
   fence_after();
   const uint32_t tmem0 = tmem_base_s;
+  if (tid == 0) TC_STAMP(1);
 
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN;
   const int total = m_tiles * n_tiles * p.n_models;
@@ -477,6 +479,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
           const int s = gchunk % TM_STAGES;
           mbar_wait(&araw_bar[s], (gchunk / TM_STAGES) & 1);
           mbar_wait(&full_bar[s], (gchunk / TM_STAGES) & 1);
+          if (gchunk == 0) TC_STAMP(2);
           fence_after();
           uint8_t* st = base + s * STAGE_BYTES;
           const uint64_t dAh = make_desc(smem_u32(st)), dAl = make_desc(smem_u32(st + A_BYTES));
@@ -494,6 +497,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
           mma_commit(&empty_bar[s]);
         }
         mma_commit(&tfull_bar[acc]);
+        TC_STAMP(3);
       }
     }
     __syncwarp();
@@ -516,6 +520,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
       const int m0 = (rem / n_tiles) * BM, n0 = (rem % n_tiles) * BN;
       const uint32_t d_main = tmem0 + acc * 2 * BN + ((uint32_t)(quarter * 32) << 16);
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      if (it == 0 && quarter == 0 && lane == 0) TC_STAMP(4);
       fence_after();
       const float* __restrict__ bias = (EPI == 1 || EPI == 4) ? g.bias + (long long)model * g.sBias : nullptr;
       const int row0 = m0 + quarter * 32;
@@ -586,12 +591,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (quarter == 0 && lane == 0) TC_STAMP(5);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
   }
   fence_before();
   __syncthreads();
+  if (tid == 0) TC_STAMP(6);
   if (warp == TM_MMA_WARP) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(4 * BN));
@@ -679,7 +686,12 @@ int launch_gemm_tma(const GemmArgs& g, const float* Bhi, const float* Blo, long 
   const CUtensorMap* mC2 = EPI == 4 ? get_tmap(g.C2, g.N, g.M, n_models, g.ldc, g.sC, 32) : mC;
   const CUtensorMap* mAux = EPI == 2 ? get_tmap(g.aux, g.N, g.M, n_models, g.ldaux, g.sAux, 32) : mC;
   if (!mA || !mBh || !mBl || !mC || !mC2 || !mAux) return 0;
-  tc::TcArgs p{g, Bhi, Blo, sBw, n_models, mode, nullptr};
+  static int dbg_on = -1, dbg_left = 3, dbg_skip = -1;
+  static unsigned long long* dbg = nullptr;
+  if (dbg_skip < 0) { const char* e = getenv("VSSR_TC_DEBUG_SKIP"); dbg_skip = e ? atoi(e) : 0; }
+  if (dbg_on < 0) { const char* e = getenv("VSSR_TC_DEBUG"); dbg_on = e ? atoi(e) : 0; if (dbg_on) cudaMalloc(&dbg, 148 * 16 * 8); }
+  if (dbg_on && dbg_skip > 0) --dbg_skip;
+  tc::TcArgs p{g, Bhi, Blo, sBw, n_models, mode, (dbg_on && dbg_left > 0 && dbg_skip == 0) ? dbg : nullptr};
   const int total = ceil_div(g.M, tc::BM) * (g.N / BN) * n_models;
   static bool configured = false;
   constexpr size_t smem = tc::tma_smem_bytes<BN>();
@@ -689,6 +701,18 @@ int launch_gemm_tma(const GemmArgs& g, const float* Bhi, const float* Blo, long 
   }
   const int grid = total < 148 ? total : 148;
   VSSR_PROF(VSSR_K_GEMM, st, (tc::gemm_tc_tma_kernel<BN, EPI><<<grid, tc::TM_THREADS, smem, st>>>(p, *mA, *mBh, *mBl, *mC, *mC2, *mAux)));
+  if (p.dbg) {
+    --dbg_left;
+    unsigned long long h[148 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull, t6 = 0;
+    for (int b = 0; b < grid; ++b) { if (h[b * 16] < t0) t0 = h[b * 16]; if (h[b * 16 + 6] > t6) t6 = h[b * 16 + 6]; }
+    for (int b : {0, grid - 1})
+      printf("[tma] BN=%d E=%d M=%d N=%d K=%d tiles=%d grid=%d span=%.1fus | cta%d: start=%.1f init=%.1f first_full=%.1f last_commit=%.1f first_tfull=%.1f last_epi=%.1f end=%.1f\n",
+             BN, EPI, g.M, g.N, g.K, total, grid, (t6 - t0) * 1e-3, b, (h[b*16]-t0)*1e-3, (h[b*16+1]-h[b*16])*1e-3, (h[b*16+2]-h[b*16])*1e-3,
+             (h[b*16+3]-h[b*16])*1e-3, (h[b*16+4]-h[b*16])*1e-3, (h[b*16+5]-h[b*16])*1e-3, (h[b*16+6]-h[b*16])*1e-3);
+  }
   *done = true;
   return 0;
 }

@@ -36,7 +36,9 @@ __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpre
 template <bool FIRST> struct MsgFwdLayout { static constexpr int PER = FIRST ? 3 * MSG_FC : 6 * MSG_FC; };
 template <bool FIRST> struct MsgBwdLayout { static constexpr int PER = FIRST ? 7 * MSG_FC : 10 * MSG_FC; };
 
-// copy `rows` rows of MSG_FC floats: src row r at src + r*src_stride, dst at dst + r*MSG_FC (per atom a)
+// copy `rows` rows of MSG_FC floats: src row r at src + r*src_stride, dst at dst + r*MSG_FC (per atom a).
+// cp.async (LDGSTS): no register round trip, so every 16-byte piece of the ~100-170 KB staged per CTA is in
+// flight at once instead of one load per thread per memory latency.  Completed by stage_wait().
 __device__ __forceinline__ void stage_rows(float* __restrict__ dst_atom0, int per, int dst_off,
                                            const float* __restrict__ src, long long src_atom_stride, int src_row_stride,
                                            int rows, int n, int tid, int nthreads) {
@@ -44,9 +46,14 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ dst_atom0, int pe
   const int per_atom = rows * Q;
   for (int idx = tid; idx < n * per_atom; idx += nthreads) {
     const int a = idx / per_atom, r = (idx % per_atom) / Q, c4 = idx % Q;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src + a * src_atom_stride + r * src_row_stride) + c4);
-    *reinterpret_cast<float4*>(dst_atom0 + a * per + dst_off + r * MSG_FC + c4 * 4) = v;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_atom0 + a * per + dst_off + r * MSG_FC + c4 * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + a * src_atom_stride + r * src_row_stride + c4 * 4));
   }
+}
+// all staged rows of this thread have landed (call before the __syncthreads that publishes them)
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 // one 16-byte cp.async per lane for the first n16*16 bytes of a record, then commit (always commits,
@@ -215,6 +222,7 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
   if (!FIRST) stage_rows(smem, PER, 3 * MSG_FC, v_in, 3 * F, F, 3, n, tid, MEMO_THREADS_FWD);
   const int f0 = h * MSG_FC + 2 * lane;
   const float* __restrict__ wbase = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC;
+  stage_wait();
   __syncthreads();
   for (int t = next_row(&row_ctr, lane); t < n; t = next_row(&row_ctr, lane)) {
     const int il = __ldg(order + a0 + t);
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
     wd2[q] = ld2(wl + L_WDT + q * F3 + 2 * F + f0);
   }
   const float2 bd0 = ld2(wl + L_BD + f0), bd1 = ld2(wl + L_BD + F + f0), bd2 = ld2(wl + L_BD + 2 * F + f0);
+  stage_wait();
   __syncthreads();
 
   for (int t = ch + n_chunks * next_row(&row_ctr, lane); t < n; t = ch + n_chunks * next_row(&row_ctr, lane)) {
@@ -475,6 +484,7 @@ __global__ void __launch_bounds__(MEMO_THREADS_BWD, 1) message_bwd_memo(
   const long long ml = (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + f0;
   const float* __restrict__ wrow = fc.wc + ml;
   const float* __restrict__ qrow = fc.qc + ml;
+  stage_wait();
   __syncthreads();
   for (int t = next_row(&row_ctr, lane); t < n; t = next_row(&row_ctr, lane)) {
     const int il = __ldg(order + a0 + t);
@@ -531,6 +541,7 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_bwd_memo_state(
   stage_rows(smem, PER, 0, ds, F, F, 1, n, tid, MEMO_THREADS_FWD);
   stage_rows(smem, PER, MSG_FC, dv, 3 * F, F, 3, n, tid, MEMO_THREADS_FWD);
   const float* __restrict__ wbase = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC;
+  stage_wait();
   __syncthreads();
   for (int t = next_row(&row_ctr, lane); t < n; t = next_row(&row_ctr, lane)) {
     const int il = __ldg(order + a0 + t);
@@ -607,6 +618,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     wd2[q] = ld2(wl + L_WDT + q * F3 + 2 * F + f0);
   }
   const float2 bd0 = ld2(wl + L_BD + f0), bd1 = ld2(wl + L_BD + F + f0), bd2 = ld2(wl + L_BD + 2 * F + f0);
+  stage_wait();
   __syncthreads();
 
   for (int t = ch + n_chunks * next_row(&row_ctr, lane); t < n; t = ch + n_chunks * next_row(&row_ctr, lane)) {
