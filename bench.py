@@ -194,8 +194,7 @@ def workload_config(args, chains):
             "l2": "per-evaluation working set (activations ~48 KB/atom/model, >1 GB) exceeds the 126 MB L2; no explicit flush"
                   if args.workload == "sto_painn" else "whole relaxation is shared-memory resident; L2 is not on the path",
             "parallelism": f"chains sharded, {args.gpus} rank(s), no data-path collective",
-            "e2e_pipeline": f"{max(1, args.groups)} interleaved chain groups per GPU (host MC logic of one group overlaps the "
-                            "relaxation of the other); value = one batch of all chains per step"}
+            "e2e_driver": f"MultiChainMC.pipeline, {max(1, args.groups)} chain group(s) per GPU; value = one batch of all chains per step"}
 
 
 def run_reference(args):
@@ -232,7 +231,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sto_painn", choices=list(WORKLOADS))
     ap.add_argument("--chains-per-gpu", type=int, default=0)
-    ap.add_argument("--groups", type=int, default=2, help="interleaved chain groups of the e2e pipeline")
+    ap.add_argument("--groups", type=int, default=1,
+                    help="interleaved chain groups of the e2e driver (MultiChainMC.pipeline); 1 = plain lock step, which is "
+                         "fastest here: the host part of a step is ~3 ms and half-size batches cost the GPU more than that")
     ap.add_argument("--cpu-baseline-proposals", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -314,8 +315,8 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------ e2e: public API, host buffers
-    # The chains run as `--groups` interleaved groups (MultiChainMC.pipeline): while the GPU relaxes one group,
-    # the host applies Metropolis to / proposes for the other.  One step = one iteration of EVERY chain.
+    # MultiChainMC.pipeline with `--groups` interleaved chain groups (with >1, the host applies Metropolis to /
+    # proposes for one group while the GPU relaxes the other).  One step = one iteration of EVERY chain.
     pipe = drv.pipeline(n_groups=max(1, args.groups))
     for _ in range(args.warmup):
         pipe.advance()

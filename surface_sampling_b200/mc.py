@@ -42,6 +42,9 @@ def hill_formula(symbols) -> str:
     return "".join(f"{k}{c[k] if c[k] > 1 else ''}" for k in keys)
 
 
+_SYMBOLS_ARR = np.array([None] + [SYMBOLS[z] for z in range(1, max(SYMBOLS) + 1)], dtype=object)
+
+
 class ChainState:
     """SurfaceSystem state restricted to what the MC loop mutates."""
 
@@ -49,6 +52,10 @@ class ChainState:
         self.n0 = len(numbers0)
         self.numbers = list(int(z) for z in numbers0)          # real_atoms numbers
         self.positions = [np.asarray(p, dtype=float) for p in positions0]
+        # the MC state keeps the UNRELAXED structure (relaxed coordinates are never written back), so the
+        # first n0 rows never change: arrays() only converts the adsorbate tail
+        self._pos0 = np.array(self.positions, dtype=np.float64).reshape(-1, 3)
+        self._num0 = np.array(self.numbers, dtype=np.int64)
         self.ads_group = [0] * self.n0 if ads_group0 is None else [int(g) for g in ads_group0]
         self.ads_coords = np.asarray(ads_coords, dtype=float)
         self.occ = np.zeros(len(self.ads_coords), dtype=int) if occ is None else np.array(occ, dtype=int)
@@ -126,7 +133,7 @@ class ChainState:
         """ChangeProposal.get_action (events/proposal.py:74-106)."""
         choices = list(adsorbates) + ["None"]
         if site_idx is None:
-            site_idx = int(self.np_rng.choice(range(len(self.occ))))
+            site_idx = int(self.np_rng.randint(0, len(self.occ)))   # == choice(range(n)): same draw, 10x cheaper
         if self.occ[site_idx] != 0:
             start = hill_formula(self.symbols_at_site(site_idx))
             choices.remove(start)
@@ -156,7 +163,11 @@ class ChainState:
             self.change_site(action["site2_idx"], action["site1_ads"])
 
     def arrays(self):
-        return np.array(self.positions, dtype=np.float64).reshape(-1, 3), np.array(self.numbers, dtype=np.int64)
+        n0 = self.n0
+        if len(self.numbers) == n0:
+            return self._pos0.copy(), self._num0.copy()
+        tail = np.array(self.positions[n0:], dtype=np.float64).reshape(-1, 3)
+        return np.concatenate([self._pos0, tail]), np.concatenate([self._num0, np.array(self.numbers[n0:], dtype=np.int64)])
 
 
 def create_anneal_schedule(start_temp=1.0, total_sweeps=1000, alpha=0.99):
@@ -224,7 +235,7 @@ class MultiChainMC:
         handle, num = launched
         out = handle.result() if hasattr(handle, "result") else handle
         # the OOB clamp of optimize_slab is invisible to Metropolis (system.py:466-469): raw energy is used
-        return [self.surface_energy_fn(float(out[k, 2]), [SYMBOLS[int(q)] for q in num[k]]) for k in range(len(num))]
+        return [self.surface_energy_fn(float(out[k, 2]), _SYMBOLS_ARR[num[k]].tolist()) for k in range(len(num))]
 
     def _energies(self, chains):
         return self._collect(self._launch(chains))
@@ -260,10 +271,10 @@ class MultiChainMC:
         idx, chains, snaps, prev, launched, temp = ticket
         curr = self._collect(launched)
         accepts = []
+        with np.errstate(over="ignore"):
+            probs = [np.exp(-float(curr[k] - prev[k]) / temp) for k in range(len(chains))]
         for k, c in enumerate(chains):
-            diff = float(curr[k] - prev[k])
-            with np.errstate(over="ignore"):
-                base_prob = np.exp(-diff / temp)
+            base_prob = probs[k]
             u = c.np_rng.rand()
             acc = bool(u < base_prob)
             if acc:
