@@ -419,8 +419,16 @@ def main():
         if dom in flops and tflops(dom):
             achieved = tflops(dom)
             is_gemm = dom == gemm_name
+            # DRAM bytes per launch of the dominant kernel class from the committed ncu --set full capture
+            traffic, traffic_src = None, None
+            caps = sorted((ROOT / "profiles").glob("r*_ncu_traffic.json"))
+            if caps:
+                cap = json.loads(caps[-1].read_text())
+                if dom in cap["classes"]:
+                    traffic = cap["classes"][dom]["dram_bytes_per_launch"]
+                    traffic_src = f"profiles/{caps[-1].name} (mean dram__bytes_read+write per launch, {cap['classes'][dom]['launches_captured']} launches)"
             roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": bf16 / 2, "unit": "TFLOP/s",
-                    "frac": achieved / (bf16 / 2), "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / (bf16 / 2), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "achieved_algorithmic_tflops": {k: tflops(k) for k in flops},
                     "frac_of_measured_ffma2_peak": None if is_gemm else achieved / FFMA2_PEAK,
                     "note": ("3xTF32 on tcgen05: 3 tensor-core MACs per algorithmic MAC" if is_gemm else
