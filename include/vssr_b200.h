@@ -107,6 +107,7 @@ int vssr_painn_energy_grad(const float* weights, int32_t n_models,
  *       frozen atoms and its whole position-gradient branch is skipped.  Energies, and the gradient rows
  *       of every other atom, are unchanged; gradient rows of frozen framework atoms are returned as 0. */
 #define VSSR_FC_CONSTRAINED_GRAD 1
+#define VSSR_FC_NO_PAIR 2   /* debugging: do not use the two-structures-per-CTA memo kernels */
 size_t vssr_painn_filter_cache_bytes(int32_t n_models, int32_t n0, int64_t e_cap0);
 size_t vssr_painn_filter_cache_workspace_bytes(int32_t n0, int64_t e_cap0);   /* scratch for the build */
 int vssr_painn_filter_cache_build(const float* weights, int32_t n_models, const float* pos0 /*[n0,3]*/,

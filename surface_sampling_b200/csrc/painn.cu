@@ -245,6 +245,11 @@ struct FilterCacheView {
   const float* wc;           // [M*3][nslots_cap][384]
   const float* qc;           // [M*3][nslots_cap][384]
   const uint8_t* frozen;     // [n0] framework atoms flagged frozen (FixAtoms)
+  // the framework's own memoised-edge lists ("canonical" lists): a structure whose rows all carry exactly
+  // these edges can be processed from them, two structures per CTA, with each filter row loaded once
+  const int32_t* nmemo0;     // [n0]
+  const float* mrec0;        // [E0][MREC], row i at rowptr[i]
+  const int32_t* order0;     // [n0] rows by nmemo0, descending
 };
 
 __global__ void __launch_bounds__(128) edge_geometry_kernel(
@@ -704,6 +709,7 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
 struct CacheBlob {
   int32_t* rowptr; int32_t* nvalid; int32_t* key; int32_t* slot; float* d; float* wc; float* qc; int32_t* counter;
   uint8_t* frozen;   // [n0] copy of fixed0
+  int32_t* nmemo0; int32_t* order0; float* mrec0;
   size_t bytes;
 };
 CacheBlob carve_cache(void* base, int M, int n0, long long e_cap0) {
@@ -721,6 +727,9 @@ CacheBlob carve_cache(void* base, int M, int n0, long long e_cap0) {
   c.d = (float*)take((size_t)e_cap0 * 4);
   c.counter = (int32_t*)take(4);
   c.frozen = (uint8_t*)take((size_t)n0);
+  c.nmemo0 = (int32_t*)take((size_t)n0 * 4);
+  c.order0 = (int32_t*)take((size_t)n0 * 4);
+  c.mrec0 = (float*)take((size_t)e_cap0 * MREC * 4);
   c.wc = (float*)take((size_t)M * NCONV * e_cap0 * F3 * 4);
   c.qc = (float*)take((size_t)M * NCONV * e_cap0 * F3 * 4);
   c.bytes = off;
@@ -732,6 +741,7 @@ FilterCacheView cache_view(const void* blob, int M, int n0, long long e_cap0) {
   CacheBlob c = carve_cache(const_cast<void*>(blob), M, n0, e_cap0);
   v.n0 = n0; v.nslots_cap = (int)e_cap0; v.rowptr = c.rowptr; v.nvalid = c.nvalid; v.key = c.key; v.slot = c.slot;
   v.d = c.d; v.wc = c.wc; v.qc = c.qc; v.frozen = c.frozen;
+  v.nmemo0 = c.nmemo0; v.mrec0 = c.mrec0; v.order0 = c.order0;
   return v;
 }
 
@@ -786,6 +796,7 @@ struct Workspace {
   // edge records (compacted per row by edge_geometry_kernel)
   int32_t* nvalid; float* erec; int32_t* nmemo; float* mrec; float* evex; float* grad0; float* gradp;
   int32_t* order_d; int32_t* order_m;   // per-structure row order, most direct / memoised edges first
+  int32_t* canonical;                   // [A] (first n_struct used): structure carries exactly the framework's memo lists
   // activations
   float* s[NCONV + 1];      // [M,A,128]
   float* v[NCONV + 1];      // [M,A,3,128]  (v[0] unused: zeros)
@@ -811,6 +822,7 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
   w.nmemo = reinterpret_cast<int32_t*>(take(A));
   w.order_d = reinterpret_cast<int32_t*>(take(A));
   w.order_m = reinterpret_cast<int32_t*>(take(A));
+  w.canonical = reinterpret_cast<int32_t*>(take(A));
   w.mrec = take((size_t)e_cap * MREC);
   w.evex = take(A);
   w.grad0 = take((size_t)A * 3);
@@ -873,8 +885,15 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const size_t memo_ring = (size_t)(MEMO_THREADS_FWD / 32) * MEMO_RING_BYTES_PER_WARP;
   const size_t sm_fwd0 = st_fwd0 + memo_ring, sm_fwd = st_fwd + memo_ring;
   const size_t sm_state = (size_t)nmax * MEMO_STATE_PER * 4 + memo_ring;
+  // group kernels: G canonical structures per CTA (as many as fit in shared memory), no ring
+  constexpr int G_FWD0 = 4, T_FWD0 = 512, G_FWD = 2, T_FWD = 512, G_STATE = 2, T_STATE = 512;
+  const bool group_on = memo && !(fc_flags & VSSR_FC_NO_PAIR);
+  const size_t sp_fwd0 = G_FWD0 * st_fwd0, sp_fwd = G_FWD * st_fwd, sp_state = (size_t)G_STATE * nmax * MEMO_STATE_PER * 4;
+  const bool pair_fwd0 = group_on && n_struct >= G_FWD0 && sp_fwd0 <= 227 * 1024;
+  const bool pair_fwd = group_on && n_struct >= G_FWD && sp_fwd <= 227 * 1024;
+  const bool pair_state = group_on && constrained && n_struct >= G_STATE && sp_state <= 227 * 1024;
   if (staged) {
-    static size_t cfg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    static size_t cfg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     auto want = [&](int k, const void* fn, size_t bytes) -> int {
       if (bytes > cfg[k]) {
         VSSR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -893,6 +912,9 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       if ((rc0 = want(6, (const void*)message_bwd_memo<true>, st_bwd0))) return rc0;
       if ((rc0 = want(7, (const void*)message_bwd_memo<false>, st_bwd))) return rc0;
       if ((rc0 = want(8, (const void*)message_bwd_memo_state, sm_state))) return rc0;
+      if (pair_fwd0 && (rc0 = want(9, (const void*)message_fwd_memo_group<true, G_FWD0, T_FWD0>, sp_fwd0))) return rc0;
+      if (pair_fwd && (rc0 = want(10, (const void*)message_fwd_memo_group<false, G_FWD, T_FWD>, sp_fwd))) return rc0;
+      if (pair_state && (rc0 = want(11, (const void*)message_bwd_memo_state_group<G_STATE, T_STATE>, sp_state))) return rc0;
     }
   }
 
@@ -901,7 +923,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       w.nvalid, w.erec, w.nmemo, w.mrec, w.evex, w.grad0));
   if (staged)
     VSSR_PROF(VSSR_K_GEOM, st, row_order_kernel<<<n_struct, 128, (size_t)2 * nmax * sizeof(int32_t), st>>>(
-        atom_ptr, w.nvalid, w.nmemo, w.order_d, w.order_m));
+        atom_ptr, w.nvalid, w.nmemo, w.order_d, w.order_m, memo ? fc.n0 : 0, fc.nmemo0, w.canonical));
   VSSR_PROF(VSSR_K_ELEMWISE, st, embed_kernel<<<dim3(ceil_div((long long)A * (F / 4), 256), M), 256, 0, st>>>(weights, z, A, w.s[0]));
 
   int rc;
@@ -919,16 +941,24 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     // F3
     if (staged) {
       if (l == 0) {
+        if (pair_fwd0)
+          VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo_group<true, G_FWD0, T_FWD0><<<dim3(n_struct / G_FWD0, F / MSG_FC, M), T_FWD0, sp_fwd0, st>>>(
+              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
         if (memo)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<true><<<memo_grid, MEMO_THREADS_FWD, sm_fwd0, st>>>(
-              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
+              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l],
+              pair_fwd0 ? w.canonical : nullptr, n_struct, G_FWD0));
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
             w.cat[l], w.vmid[l], memo ? 1 : 0));
       } else {
+        if (pair_fwd)
+          VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo_group<false, G_FWD, T_FWD><<<dim3(n_struct / G_FWD, F / MSG_FC, M), T_FWD, sp_fwd, st>>>(
+              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
         if (memo)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<false><<<memo_grid, MEMO_THREADS_FWD, sm_fwd, st>>>(
-              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
+              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l],
+              pair_fwd ? w.canonical : nullptr, n_struct, G_FWD));
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
             w.cat[l], w.vmid[l], memo ? 1 : 0));
@@ -1012,9 +1042,13 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
             dv_cur, nullptr, nullptr, w.gradp, (memo && !constrained) ? 3 : 0));
       } else {
+        if (pair_state)
+          VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo_state_group<G_STATE, T_STATE><<<dim3(n_struct / G_STATE, F / MSG_FC, M), T_STATE, sp_state, st>>>(
+              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt));
         if (constrained)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo_state<<<memo_grid, MEMO_THREADS_FWD, sm_state, st>>>(
-              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt));
+              l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt,
+              pair_state ? w.canonical : nullptr, n_struct, G_STATE));
         else if (memo)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<false><<<memo_grid, MEMO_THREADS_BWD, st_bwd, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));
@@ -1112,6 +1146,15 @@ extern "C" int vssr_painn_filter_cache_build(const float* weights, int32_t n_mod
   VSSR_PROF(VSSR_K_GEOM, st, cache_slot_kernel<<<1, 32, 0, st>>>(erec, c.rowptr, c.nvalid, fixed0, n0, c.key, c.slot, c.d, c.counter));
   VSSR_PROF(VSSR_K_GEOM, st, cache_fill_kernel<<<dim3((unsigned)e_cap0, n_models * NCONV), 128, 0, st>>>(
       weights, erec, c.slot, (int)e_cap0, c.wc, c.qc));
+  // the framework's own memoised lists: the same geometry kernel, now WITH the memo, run on the framework itself
+  {
+    const FilterCacheView self = cache_view(cache, n_models, n0, e_cap0);
+    VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(n0, 4), 128, 0, st>>>(
+        pos0, atom_ptr, cell, 1, n0, c.rowptr, col, shift, (long long)e_cap0, cutoff, self, deg, erec, c.nmemo0, c.mrec0,
+        evex, grad0));
+    VSSR_PROF(VSSR_K_GEOM, st, row_order_kernel<<<1, 128, (size_t)2 * n0 * sizeof(int32_t), st>>>(
+        atom_ptr, c.nmemo0, c.nmemo0, c.order0, nmemo, 0, nullptr, nullptr));
+  }
   int32_t host[2] = {0, 0};
   VSSR_CUDA(cudaMemcpyAsync(&host[0], c.counter, 4, cudaMemcpyDeviceToHost, st));
   VSSR_CUDA(cudaMemcpyAsync(&host[1], status, 4, cudaMemcpyDeviceToHost, st));

@@ -79,13 +79,29 @@ __device__ __forceinline__ int next_row(int* ctr, int lane) {
   return __shfl_sync(0xffffffffu, t, 0);
 }
 
-// order[a0 + rank] = local index of the row with that rank (cost descending, index ascending on ties)
+// is structure b handled by a group kernel (G consecutive canonical structures per CTA)?
+__device__ __forceinline__ bool in_canonical_group(const int32_t* __restrict__ canonical, int b, int n_struct, int G) {
+  if (!canonical) return false;
+  const int q = (b / G) * G;
+  if (q + G > n_struct) return false;
+  for (int s = 0; s < G; ++s)
+    if (!__ldg(canonical + q + s)) return false;
+  return true;
+}
+
+// order[a0 + rank] = local index of the row with that rank (cost descending, index ascending on ties).
+// With a framework (n0 > 0) also: canonical[b] = 1 iff every framework row of structure b carries exactly the
+// framework's own memoised edges (same count => same set and order, both are in CSR order) -- then the pair
+// kernels below may walk the framework's lists instead of the structure's.
 __global__ void __launch_bounds__(128) row_order_kernel(const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ cost_a,
                                                         const int32_t* __restrict__ cost_b, int32_t* __restrict__ order_a,
-                                                        int32_t* __restrict__ order_b) {
+                                                        int32_t* __restrict__ order_b, int n0,
+                                                        const int32_t* __restrict__ nmemo0, int32_t* __restrict__ canonical) {
   extern __shared__ int32_t costs[];   // [2][n]
+  __shared__ int mismatch;
   const int b = blockIdx.x;
   const int a0 = atom_ptr[b], n = atom_ptr[b + 1] - a0;
+  if (threadIdx.x == 0) mismatch = 0;
   for (int k = threadIdx.x; k < n; k += blockDim.x) { costs[k] = cost_a[a0 + k]; costs[n + k] = cost_b[a0 + k]; }
   __syncthreads();
   for (int k = threadIdx.x; k < 2 * n; k += blockDim.x) {
@@ -95,6 +111,11 @@ __global__ void __launch_bounds__(128) row_order_kernel(const int32_t* __restric
     int rank = 0;
     for (int o = 0; o < n; ++o) rank += (c[o] > mine) || (c[o] == mine && o < il);
     (which ? order_b : order_a)[a0 + rank] = il;
+    if (which && n0 > 0 && il < n0 && mine != nmemo0[il]) mismatch = 1;   // benign race: all writers store 1
+  }
+  if (canonical) {
+    __syncthreads();
+    if (threadIdx.x == 0) canonical[b] = (n0 > 0 && n >= n0 && !mismatch) ? 1 : 0;
   }
 }
 
@@ -203,9 +224,10 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
     int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ rowptr,
     const int32_t* __restrict__ order, const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
     const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
-    float* __restrict__ cat, float* __restrict__ v_mid) {
+    float* __restrict__ cat, float* __restrict__ v_mid, const int32_t* __restrict__ canonical, int n_struct, int group) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int row_ctr;
+  if (in_canonical_group(canonical, blockIdx.x, n_struct, group)) return;   // done by message_fwd_memo_group
   if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MsgFwdLayout<FIRST>::PER;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -521,9 +543,11 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_bwd_memo_state(
     int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ rowptr,
     const int32_t* __restrict__ order, const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
     const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
-    const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in) {
+    const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in,
+    const int32_t* __restrict__ canonical, int n_struct, int group) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int row_ctr;
+  if (in_canonical_group(canonical, blockIdx.x, n_struct, group)) return;   // done by message_bwd_memo_state_group
   if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MEMO_STATE_PER;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -668,6 +692,181 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
       bwd_edge<FIRST>(g, rec[7], smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane, o, w0, w1, w2, q0, q1, q2, a);
     }
     bwd_store<FIRST>(o, a, il, i, f0, lane, m, h, n_atoms, dphi, dv_in, gradp, accum);
+  }
+}
+
+// ============================================================================================
+// Pair kernels: two CANONICAL structures per CTA (row_order_kernel), walking the framework's own memoised
+// lists.  Each filter row is loaded once (LDG, straight to registers) and used for both structures, so
+// the per-edge LSU work -- the bound of the single-structure memo kernels -- nearly halves, and no
+// per-chain records are read at all.  Same per-edge arithmetic in the same order => same bits.
+// ============================================================================================
+template <bool ROW0, typename Body>
+__device__ __forceinline__ void canon_walk(const float4* __restrict__ mr, int ne, int lane,
+                                           const float* __restrict__ wlane, Body body) {
+  for (int base = 0; base < ne; base += 32) {
+    const int cnt = min(32, ne - base);
+    float4 gl = make_float4(0.f, 0.f, 0.f, 1.f), jl = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (lane < cnt) { gl = __ldg(mr + 2 * (base + lane)); jl = __ldg(mr + 2 * (base + lane) + 1); }
+#pragma unroll 4
+    for (int e = 0; e < cnt; ++e) {
+      const int slot = __shfl_sync(0xffffffffu, __float_as_int(jl.y), e);
+      const float* wr = wlane + (long long)slot * F3;
+      const float2 w1 = ldg2(wr + F), w2 = ldg2(wr + 2 * F), w0 = ROW0 ? ldg2(wr) : dup2(0.f);
+      const float4 g = make_float4(__shfl_sync(0xffffffffu, gl.x, e), __shfl_sync(0xffffffffu, gl.y, e),
+                                   __shfl_sync(0xffffffffu, gl.z, e), __shfl_sync(0xffffffffu, gl.w, e));
+      const int j = __shfl_sync(0xffffffffu, __float_as_int(jl.x), e);
+      body(g, j, w0, w1, w2);
+    }
+  }
+}
+
+template <bool FIRST, int G, int T>
+__global__ void __launch_bounds__(T, 1) message_fwd_memo_group(
+    int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ canonical,
+    FilterCacheView fc, const float* __restrict__ phi, const float* __restrict__ s_in,
+    const float* __restrict__ v_in, float* __restrict__ cat, float* __restrict__ v_mid) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int row_ctr;
+  constexpr int PER = MsgFwdLayout<FIRST>::PER;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b0 = G * blockIdx.x, h = blockIdx.y, m = blockIdx.z;
+#pragma unroll
+  for (int s = 0; s < G; ++s)
+    if (!__ldg(canonical + b0 + s)) return;
+  if (tid == 0) row_ctr = 0;
+  const long long mA = (long long)m * n_atoms;
+  int a0[G], n[G];
+  float* sm[G];
+#pragma unroll
+  for (int s = 0; s < G; ++s) { a0[s] = __ldg(atom_ptr + b0 + s); n[s] = __ldg(atom_ptr + b0 + s + 1) - a0[s]; }
+  sm[0] = smem;
+#pragma unroll
+  for (int s = 1; s < G; ++s) sm[s] = sm[s - 1] + (size_t)n[s - 1] * PER;
+#pragma unroll
+  for (int s = 0; s < G; ++s) {
+    stage_rows(sm[s], PER, 0, phi + (mA + a0[s]) * F3 + h * MSG_FC, F3, F, 3, n[s], tid, T);
+    if (!FIRST) stage_rows(sm[s], PER, 3 * MSG_FC, v_in + (mA + a0[s]) * 3 * F + h * MSG_FC, 3 * F, F, 3, n[s], tid, T);
+  }
+  const int f0 = h * MSG_FC + 2 * lane;
+  const float* __restrict__ wlane = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + f0;
+  int nrows = n[0];
+#pragma unroll
+  for (int s = 1; s < G; ++s) nrows = max(nrows, n[s]);
+  stage_wait();
+  __syncthreads();
+  for (int t = next_row(&row_ctr, lane); t < nrows; t = next_row(&row_ctr, lane)) {
+    const int il = t < fc.n0 ? __ldg(fc.order0 + t) : t;   // rows past the framework (adsorbates) have no memoised edge
+    float2 ds[G], dvx[G], dvy[G], dvz[G];
+#pragma unroll
+    for (int s = 0; s < G; ++s) ds[s] = dvx[s] = dvy[s] = dvz[s] = dup2(0.f);
+    if (il < fc.n0) {
+      const float4* mr = reinterpret_cast<const float4*>(fc.mrec0 + (long long)__ldg(fc.rowptr + il) * MREC);
+      canon_walk<!FIRST>(mr, __ldg(fc.nmemo0 + il), lane, wlane, [&](const float4 g, int j, float2 w0, float2 w1, float2 w2) {
+#pragma unroll
+        for (int s = 0; s < G; ++s) fwd_edge<FIRST>(g, sm[s] + j * PER + 2 * lane, w0, w1, w2, ds[s], dvx[s], dvy[s], dvz[s]);
+      });
+    }
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+      if (il >= n[s]) continue;
+      const long long i = mA + a0[s] + il;
+      const float2 s0 = ld2(s_in + i * F + f0);
+      *reinterpret_cast<float2*>(cat + i * 2 * F + f0) = __fadd2_rn(s0, ds[s]);
+      float2 ox = dvx[s], oy = dvy[s], oz = dvz[s];
+      if (!FIRST) {
+        const float* si = sm[s] + il * PER + 2 * lane;
+        ox = __fadd2_rn(ox, ld2(si + 3 * MSG_FC));
+        oy = __fadd2_rn(oy, ld2(si + 4 * MSG_FC));
+        oz = __fadd2_rn(oz, ld2(si + 5 * MSG_FC));
+      }
+      float* vo = v_mid + i * 3 * F + f0;
+      *reinterpret_cast<float2*>(vo) = ox;
+      *reinterpret_cast<float2*>(vo + F) = oy;
+      *reinterpret_cast<float2*>(vo + 2 * F) = oz;
+    }
+  }
+}
+
+template <int G, int T>
+__global__ void __launch_bounds__(T, 1) message_bwd_memo_state_group(
+    int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ canonical,
+    FilterCacheView fc, const float* __restrict__ phi, const float* __restrict__ v_in,
+    const float* __restrict__ ds, const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int row_ctr;
+  constexpr int PER = MEMO_STATE_PER;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b0 = G * blockIdx.x, h = blockIdx.y, m = blockIdx.z;
+#pragma unroll
+  for (int s = 0; s < G; ++s)
+    if (!__ldg(canonical + b0 + s)) return;
+  if (tid == 0) row_ctr = 0;
+  const long long mA = (long long)m * n_atoms;
+  int a0[G], n[G];
+  float* sm[G];
+#pragma unroll
+  for (int s = 0; s < G; ++s) { a0[s] = __ldg(atom_ptr + b0 + s); n[s] = __ldg(atom_ptr + b0 + s + 1) - a0[s]; }
+  sm[0] = smem;
+#pragma unroll
+  for (int s = 1; s < G; ++s) sm[s] = sm[s - 1] + (size_t)n[s - 1] * PER;
+#pragma unroll
+  for (int s = 0; s < G; ++s) {
+    stage_rows(sm[s], PER, 0, ds + (mA + a0[s]) * F + h * MSG_FC, F, F, 1, n[s], tid, T);
+    stage_rows(sm[s], PER, MSG_FC, dv + (mA + a0[s]) * 3 * F + h * MSG_FC, 3 * F, F, 3, n[s], tid, T);
+  }
+  const int f0 = h * MSG_FC + 2 * lane;
+  const float* __restrict__ wlane = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + f0;
+  int nrows = n[0];
+#pragma unroll
+  for (int s = 1; s < G; ++s) nrows = max(nrows, n[s]);
+  stage_wait();
+  __syncthreads();
+  for (int t = next_row(&row_ctr, lane); t < nrows; t = next_row(&row_ctr, lane)) {
+    const int il = t < fc.n0 ? __ldg(fc.order0 + t) : t;
+    float2 pi0[G], vix[G], viy[G], viz[G], dp0[G], dp1[G], dp2n[G], dvx[G], dvy[G], dvz[G];
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+      dp0[s] = dp1[s] = dp2n[s] = dvx[s] = dvy[s] = dvz[s] = dup2(0.f);
+      pi0[s] = vix[s] = viy[s] = viz[s] = dup2(0.f);
+      if (il < n[s] && il < fc.n0) {
+        const long long i = mA + a0[s] + il;
+        pi0[s] = ldg2(phi + i * F3 + f0);
+        vix[s] = ldg2(v_in + i * 3 * F + f0); viy[s] = ldg2(v_in + i * 3 * F + F + f0); viz[s] = ldg2(v_in + i * 3 * F + 2 * F + f0);
+      }
+    }
+    if (il < fc.n0) {
+      const float4* mr = reinterpret_cast<const float4*>(fc.mrec0 + (long long)__ldg(fc.rowptr + il) * MREC);
+      canon_walk<true>(mr, __ldg(fc.nmemo0 + il), lane, wlane, [&](const float4 g, int j, float2 w0, float2 w1, float2 w2) {
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+          const float* sj = sm[s] + j * PER + 2 * lane;
+          const float2 gsj = ld2(sj), gvjx = ld2(sj + MSG_FC), gvjy = ld2(sj + 2 * MSG_FC), gvjz = ld2(sj + 3 * MSG_FC);
+          // same operation order as message_bwd_memo_state / bwd_edge
+          const float2 nB2 = __ffma2_rn(gvjz, dup2(g.z), __ffma2_rn(gvjy, dup2(g.y), __fmul2_rn(gvjx, dup2(g.x))));
+          const float2 dxB0 = __ffma2_rn(gvjz, viz[s], __ffma2_rn(gvjy, viy[s], __fmul2_rn(gvjx, vix[s])));
+          dp0[s] = __ffma2_rn(dxB0, w0, dp0[s]);
+          dp1[s] = __ffma2_rn(gsj, w1, dp1[s]);
+          dp2n[s] = __ffma2_rn(nB2, w2, dp2n[s]);
+          const float2 tv = __fmul2_rn(pi0[s], w0);
+          dvx[s] = __ffma2_rn(tv, gvjx, dvx[s]); dvy[s] = __ffma2_rn(tv, gvjy, dvy[s]); dvz[s] = __ffma2_rn(tv, gvjz, dvz[s]);
+        }
+      });
+    }
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+      if (il >= n[s]) continue;
+      const long long i = mA + a0[s] + il;
+      const float* si = sm[s] + il * PER + 2 * lane;
+      float* dpo = dphi + i * F3 + f0;
+      float* dvo = dv_in + i * 3 * F + f0;
+      *reinterpret_cast<float2*>(dpo) = dp0[s];
+      *reinterpret_cast<float2*>(dpo + F) = dp1[s];
+      *reinterpret_cast<float2*>(dpo + 2 * F) = neg2(dp2n[s]);
+      *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ld2(si + MSG_FC), dvx[s]);
+      *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ld2(si + 2 * MSG_FC), dvy[s]);
+      *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ld2(si + 3 * MSG_FC), dvz[s]);
+    }
   }
 }
 

@@ -215,7 +215,7 @@ class PainnEngine:
         self._ws_relax = _Workspace()
         self._fc = None          # (blob tensor, n0, e_cap0, nslots) of the frozen-pair filter memo
 
-    def set_framework(self, pos0, cell, pbc, fixed0, constrained_forces: bool = False) -> int:
+    def set_framework(self, pos0, cell, pbc, fixed0, constrained_forces: bool = False, pair_kernels: bool = True) -> int:
         """Build the radial-filter memo for a frozen framework shared by every structure (its atoms must
         be the FIRST n0 atoms of each structure, as in VSSR-MC where adsorbates are appended).  Edges
         whose distance is bitwise equal to a framework edge between two frozen atoms reuse the memoised
@@ -226,7 +226,8 @@ class PainnEngine:
         carry FixAtoms, as in every VSSR-MC relaxation (mcmc/dynamics.py:25-141 -> ASE zeroes their
         forces): dE/dx of those atoms is then not computed at all (their force rows come back as 0),
         which removes the whole position-gradient branch of every memoised edge.  Energies and the
-        forces of all other atoms are unchanged."""
+        forces of all other atoms are unchanged.  pair_kernels=False (VSSR_FC_NO_PAIR) keeps the
+        one-structure-per-CTA memo kernels (same bits; for tests)."""
         lib, dev = self.lib, self.device
         pos0 = np.ascontiguousarray(pos0, dtype=np.float32)
         n0 = len(pos0)
@@ -247,7 +248,7 @@ class PainnEngine:
                                                      _ptr(blob), blob.numel(), _ptr(ws), ws.numel(),
                                                      ctypes.addressof(nslots), _stream()),
                    "vssr_painn_filter_cache_build")
-        self._fc = (blob, n0, e_cap0, int(nslots.value), 1 if constrained_forces else 0,
+        self._fc = (blob, n0, e_cap0, int(nslots.value), (1 if constrained_forces else 0) | (0 if pair_kernels else 2),
                     np.ascontiguousarray(fixed0).astype(bool))
         return int(nslots.value)
 
@@ -319,7 +320,7 @@ class PainnEngine:
         updated in place.  Returns dict(out[B,8], forces, forces_std, status)."""
         lib, dev = self.lib, self.device
         A, B, M = batch.n_atoms, batch.n_struct, self.n_models
-        if self._fc is not None and self._fc[4] and batch.fixed_host is not None:
+        if self._fc is not None and (self._fc[4] & 1) and batch.fixed_host is not None:
             # VSSR_FC_CONSTRAINED_GRAD contract: the framework's frozen atoms are FixAtoms in every structure
             frozen = np.flatnonzero(self._fc[5])
             idx = (batch.atom_ptr_host[:-1, None] + frozen[None, :]).reshape(-1)

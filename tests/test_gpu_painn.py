@@ -205,6 +205,13 @@ def test_frozen_pair_filter_memo(structures, potentials, sto_weights):
     assert torch.equal(b2.pos, b1.pos), (b2.pos - b1.pos).abs().max().item()
     with pytest.raises(Exception):          # contract check: the batch must hold the frozen atoms fixed
         cons.relax(_batch(structs), relax_steps=1)
+    # two-structures-per-CTA memo kernels (canonical framework lists) vs the one-structure kernels: same bits
+    for cons_mode in (False, True):
+        solo = engine.PainnEngine(sto_weights, od)
+        solo.set_framework(base["positions"], base["cell"], PBC3, fixed0, constrained_forces=cons_mode, pair_kernels=False)
+        ra = solo.energy_forces(_batch(structs + structs[:1]))
+        rb = (cons if cons_mode else memo).energy_forces(_batch(structs + structs[:1]))
+        assert torch.equal(ra["energy"], rb["energy"]) and torch.equal(ra["forces"], rb["forces"])
     # a framework that does not match the batch (shifted atoms) silently disables the memo: same answers
     other = engine.PainnEngine(sto_weights, od)
     other.set_framework(base["positions"] + 0.123, base["cell"], PBC3, fixed0)
