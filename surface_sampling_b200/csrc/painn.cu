@@ -879,7 +879,9 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
   const bool memo = staged && fc.n0 > 0;   // two passes: memoised edges (light kernels), then direct edges
   const bool constrained = memo && (fc_flags & VSSR_FC_CONSTRAINED_GRAD);   // no dE/dx wanted on frozen atoms
-  const int n_chunks = 2;
+  static int n_chunks_env = -1;
+  if (n_chunks_env < 0) { const char* e = getenv("VSSR_MSG_CHUNKS"); n_chunks_env = e ? atoi(e) : 2; if (n_chunks_env < 1) n_chunks_env = 2; }
+  const int n_chunks = n_chunks_env;   // CTAs per (structure, feature half, model) in the direct pass
   const dim3 v2_grid(n_struct * n_chunks, F / MSG_FC, M);
   const dim3 memo_grid(n_struct, F / MSG_FC, M);
   const size_t memo_ring = (size_t)(MEMO_THREADS_FWD / 32) * MEMO_RING_BYTES_PER_WARP;
@@ -1040,7 +1042,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp));
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
-            dv_cur, nullptr, nullptr, w.gradp, (memo && !constrained) ? 3 : 0));
+            dv_cur, nullptr, nullptr, w.gradp, (memo && !constrained) ? 3 : 0, constrained ? fc.frozen : nullptr, fc.n0));
       } else {
         if (pair_state)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo_state_group<G_STATE, T_STATE><<<dim3(n_struct / G_STATE, F / MSG_FC, M), T_STATE, sp_state, st>>>(
@@ -1054,7 +1056,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
-            dv_cur, w.dphi, dv_nxt, w.gradp, constrained ? 1 : (memo ? 3 : 0)));
+            dv_cur, w.dphi, dv_nxt, w.gradp, constrained ? 1 : (memo ? 3 : 0), constrained ? fc.frozen : nullptr, fc.n0));
       }
       VSSR_PROF(VSSR_K_ELEMWISE, st, grad_accum_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.gradp, 3 * A, grad));
     } else {

@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     const float* __restrict__ erec,
     const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
     const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in, float* __restrict__ gradp,
-    int accum) {
+    int accum, const uint8_t* __restrict__ frozen, int n0) {
   extern __shared__ __align__(16) float smem_all[];
   __shared__ int row_ctr;
   if (threadIdx.x == 0) row_ctr = 0;
@@ -654,6 +654,71 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
       if (!(accum & 2) && lane == 0) {
         float* gp = gradp + (((long long)m * 2 + h) * n_atoms + i) * 3;
         gp[0] = 0.f; gp[1] = 0.f; gp[2] = 0.f;
+      }
+      continue;
+    }
+    if (frozen && il < n0 && frozen[il]) {
+      // constrained mode, frozen receiver: dE/dx_i is not wanted, so only the state terms of edge B remain
+      // (filter w without its derivative: 60 + 13 FFMA2 instead of 180); nothing at all at the first layer
+      if (lane == 0) {
+        float* gp = gradp + (((long long)m * 2 + h) * n_atoms + i) * 3;
+        gp[0] = 0.f; gp[1] = 0.f; gp[2] = 0.f;
+      }
+      if (FIRST) continue;
+      using O = BwdOffsets<FIRST>;
+      constexpr int N16L = (REC_RE + 44) / 4;   // geometry + rbf rows only
+      const float* si = smem + il * PER + 2 * lane;
+      const float2 pi0 = ld2(si), vix = ld2(si + O::O_V), viy = ld2(si + O::O_V + MSG_FC), viz = ld2(si + O::O_V + 2 * MSG_FC);
+      float2 dp0 = dup2(0.f), dp1 = dup2(0.f), dp2n = dup2(0.f), dvx = dup2(0.f), dvy = dup2(0.f), dvz = dup2(0.f);
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < MSG_STAGES - 1; ++s) prefetch_record(ring + s * REC, rec0 + (long long)s * REC, lane, N16L, s < ne);
+      for (int e = 0; e < ne; ++e) {
+        wait_record();
+        const int nx = e + MSG_STAGES - 1;
+        prefetch_record(ring + (nx % MSG_STAGES) * REC, rec0 + (long long)nx * REC, lane, N16L, nx < ne);
+        const float* rec = ring + (e % MSG_STAGES) * REC;
+        const float4 g = *reinterpret_cast<const float4*>(rec);
+        const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
+        const float4 ev = r4[10];
+        const float2 env2 = make_float2(ev.x, ev.y);
+        float2 w0 = __fmul2_rn(bd0, env2), w1 = __fmul2_rn(bd1, env2), w2 = __fmul2_rn(bd2, env2);
+#pragma unroll
+        for (int q = 0; q < NRBF / 2; ++q) {
+          const float4 t4 = r4[q];
+          const float2 ra = make_float2(t4.x, t4.y), rb = make_float2(t4.z, t4.w);
+          w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);
+          w0 = __ffma2_rn(wd0[2 * q + 1], rb, w0); w1 = __ffma2_rn(wd1[2 * q + 1], rb, w1);
+          w2 = __ffma2_rn(wd2[2 * q + 1], rb, w2);
+        }
+        const float* sj = smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane;
+        const float2 gsj = ld2(sj + O::O_DS);
+        const float2 gvjx = ld2(sj + O::O_DV), gvjy = ld2(sj + O::O_DV + MSG_FC), gvjz = ld2(sj + O::O_DV + 2 * MSG_FC);
+        // same operation order as bwd_edge
+        const float2 nB2 = __ffma2_rn(gvjz, dup2(g.z), __ffma2_rn(gvjy, dup2(g.y), __fmul2_rn(gvjx, dup2(g.x))));
+        const float2 dxB0 = __ffma2_rn(gvjz, viz, __ffma2_rn(gvjy, viy, __fmul2_rn(gvjx, vix)));
+        dp0 = __ffma2_rn(dxB0, w0, dp0);
+        dp1 = __ffma2_rn(gsj, w1, dp1);
+        dp2n = __ffma2_rn(nB2, w2, dp2n);
+        const float2 tv = __fmul2_rn(pi0, w0);
+        dvx = __ffma2_rn(tv, gvjx, dvx); dvy = __ffma2_rn(tv, gvjy, dvy); dvz = __ffma2_rn(tv, gvjz, dvz);
+      }
+      float* dpo = dphi + (long long)il * F3 + f0;
+      float* dvo = dv_in + (long long)il * 3 * F + f0;
+      if (accum & 1) {
+        *reinterpret_cast<float2*>(dpo) = __fadd2_rn(ld2(dpo), dp0);
+        *reinterpret_cast<float2*>(dpo + F) = __fadd2_rn(ld2(dpo + F), dp1);
+        *reinterpret_cast<float2*>(dpo + 2 * F) = __fadd2_rn(ld2(dpo + 2 * F), neg2(dp2n));
+        *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ld2(dvo), dvx);
+        *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ld2(dvo + F), dvy);
+        *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ld2(dvo + 2 * F), dvz);
+      } else {
+        *reinterpret_cast<float2*>(dpo) = dp0;
+        *reinterpret_cast<float2*>(dpo + F) = dp1;
+        *reinterpret_cast<float2*>(dpo + 2 * F) = neg2(dp2n);
+        *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ld2(si + O::O_DV), dvx);
+        *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ld2(si + O::O_DV + MSG_FC), dvy);
+        *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ld2(si + O::O_DV + 2 * MSG_FC), dvz);
       }
       continue;
     }
