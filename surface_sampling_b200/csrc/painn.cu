@@ -874,7 +874,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   // staged rows of one structure (memo pass) + the per-warp record rings (direct pass)
   const size_t st_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4, st_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4;
   const size_t st_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4, st_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4;
-  const size_t smem_fwd0 = st_fwd0 + MSG_PIPE_BYTES, smem_fwd = st_fwd + MSG_PIPE_BYTES;
+  const size_t smem_fwd0 = st_fwd0 + MSG_PIPE_BYTES_FWD, smem_fwd = st_fwd + MSG_PIPE_BYTES_FWD;
   const size_t smem_bwd0 = st_bwd0 + MSG_PIPE_BYTES, smem_bwd = st_bwd + MSG_PIPE_BYTES;
   const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
   const bool memo = staged && fc.n0 > 0;   // two passes: memoised edges (light kernels), then direct edges

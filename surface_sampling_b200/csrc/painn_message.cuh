@@ -24,6 +24,8 @@ constexpr int MSG_THREADS = 256;  // direct pass: 8 warps
 constexpr int MSG_WARPS = MSG_THREADS / 32;
 constexpr int MSG_STAGES = 3;     // cp.async ring depth per warp
 constexpr int MSG_PIPE_BYTES = MSG_WARPS * MSG_STAGES * REC * 4;
+constexpr int MSG_STAGES_FWD = 4;    // direct forward pass: two edges per iteration, two more in flight
+constexpr int MSG_PIPE_BYTES_FWD = MSG_WARPS * MSG_STAGES_FWD * REC * 4;
 constexpr int MEMO_THREADS_FWD = 768;   // memo pass: 24 warps share one staged structure
 constexpr int MEMO_THREADS_BWD = 512;
 
@@ -285,8 +287,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
   constexpr int PER = MsgFwdLayout<FIRST>::PER;
   constexpr int N16 = (REC_RE + 44) / 4;  // 13 x 16 B: geometry + rbf rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* ring = smem_all + warp * MSG_STAGES * REC;
-  float* smem = smem_all + MSG_WARPS * MSG_STAGES * REC;
+  float* ring = smem_all + warp * MSG_STAGES_FWD * REC;
+  float* smem = smem_all + MSG_WARPS * MSG_STAGES_FWD * REC;
   const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
   const int h = blockIdx.y, m = blockIdx.z;
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
@@ -320,28 +322,43 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
     const int ne = __ldg(nvalid + i);
     if (accum && ne == 0) continue;   // nothing to add to the memo pass' result
     float2 ds = dup2(0.f), dvx = dup2(0.f), dvy = dup2(0.f), dvz = dup2(0.f);
+    // two edges per iteration: their filter evaluations (2 x 60 independent FFMA2 on the same weight registers)
+    // and gathers interleave, which hides the shared-memory latencies that 8 warps per SM cannot
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < MSG_STAGES - 1; ++s) prefetch_record(ring + s * REC, rec0 + (long long)s * REC, lane, N16, s < ne);
-    for (int e = 0; e < ne; ++e) {
-      wait_record();
-      const int nx = e + MSG_STAGES - 1;
-      prefetch_record(ring + (nx % MSG_STAGES) * REC, rec0 + (long long)nx * REC, lane, N16, nx < ne);
-      const float* rec = ring + (e % MSG_STAGES) * REC;
-      const float4 g = *reinterpret_cast<const float4*>(rec);
-      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
-      const float4 ev = r4[10];  // (env,env,denv,denv)
-      const float2 env2 = make_float2(ev.x, ev.y);
-      float2 w0 = __fmul2_rn(bd0, env2), w1 = __fmul2_rn(bd1, env2), w2 = __fmul2_rn(bd2, env2);
+    for (int s = 0; s < MSG_STAGES_FWD; ++s) prefetch_record(ring + s * REC, rec0 + (long long)s * REC, lane, N16, s < ne);
+    for (int e = 0; e < ne; e += 2) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(MSG_STAGES_FWD - 2));   // records e and e+1 have landed
+      __syncwarp();
+      const float* reca = ring + (e % MSG_STAGES_FWD) * REC;
+      const float* recb = ring + ((e + 1) % MSG_STAGES_FWD) * REC;
+      const float4 ga = *reinterpret_cast<const float4*>(reca), gb = *reinterpret_cast<const float4*>(recb);
+      const float4* ra4 = reinterpret_cast<const float4*>(reca + REC_RE);
+      const float4* rb4 = reinterpret_cast<const float4*>(recb + REC_RE);
+      const float4 eva = ra4[10], evb = rb4[10];  // (env,env,denv,denv)
+      const float2 enva = make_float2(eva.x, eva.y), envb = make_float2(evb.x, evb.y);
+      float2 w0a = __fmul2_rn(bd0, enva), w1a = __fmul2_rn(bd1, enva), w2a = __fmul2_rn(bd2, enva);
+      float2 w0b = __fmul2_rn(bd0, envb), w1b = __fmul2_rn(bd1, envb), w2b = __fmul2_rn(bd2, envb);
 #pragma unroll
       for (int q = 0; q < NRBF / 2; ++q) {
-        const float4 t = r4[q];
-        const float2 ra = make_float2(t.x, t.y), rb = make_float2(t.z, t.w);
-        w0 = __ffma2_rn(wd0[2 * q], ra, w0); w1 = __ffma2_rn(wd1[2 * q], ra, w1); w2 = __ffma2_rn(wd2[2 * q], ra, w2);
-        w0 = __ffma2_rn(wd0[2 * q + 1], rb, w0); w1 = __ffma2_rn(wd1[2 * q + 1], rb, w1);
-        w2 = __ffma2_rn(wd2[2 * q + 1], rb, w2);
+        const float4 ta = ra4[q], tb = rb4[q];
+        const float2 a0r = make_float2(ta.x, ta.y), a1r = make_float2(ta.z, ta.w);
+        const float2 b0r = make_float2(tb.x, tb.y), b1r = make_float2(tb.z, tb.w);
+        w0a = __ffma2_rn(wd0[2 * q], a0r, w0a); w1a = __ffma2_rn(wd1[2 * q], a0r, w1a); w2a = __ffma2_rn(wd2[2 * q], a0r, w2a);
+        w0b = __ffma2_rn(wd0[2 * q], b0r, w0b); w1b = __ffma2_rn(wd1[2 * q], b0r, w1b); w2b = __ffma2_rn(wd2[2 * q], b0r, w2b);
+        w0a = __ffma2_rn(wd0[2 * q + 1], a1r, w0a); w1a = __ffma2_rn(wd1[2 * q + 1], a1r, w1a);
+        w2a = __ffma2_rn(wd2[2 * q + 1], a1r, w2a);
+        w0b = __ffma2_rn(wd0[2 * q + 1], b1r, w0b); w1b = __ffma2_rn(wd1[2 * q + 1], b1r, w1b);
+        w2b = __ffma2_rn(wd2[2 * q + 1], b1r, w2b);
       }
-      fwd_edge<FIRST>(g, smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane, w0, w1, w2, ds, dvx, dvy, dvz);
+      const int ja = __float_as_int(reca[REC_EJ]), jb = __float_as_int(recb[REC_EJ]);
+      fwd_edge<FIRST>(ga, smem + (ja - a0) * PER + 2 * lane, w0a, w1a, w2a, ds, dvx, dvy, dvz);
+      if (e + 1 < ne) fwd_edge<FIRST>(gb, smem + (jb - a0) * PER + 2 * lane, w0b, w1b, w2b, ds, dvx, dvy, dvz);
+      __syncwarp();   // both stages are free again
+      prefetch_record(ring + (e % MSG_STAGES_FWD) * REC, rec0 + (long long)(e + MSG_STAGES_FWD) * REC, lane, N16,
+                      e + MSG_STAGES_FWD < ne);
+      prefetch_record(ring + ((e + 1) % MSG_STAGES_FWD) * REC, rec0 + (long long)(e + 1 + MSG_STAGES_FWD) * REC, lane, N16,
+                      e + 1 + MSG_STAGES_FWD < ne);
     }
     float* so = cat + (long long)il * 2 * F + f0;
     float* vo = v_mid + (long long)il * 3 * F + f0;
