@@ -248,6 +248,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1) // 2))   # host threads are for launching, not for BLAS
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
@@ -321,6 +322,8 @@ def main():
     for _ in range(args.warmup):
         pipe.advance()
     sampler = ClockSampler(local)
+    if rank != 0:
+        sampler.start = lambda: None      # one nvidia-smi poller per job (rank 0's GPU): N pollers contend for the driver
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

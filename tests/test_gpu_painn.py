@@ -212,6 +212,19 @@ def test_frozen_pair_filter_memo(structures, potentials, sto_weights):
         ra = solo.energy_forces(_batch(structs + structs[:1]))
         rb = (cons if cons_mode else memo).energy_forces(_batch(structs + structs[:1]))
         assert torch.equal(ra["energy"], rb["energy"]) and torch.equal(ra["forces"], rb["forces"])
+    # mixed batch: one structure has a "frozen" atom displaced (its rows lose memo hits => not canonical => the
+    # group kernels hand its whole group to the one-structure kernels); a 16-adsorbate structure exceeds the
+    # group kernels' shared-memory budget.  Same answers as without any memo.
+    bad = dict(base)
+    bad["positions"] = base["positions"].copy()
+    bad["positions"][np.flatnonzero(fixed0)[5]] += 0.01
+    mixed = [structs[1], bad, structs[2], structs[0], structs[1], structs[2], bad]
+    rm, rp = memo.energy_forces(_batch(mixed)), plain.energy_forces(_batch(mixed))
+    assert (rm["energy"] - rp["energy"]).abs().max().item() < 2e-6 * 60
+    assert (rm["forces"] - rp["forces"]).abs().max().item() < 2e-5
+    big = [with_adsorbates(base, rng, 16, [8, 38, 22]), structs[0], structs[1]]
+    rm, rp = memo.energy_forces(_batch(big)), plain.energy_forces(_batch(big))
+    assert (rm["forces"] - rp["forces"]).abs().max().item() < 2e-5 + 2e-6 * rp["forces"].abs().max().item()
     # a framework that does not match the batch (shifted atoms) silently disables the memo: same answers
     other = engine.PainnEngine(sto_weights, od)
     other.set_framework(base["positions"] + 0.123, base["cell"], PBC3, fixed0)
