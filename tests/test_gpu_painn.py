@@ -234,3 +234,20 @@ def test_frozen_pair_filter_memo(structures, potentials, sto_weights):
     other.set_framework(base["positions"] + 0.123, base["cell"], PBC3, fixed0)
     r2 = other.energy_forces(_batch(structs))
     assert torch.equal(r2["forces"], r0["forces"]) or (r2["forces"] - r0["forces"]).abs().max().item() < 2e-5
+
+
+def test_large_structure_global_gather_path(structures):
+    """Structures beyond the shared-memory staging budget (> 84 atoms) take the global-gather message kernels;
+    same tolerances vs the oracle, also inside a batch with a small structure."""
+    from surface_sampling_b200 import engine
+    states = [init_random_weights(s) for s in (0, 1, 2)]
+    eng = engine.PainnEngine(states, None)
+    ens = EnsembleOracle(states, None, dtype=torch.float64)
+    base = structures["SrTiO3_001_2x2"]
+    ztop = base["positions"][:, 2].max()
+    grid = np.array([[0.5 + 1.9 * (a % 4) + 0.9 * (a // 16), 0.5 + 1.9 * ((a // 4) % 4) + 0.9 * (a // 16),
+                      ztop + 1.5 + 1.9 * (a // 16)] for a in range(32)])
+    big = {"positions": np.vstack([base["positions"], grid]), "cell": base["cell"],
+           "numbers": np.concatenate([base["numbers"], np.array([8, 38, 22, 8] * 8)])}
+    assert len(big["numbers"]) == 92
+    _compare(eng, ens, [big, base])
