@@ -34,6 +34,22 @@ def _set_positions(atoms, pos):
     atoms.positions = np.asarray(pos, dtype=float).copy()
 
 
+def _auto_framework(engine, pos, cell, pbc, fixed):
+    """Register the slab's FixAtoms block as the engine's frozen framework (radial-filter memo + no dE/dx on
+    frozen atoms during the FIRE steps; engine.PainnEngine.set_framework).  The MC loop calls optimize_slab
+    with the same bulk over and over, so the one-time build is cached on the engine by a hash of the frozen
+    coordinates.  Results of the relaxation are unchanged (tests/test_gpu_painn.py, test_gpu_boundary.py)."""
+    if not hasattr(engine, "set_framework") or not np.any(fixed):
+        return
+    n0 = int(np.flatnonzero(fixed)[-1]) + 1
+    p0 = np.ascontiguousarray(pos[:n0], dtype=np.float32)
+    key = (n0, hash(p0[np.asarray(fixed[:n0], bool)].tobytes()), hash(np.asarray(cell, dtype=np.float64).tobytes()),
+           hash(np.asarray(fixed[:n0], bool).tobytes()))
+    if getattr(engine, "_auto_fc_key", None) != key:
+        engine.set_framework(p0, cell, pbc, np.asarray(fixed[:n0], bool), constrained_forces=True)
+        engine._auto_fc_key = key
+
+
 def optimize_slab(slab, optimizer="FIRE", save_traj=True, logger=None, **kwargs) -> tuple:
     logger = logger or logging.getLogger(__name__)
     calc = slab.calc
@@ -50,6 +66,7 @@ def optimize_slab(slab, optimizer="FIRE", save_traj=True, logger=None, **kwargs)
         engine = calc.engine
         pos, num, cell, pbc, fixed = as_arrays(slab)
         batch = eng.Batch.from_arrays([pos], [num], [cell], [pbc], [fixed])
+        _auto_framework(engine, pos, cell, pbc, fixed)
         calc_slab = slab.copy()
         calc_slab.calc = calc
         if not save_traj:

@@ -255,10 +255,11 @@ class PainnEngine:
     def clear_framework(self):
         self._fc = None
 
-    def _fc_args(self):
+    def _fc_args(self, constrained: bool = True):
         if self._fc is None:
             return None, 0, 0, 0
-        return self._fc[0].data_ptr(), self._fc[1], self._fc[2], self._fc[4]
+        flags = self._fc[4] if constrained else (self._fc[4] & ~1)
+        return self._fc[0].data_ptr(), self._fc[1], self._fc[2], flags
 
     # -- H5 stoichiometric offset (per structure, host, exact fp64) ---------------------------
     def offsets_ev(self, z_host: np.ndarray, atom_ptr: np.ndarray) -> np.ndarray | None:
@@ -278,8 +279,11 @@ class PainnEngine:
             tot = tot + cnt * float(sto[sym])
         return tot * HARTREE_TO_KCAL_MOL / KCAL_PER_EV
 
-    def energy_forces(self, batch: Batch, z_host: np.ndarray | None = None, want_embedding=False, nbrs=None):
-        """One ensemble evaluation of every structure in the batch."""
+    def energy_forces(self, batch: Batch, z_host: np.ndarray | None = None, want_embedding=False, nbrs=None,
+                      constrained_forces: bool = False):
+        """One ensemble evaluation of every structure in the batch.  Forces are the raw forces on every
+        atom (what EnsembleNFF.calculate returns) unless constrained_forces=True AND the framework was
+        registered with constrained_forces=True: then the force rows of its frozen atoms are zero."""
         lib, dev = self.lib, self.device
         A, B, M = batch.n_atoms, batch.n_struct, self.n_models
         if nbrs is None:
@@ -298,7 +302,7 @@ class PainnEngine:
         emb = torch.empty((M, A, F), dtype=torch.float32, device=dev) if want_embedding else None
         _lib.check(lib.vssr_painn_energy_grad(_ptr(self.weights), M, _ptr(pos32), _ptr(batch.z), _ptr(batch.atom_ptr),
                                               _ptr(cell32), B, A, batch.max_atoms, _ptr(rowptr), _ptr(col), _ptr(shift), e_cap,
-                                              self.cutoff, *self._fc_args(), _ptr(ws), ws.numel(), _ptr(energy), _ptr(grad), _ptr(emb),
+                                              self.cutoff, *self._fc_args(constrained_forces), _ptr(ws), ws.numel(), _ptr(energy), _ptr(grad), _ptr(emb),
                                               _stream()), "vssr_painn_energy_grad")
         off = None
         if self.offset_data is not None:

@@ -194,7 +194,9 @@ def test_frozen_pair_filter_memo(structures, potentials, sto_weights):
     cons = engine.PainnEngine(sto_weights, od)
     cons.set_framework(base["positions"], base["cell"], PBC3, fixed0, constrained_forces=True)
     b3 = _batch(structs)
-    r3 = cons.energy_forces(b3)
+    r3 = cons.energy_forces(b3, constrained_forces=True)
+    r3f = cons.energy_forces(b3)           # calculators keep the raw forces on every atom
+    assert torch.equal(r3f["forces"], r1["forces"])
     assert torch.equal(r3["energy"], r1["energy"])
     frozen = torch.from_numpy(np.concatenate(fixed)).cuda()
     assert torch.equal(r3["forces"][~frozen], r1["forces"][~frozen])
@@ -209,8 +211,8 @@ def test_frozen_pair_filter_memo(structures, potentials, sto_weights):
     for cons_mode in (False, True):
         solo = engine.PainnEngine(sto_weights, od)
         solo.set_framework(base["positions"], base["cell"], PBC3, fixed0, constrained_forces=cons_mode, pair_kernels=False)
-        ra = solo.energy_forces(_batch(structs + structs[:1]))
-        rb = (cons if cons_mode else memo).energy_forces(_batch(structs + structs[:1]))
+        ra = solo.energy_forces(_batch(structs + structs[:1]), constrained_forces=cons_mode)
+        rb = (cons if cons_mode else memo).energy_forces(_batch(structs + structs[:1]), constrained_forces=cons_mode)
         assert torch.equal(ra["energy"], rb["energy"]) and torch.equal(ra["forces"], rb["forces"])
     # mixed batch: one structure has a "frozen" atom displaced (its rows lose memo hits => not canonical => the
     # group kernels hand its whole group to the one-structure kernels); a 16-adsorbate structure exceeds the
