@@ -146,13 +146,17 @@ class ChainState:
     def propose_switch(self):
         """SwitchProposal.get_action -> get_complementary_idx with uniform weights (slab.py:168-232).
         Note the reference's groupby-into-dict keeps only the LAST run of each symbol; replicated."""
-        filled = np.argwhere(self.occ != 0).flatten().tolist()
-        curr = {k: list(g) for k, g in itertools.groupby(filled, key=lambda x: SYMBOLS[self.numbers[self.occ[x]]])}
-        empty = np.argwhere(self.occ == 0).flatten().tolist()
+        occ = self.occ.tolist()
+        filled = [x for x, o in enumerate(occ) if o != 0]
+        numbers = self.numbers
+        curr = {k: list(g) for k, g in itertools.groupby(filled, key=lambda x: SYMBOLS[numbers[occ[x]]])}
+        empty = [x for x, o in enumerate(occ) if o == 0]
         if empty:
             curr["None"] = empty
         t1, t2 = self.py_rng.sample(list(curr.keys()), 2)
-        s1, s2 = (self.py_rng.choices(curr[t], weights=np.ones_like(curr[t]), k=1)[0] for t in (t1, t2))
+        # random.choices(pop, weights=ones, k=1) draws ONE random() and bisects the cumulative weights 1..n at
+        # r*n, i.e. picks pop[floor(r*n)]: same draw, same element, without building numpy weight arrays
+        s1, s2 = (curr[t][int(self.py_rng.random() * len(curr[t]))] for t in (t1, t2))
         return {"name": "switch", "site1_idx": s1, "site2_idx": s2, "site1_ads": t1, "site2_ads": t2}
 
     def apply(self, action):
