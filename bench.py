@@ -194,7 +194,15 @@ def workload_config(args, chains):
             "l2": "per-evaluation working set (activations ~48 KB/atom/model, >1 GB) exceeds the 126 MB L2; no explicit flush"
                   if args.workload == "sto_painn" else "whole relaxation is shared-memory resident; L2 is not on the path",
             "parallelism": f"chains sharded, {args.gpus} rank(s), no data-path collective",
-            "e2e_driver": f"MultiChainMC.pipeline, {max(1, args.groups)} chain group(s) per GPU; value = one batch of all chains per step"}
+            "e2e_driver": f"MultiChainMC.pipeline, {max(1, args.groups)} chain group(s) per GPU; value = one batch of all chains per step",
+            "engine_options": ({"filter_memo": not os.environ.get("VSSR_NO_FILTER_MEMO"),
+                                "constrained_gradients": not (os.environ.get("VSSR_FULL_GRAD") or os.environ.get("VSSR_NO_FILTER_MEMO")),
+                                "note": "every evaluation runs the full 3-layer forward and backward of all 3 models; the memo holds the "
+                                        "radial filter rows w(d), dw/dd of frozen-frozen pairs (functions of weights and the frozen "
+                                        "geometry only), and dE/dx of FixAtoms atoms -- which the optimiser discards -- is not formed "
+                                        "during FIRE steps; energies, positions and accept/reject are bit-identical to the plain mode "
+                                        "(tests/test_gpu_painn.py); VSSR_FULL_GRAD=1 / VSSR_NO_FILTER_MEMO=1 switch them off"}
+                               if args.workload == "sto_painn" else None)}
 
 
 def run_reference(args):
