@@ -74,6 +74,25 @@ class ChainState:
         self.numbers, self.positions, self.ads_group, self.occ, self.results = (
             list(snap[0]), list(snap[1]), list(snap[2]), snap[3].copy(), dict(snap[4]))
 
+    # ---- checkpoint (SurfaceSystem.todict/fromdict, system.py:591-653; here incl. both RNG states, which the
+    # reference does not checkpoint: a resumed chain continues bit-identically) ----
+    def todict(self) -> dict:
+        return {"n0": self.n0, "numbers": list(self.numbers), "positions": np.array(self.positions, dtype=float).reshape(-1, 3),
+                "ads_group": list(self.ads_group), "ads_coords": self.ads_coords.copy(), "occ": self.occ.copy(),
+                "results": dict(self.results), "np_rng": self.np_rng.get_state(), "py_rng": self.py_rng.getstate()}
+
+    @classmethod
+    def fromdict(cls, d: dict) -> "ChainState":
+        n0 = int(d["n0"])
+        c = cls(d["numbers"][:n0], d["positions"][:n0], d["ads_coords"], occ=d["occ"], ads_group0=d["ads_group"][:n0])
+        c.numbers = [int(z) for z in d["numbers"]]
+        c.positions = [np.asarray(p, dtype=float) for p in d["positions"]]
+        c.ads_group = [int(g) for g in d["ads_group"]]
+        c.results = dict(d["results"])
+        c.np_rng.set_state(d["np_rng"])
+        c.py_rng.setstate(d["py_rng"])
+        return c
+
     @property
     def num_adsorbates(self):
         return int(np.count_nonzero(self.occ))
@@ -311,12 +330,24 @@ class MultiChainMC:
                 return
             self.step(active=todo, force_semigrand=[True] * len(todo))
 
+    def state_dict(self) -> dict:
+        """Everything needed to resume: chain states with their RNG streams, temperature, counters."""
+        return {"chains": [c.todict() for c in self.chains], "temp": self.temp, "n_relaxed": self.n_relaxed,
+                "decisions": [list(d) for d in self.decisions]}
+
+    def load_state_dict(self, sd: dict):
+        self.chains = [ChainState.fromdict(d) for d in sd["chains"]]
+        self.temp, self.n_relaxed = sd["temp"], sd["n_relaxed"]
+        self.decisions = [list(d) for d in sd["decisions"]]
+
     def run(self, total_sweeps=10, sweep_size=20, start_temp=1.0, perform_annealing=True, alpha=0.99,
-            anneal_schedule=None, gather=None):
+            anneal_schedule=None, gather=None, starting_iteration=0, history=False):
         """MCMC.run (mcmc.py:301-390) for every chain; returns per-chain histories
-        (energy_hist, frac_accept_hist, adsorption_count_hist) as [C, total_sweeps] arrays."""
+        (energy_hist, frac_accept_hist, adsorption_count_hist) as [C, total_sweeps] arrays.
+        `starting_iteration` resumes a run (mcmc.py:313,381) after load_state_dict; `history=True` also returns
+        the per-sweep chain snapshots (`results["history"]`, scripts/sample_surface.py:204-208) as todict()s."""
         self.temp = start_temp
-        if self.canonical:
+        if self.canonical and starting_iteration == 0:
             self.prepare_canonical()
         if anneal_schedule is not None:
             temps = list(anneal_schedule)
@@ -328,7 +359,8 @@ class MultiChainMC:
         energy_hist = np.zeros((C, total_sweeps))
         frac_accept = np.zeros((C, total_sweeps))
         ads_count = np.zeros((C, total_sweeps), dtype=int)
-        for i in range(total_sweeps):
+        snapshots = []
+        for i in range(int(starting_iteration), total_sweeps):
             self.temp = temps[i]
             n_acc = np.zeros(C)
             for _ in range(sweep_size):
@@ -337,9 +369,14 @@ class MultiChainMC:
             energy_hist[:, i] = [c.results["surface_energy"] for c in self.chains]
             frac_accept[:, i] = n_acc / sweep_size
             ads_count[:, i] = [c.num_adsorbates for c in self.chains]
+            if history:
+                snapshots.append([c.todict() for c in self.chains])
             if gather is not None:
                 gather(i, energy_hist[:, i], frac_accept[:, i], ads_count[:, i])
-        return {"energy_hist": energy_hist, "frac_accept_hist": frac_accept, "adsorption_count_hist": ads_count}
+        out = {"energy_hist": energy_hist, "frac_accept_hist": frac_accept, "adsorption_count_hist": ads_count}
+        if history:
+            out["history"] = snapshots
+        return out
 
 
 class _Pipeline:
@@ -369,3 +406,13 @@ class _Pipeline:
             if self.tickets[gi] is not None:
                 self.drv.step_end(self.tickets[gi])
                 self.tickets[gi] = None
+
+
+def write_stats_csv(path, results: dict, chain: int = 0):
+    """stats.csv of one chain in the reference's format (scripts/sample_surface.py:220-229: columns energy,
+    frac_accept, adsorption_count; float_format %.3f, no index)."""
+    e, f, a = (np.asarray(results[k])[chain] for k in ("energy_hist", "frac_accept_hist", "adsorption_count_hist"))
+    with open(path, "w") as fh:
+        fh.write("energy,frac_accept,adsorption_count\n")
+        for k in range(len(e)):
+            fh.write("%.3f,%.3f,%d\n" % (e[k], f[k], int(a[k])))

@@ -110,3 +110,27 @@ def test_pipelined_groups_make_the_same_decisions():
     for a, b in zip(drv.chains, ref.chains):
         assert np.array_equal(a.occ, b.occ) and np.array_equal(a.arrays()[0], b.arrays()[0])
     assert [f[3] for f in flags] == [d[0] for d in ref.decisions[3]]
+
+
+def test_checkpoint_resume_and_stats_csv(tmp_path):
+    """8f-3: state_dict/load_state_dict (incl. both RNG streams) resumes a run bit-identically at a sweep
+    boundary; stats.csv is written in the reference's format."""
+    import pickle
+    seeds = [3, 4, 5]
+    ref, _ = _driver(seeds)
+    full = ref.run(total_sweeps=4, sweep_size=5, start_temp=1.0, alpha=0.9, history=True)
+    a, _ = _driver(seeds)
+    part = a.run(total_sweeps=2, sweep_size=5, start_temp=1.0, alpha=0.9)
+    blob = pickle.dumps(a.state_dict())
+    b, _ = _driver([99, 98, 97])                      # different seeds: everything must come from the checkpoint
+    b.load_state_dict(pickle.loads(blob))
+    rest = b.run(total_sweeps=4, sweep_size=5, start_temp=1.0, alpha=0.9, starting_iteration=2)
+    assert np.array_equal(part["energy_hist"][:, :2], full["energy_hist"][:, :2])
+    assert np.array_equal(rest["energy_hist"][:, 2:], full["energy_hist"][:, 2:])
+    assert np.array_equal(rest["adsorption_count_hist"][:, 2:], full["adsorption_count_hist"][:, 2:])
+    assert b.decisions == ref.decisions
+    assert len(full["history"]) == 4 and np.array_equal(full["history"][-1][1]["occ"], ref.chains[1].occ)
+    mc.write_stats_csv(tmp_path / "stats.csv", full, chain=1)
+    lines = (tmp_path / "stats.csv").read_text().splitlines()
+    assert lines[0] == "energy,frac_accept,adsorption_count" and len(lines) == 5
+    assert lines[1] == "%.3f,%.3f,%d" % (full["energy_hist"][1, 0], full["frac_accept_hist"][1, 0], full["adsorption_count_hist"][1, 0])
