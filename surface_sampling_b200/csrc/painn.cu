@@ -888,7 +888,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const size_t sm_fwd0 = st_fwd0 + memo_ring, sm_fwd = st_fwd + memo_ring;
   const size_t sm_state = (size_t)nmax * MEMO_STATE_PER * 4 + memo_ring;
   // group kernels: G canonical structures per CTA (as many as fit in shared memory), no ring
-  constexpr int G_FWD0 = 4, T_FWD0 = 512, G_FWD = 2, T_FWD = 512, G_STATE = 2, T_STATE = 512;
+  constexpr int G_FWD0 = 4, T_FWD0 = 512, G_FWD = 2, T_FWD = 832, G_STATE = 2, T_STATE = 512;
   const bool group_on = memo && !(fc_flags & VSSR_FC_NO_PAIR);
   const size_t sp_fwd0 = G_FWD0 * st_fwd0, sp_fwd = G_FWD * st_fwd, sp_state = (size_t)G_STATE * nmax * MEMO_STATE_PER * 4;
   const bool pair_fwd0 = group_on && n_struct >= G_FWD0 && sp_fwd0 <= 227 * 1024;

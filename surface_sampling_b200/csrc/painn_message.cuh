@@ -783,14 +783,14 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
 // the per-edge LSU work -- the bound of the single-structure memo kernels -- nearly halves, and no
 // per-chain records are read at all.  Same per-edge arithmetic in the same order => same bits.
 // ============================================================================================
-template <bool ROW0, typename Body>
+template <bool ROW0, int U, typename Body>
 __device__ __forceinline__ void canon_walk(const float4* __restrict__ mr, int ne, int lane,
                                            const float* __restrict__ wlane, Body body) {
   for (int base = 0; base < ne; base += 32) {
     const int cnt = min(32, ne - base);
     float4 gl = make_float4(0.f, 0.f, 0.f, 1.f), jl = make_float4(0.f, 0.f, 1.f, 0.f);
     if (lane < cnt) { gl = __ldg(mr + 2 * (base + lane)); jl = __ldg(mr + 2 * (base + lane) + 1); }
-#pragma unroll 4
+#pragma unroll U
     for (int e = 0; e < cnt; ++e) {
       const int slot = __shfl_sync(0xffffffffu, __float_as_int(jl.y), e);
       const float* wr = wlane + (long long)slot * F3;
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(T, 1) message_fwd_memo_group(
     for (int s = 0; s < G; ++s) ds[s] = dvx[s] = dvy[s] = dvz[s] = dup2(0.f);
     if (il < fc.n0) {
       const float4* mr = reinterpret_cast<const float4*>(fc.mrec0 + (long long)__ldg(fc.rowptr + il) * MREC);
-      canon_walk<!FIRST>(mr, __ldg(fc.nmemo0 + il), lane, wlane, [&](const float4 g, int j, float2 w0, float2 w1, float2 w2) {
+      canon_walk<!FIRST, (T > 640 ? 2 : 4)>(mr, __ldg(fc.nmemo0 + il), lane, wlane, [&](const float4 g, int j, float2 w0, float2 w1, float2 w2) {
 #pragma unroll
         for (int s = 0; s < G; ++s) fwd_edge<FIRST>(g, sm[s] + j * PER + 2 * lane, w0, w1, w2, ds[s], dvx[s], dvy[s], dvz[s]);
       });
@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(T, 1) message_bwd_memo_state_group(
     }
     if (il < fc.n0) {
       const float4* mr = reinterpret_cast<const float4*>(fc.mrec0 + (long long)__ldg(fc.rowptr + il) * MREC);
-      canon_walk<true>(mr, __ldg(fc.nmemo0 + il), lane, wlane, [&](const float4 g, int j, float2 w0, float2 w1, float2 w2) {
+      canon_walk<true, (T > 640 ? 2 : 4)>(mr, __ldg(fc.nmemo0 + il), lane, wlane, [&](const float4 g, int j, float2 w0, float2 w1, float2 w2) {
 #pragma unroll
         for (int s = 0; s < G; ++s) {
           const float* sj = sm[s] + j * PER + 2 * lane;
