@@ -9,14 +9,18 @@
 // 66 TFLOP/s vs 42 for scalar FFMA (profiles/microbench/ffma2.cu).
 //
 // Two passes per layer, because the two kinds of edges want opposite register budgets:
-//   *_memo  : edges whose radial filter is memoised (frozen pairs, see FilterCacheView).  The filter
-//             rows are simply loaded, so a thread needs ~60 registers and the CTA runs 16-32 warps:
-//             the per-edge dependency chain (record -> gather -> FMA) hides behind other warps.
-//   *_v2    : all remaining ("direct") edges.  The filter w(d) = Wd.(rbf*env) + bd*env is evaluated in
-//             60 register pairs per lane (120 FFMA2 per edge in the backward), 8 warps per CTA; per-edge
-//             records stream through a private 3-stage cp.async ring per warp.
+//   *_memo*  : edges whose radial filter is memoised (frozen pairs, see FilterCacheView).  The filter
+//              rows are simply loaded, so a thread needs 60-120 registers and the CTA runs 16-26 warps.
+//              *_group kernels: G "canonical" structures per CTA walk the framework's own edge lists and
+//              share every filter row (the normal case); *_memo / *_memo_state: one structure per CTA with
+//              the rows in a per-warp cp.async ring (fallback); message_bwd_memo: full-gradient variant.
+//   *_v2     : all remaining ("direct") edges.  The filter w(d) = Wd.(rbf*env) + bd*env is evaluated in
+//              60 register pairs per lane (120 FFMA2 per edge in the backward), 8 warps per CTA; per-edge
+//              records stream through a private cp.async ring per warp.  Frozen receivers in constrained
+//              mode only need the state terms (no dw/dd).
 // The second pass accumulates onto the first (fixed order: memoised edges, then direct edges).
-// Determinism: a lane walks its receiver's edge lists serially; there are no atomics.
+// Rows are handed to warps most-expensive-first (row_order_kernel + a shared-memory counter).
+// Determinism: a lane walks its receiver's edge lists serially; there are no atomics on data.
 #pragma once
 
 constexpr int MSG_FC = 64;        // features per CTA
