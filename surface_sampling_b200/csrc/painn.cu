@@ -207,7 +207,18 @@ inline bool use_tensor_cores() {
 template <int BN, int AMODE, int EPI>
 int run_gemm(GemmArgs g, const float* Bkn, int ldb_kn, const float* Bnk, int n_models, cudaStream_t st) {
   g.B = Bkn; g.ldb = ldb_kn; g.sB = W_STRIDE;
-  if (use_tensor_cores()) return launch_gemm_tc<BN, AMODE, EPI>(g, Bnk + W_TOTAL, Bnk + 2 * W_TOTAL, W_STRIDE, n_models, st);
+  if (use_tensor_cores()) {
+    // wave quantisation: a 128-column GEMM on ~8000 rows is 195 tiles = 1.3 waves of the 148 persistent CTAs, i.e.
+    // two rounds; with 64-column tiles it is 390 half-size tiles = three half rounds
+    if (BN == 128 && AMODE == 0 && g.N == 128) {
+      static int narrow = -1;
+      if (narrow < 0) { const char* e = getenv("VSSR_GEMM_NARROW"); narrow = e ? atoi(e) : 1; }
+      const long long tiles = (long long)ceil_div(g.M, 128) * n_models;
+      if (narrow && tiles < 2 * 148)
+        return launch_gemm_tc<64, AMODE, EPI>(g, Bnk + W_TOTAL, Bnk + 2 * W_TOTAL, W_STRIDE, n_models, st);
+    }
+    return launch_gemm_tc<BN, AMODE, EPI>(g, Bnk + W_TOTAL, Bnk + 2 * W_TOTAL, W_STRIDE, n_models, st);
+  }
   return launch_gemm<BN, AMODE, EPI>(g, n_models, st);
 }
 
