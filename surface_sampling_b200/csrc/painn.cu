@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <initializer_list>
+#include <type_traits>
 #include <mutex>
 #include <unordered_map>
 #include <utility>
@@ -237,6 +238,9 @@ int run_gemm(GemmArgs g, const float* Bkn, int ldb_kn, const float* Bnk, int n_m
 // ------------------------------------------------------------------------------------------
 constexpr int REC = 96, REC_EJ = 4, REC_SLOT = 5, REC_RE = 8, REC_DRE = 52;
 constexpr int MREC = 8;   // memoised-edge record: (ux,uy,uz,d), sender, slot, 1/d, pad
+// compact direct-edge record for the k-block kernels (256 B): [0..3] (u,d) [4] sender [6] key [7] 1/d
+// [8..27] rbf_n*env [28] env [29] denv [32..51] d(rbf_n*env)/dd   (scalars: FFMA2 broadcasts an .F32 operand)
+constexpr int CREC = 64, CREC_RE = 8, CREC_DRE = 32;
 
 // Radial-filter memo ("frozen-pair cache").  The filter w(d) = Wd.(rbf(d)*env(d)) + bd*env(d) and its
 // derivative q(d) depend on the edge only through the scalar d.  In VSSR-MC every chain shares the same
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
     int n_atoms, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const int8_t* __restrict__ shift, long long e_cap, float cutoff, FilterCacheView fc,
     int32_t* __restrict__ nvalid, float* __restrict__ erec, int32_t* __restrict__ nmemo, float* __restrict__ mrec,
-    float* __restrict__ evex, float* __restrict__ grad0) {
+    float* __restrict__ evex, float* __restrict__ grad0, float* __restrict__ crec) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n_atoms) return;
@@ -350,6 +354,12 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
         }
         float2* rrow = reinterpret_cast<float2*>(rec + REC_RE);
         float2* drow = reinterpret_cast<float2*>(rec + REC_DRE);
+        float* cr = crec ? crec + w * CREC : nullptr;
+        if (cr) {
+          *reinterpret_cast<float4*>(cr) = make_float4(ux, uy, uz, d);
+          *reinterpret_cast<float4*>(cr + 4) = make_float4(__int_as_float(j), __int_as_float(-1), __int_as_float(key), inv_d);
+          cr[CREC_RE + 20] = env; cr[CREC_RE + 21] = denv;
+        }
 #pragma unroll
         for (int n = 0; n < NRBF; ++n) {
           float r = 0.f, dr = 0.f;
@@ -363,6 +373,7 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
           const float a = r * env, bq = dr * env + r * denv;
           rrow[n] = make_float2(a, a);
           drow[n] = make_float2(bq, bq);
+          if (cr) { cr[CREC_RE + n] = a; cr[CREC_DRE + n] = bq; }
         }
         rrow[20] = make_float2(env, env);
         rrow[21] = make_float2(denv, denv);
@@ -716,6 +727,22 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
 
 #include "painn_message.cuh"
 
+// launch helpers of the k-block kernels: opt in to the dynamic shared memory once per size, profile, check
+template <int KB, bool FIRST, int T, typename... Args>
+int kb_launch_fwd(size_t smem, dim3 grid, cudaStream_t st, Args... args) {
+  static size_t cfg = 0;
+  if (smem > cfg) { VSSR_CUDA(cudaFuncSetAttribute(msg_fwd_kb<KB, FIRST, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = smem; }
+  VSSR_PROF(VSSR_K_MSG_FWD, st, (msg_fwd_kb<KB, FIRST, T><<<grid, T, smem, st>>>(args...)));
+  return VSSR_OK;
+}
+template <int KB, bool FIRST, int T, typename... Args>
+int kb_launch_bwd(size_t smem, dim3 grid, cudaStream_t st, Args... args) {
+  static size_t cfg = 0;
+  if (smem > cfg) { VSSR_CUDA(cudaFuncSetAttribute(msg_bwd_kb<KB, FIRST, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = smem; }
+  VSSR_PROF(VSSR_K_MSG_BWD, st, (msg_bwd_kb<KB, FIRST, T><<<grid, T, smem, st>>>(args...)));
+  return VSSR_OK;
+}
+
 // ---- filter memo construction (one-time per framework + weights) ----
 struct CacheBlob {
   int32_t* rowptr; int32_t* nvalid; int32_t* key; int32_t* slot; float* d; float* wc; float* qc; int32_t* counter;
@@ -805,7 +832,7 @@ __global__ void __launch_bounds__(128) cache_fill_kernel(const float* __restrict
 
 struct Workspace {
   // edge records (compacted per row by edge_geometry_kernel)
-  int32_t* nvalid; float* erec; int32_t* nmemo; float* mrec; float* evex; float* grad0; float* gradp;
+  int32_t* nvalid; float* erec; float* crec; int32_t* nmemo; float* mrec; float* evex; float* grad0; float* gradp;
   int32_t* order_d; int32_t* order_m;   // per-structure row order, most direct / memoised edges first
   int32_t* canonical;                   // [A] (first n_struct used): structure carries exactly the framework's memo lists
   // activations
@@ -830,6 +857,7 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
   const size_t MA = (size_t)M * (size_t)A;
   w.nvalid = reinterpret_cast<int32_t*>(take(A));
   w.erec = take((size_t)e_cap * REC);
+  w.crec = take((size_t)e_cap * CREC);
   w.nmemo = reinterpret_cast<int32_t*>(take(A));
   w.order_d = reinterpret_cast<int32_t*>(take(A));
   w.order_m = reinterpret_cast<int32_t*>(take(A));
@@ -890,6 +918,15 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
   const bool memo = staged && fc.n0 > 0;   // two passes: memoised edges (light kernels), then direct edges
   const bool constrained = memo && (fc_flags & VSSR_FC_CONSTRAINED_GRAD);   // no dE/dx wanted on frozen atoms
+  // direct edges: optional variant with one kernel per filter block (k-block kernels, VSSR_MSG_KB=1).  OFF by
+  // default: parity-green and 16 warps/SM instead of 8, but measured slower than the fused kernels (fwd 22.1 ->
+  // 24.6 ms, bwd 31.6 -> 34.6-38.1 ms): the per-edge ring / shuffle / address overhead is paid three times and
+  // outweighs the occupancy gain (profiles/r2_notes.md section 5).
+  static int kb_env = -1;
+  if (kb_env < 0) { const char* e = getenv("VSSR_MSG_KB"); kb_env = e ? atoi(e) : 0; }
+  constexpr int KB_T = 256, KB_T0 = 512;   // threads: blocks 1, 2 (two CTAs per SM) / block 0 of the backward (one CTA)
+  const bool kb_on = staged && kb_env != 0;
+  auto kb_smem = [&](int per, int threads) { return (size_t)nmax * per * 4 + (size_t)kb_ring_floats(threads) * 4; };
   static int n_chunks_env = -1;
   if (n_chunks_env < 0) { const char* e = getenv("VSSR_MSG_CHUNKS"); n_chunks_env = e ? atoi(e) : 2; if (n_chunks_env < 1) n_chunks_env = 2; }
   const int n_chunks = n_chunks_env;   // CTAs per (structure, feature half, model) in the direct pass
@@ -933,7 +970,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
 
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(
       pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, staged ? fc : FilterCacheView{},
-      w.nvalid, w.erec, w.nmemo, w.mrec, w.evex, w.grad0));
+      w.nvalid, w.erec, w.nmemo, w.mrec, w.evex, w.grad0, kb_on ? w.crec : nullptr));
   if (staged)
     VSSR_PROF(VSSR_K_GEOM, st, row_order_kernel<<<n_struct, 128, (size_t)2 * nmax * sizeof(int32_t), st>>>(
         atom_ptr, w.nvalid, w.nmemo, w.order_d, w.order_m, memo ? fc.n0 : 0, fc.nmemo0, w.canonical));
@@ -961,6 +998,12 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<true><<<memo_grid, MEMO_THREADS_FWD, sm_fwd0, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l],
               pair_fwd0 ? w.canonical : nullptr, n_struct, G_FWD0));
+        if (kb_on) {
+          if ((rc = kb_launch_fwd<1, true, KB_T>(kb_smem(kb_fwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
+                                                 w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
+          if ((rc = kb_launch_fwd<2, true, KB_T>(kb_smem(kb_fwd_per(2), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
+                                                 w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
+        } else
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
             w.cat[l], w.vmid[l], memo ? 1 : 0));
@@ -972,6 +1015,14 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<false><<<memo_grid, MEMO_THREADS_FWD, sm_fwd, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l],
               pair_fwd ? w.canonical : nullptr, n_struct, G_FWD));
+        if (kb_on) {
+          if ((rc = kb_launch_fwd<1, false, KB_T>(kb_smem(kb_fwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
+                                                  w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
+          if ((rc = kb_launch_fwd<2, false, KB_T>(kb_smem(kb_fwd_per(2), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
+                                                  w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
+          if ((rc = kb_launch_fwd<0, false, KB_T>(kb_smem(kb_fwd_per(0), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
+                                                  w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
+        } else
         VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
             w.cat[l], w.vmid[l], memo ? 1 : 0));
@@ -1051,6 +1102,14 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
         if (memo && !constrained)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<true><<<memo_grid, MEMO_THREADS_BWD, st_bwd0, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp));
+        if (kb_on) {
+          const int acc = (memo && !constrained) ? 1 : 0;   // the full-gradient memo pass started state and gradp
+          const uint8_t* fz = constrained ? fc.frozen : nullptr;
+          if ((rc = kb_launch_bwd<1, true, KB_T>(kb_smem(kb_bwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
+                                                 w.nvalid, w.crec, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp, acc, acc, fz, fc.n0))) return rc;
+          if ((rc = kb_launch_bwd<2, true, KB_T>(kb_smem(kb_bwd_per(2), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
+                                                 w.nvalid, w.crec, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp, acc, 1, fz, fc.n0))) return rc;
+        } else
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
             dv_cur, nullptr, nullptr, w.gradp, (memo && !constrained) ? 3 : 0, constrained ? fc.frozen : nullptr, fc.n0));
@@ -1065,6 +1124,17 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
         else if (memo)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<false><<<memo_grid, MEMO_THREADS_BWD, st_bwd, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));
+        if (kb_on) {
+          const int acc = memo ? 1 : 0;                        // a memo pass started the state outputs
+          const int gacc = (memo && !constrained) ? 1 : 0;     // ... and gradp only in full-gradient mode
+          const uint8_t* fz = constrained ? fc.frozen : nullptr;
+          if ((rc = kb_launch_bwd<1, false, KB_T>(kb_smem(kb_bwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
+                                                  w.nvalid, w.crec, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp, acc, gacc, fz, fc.n0))) return rc;
+          if ((rc = kb_launch_bwd<2, false, KB_T>(kb_smem(kb_bwd_per(2), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
+                                                  w.nvalid, w.crec, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp, acc, 1, fz, fc.n0))) return rc;
+          if ((rc = kb_launch_bwd<0, false, KB_T0>(kb_smem(kb_bwd_per(0), KB_T0), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
+                                                   w.nvalid, w.crec, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp, acc, 1, fz, fc.n0))) return rc;
+        } else
         VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
             weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
             dv_cur, w.dphi, dv_nxt, w.gradp, constrained ? 1 : (memo ? 3 : 0), constrained ? fc.frozen : nullptr, fc.n0));
@@ -1155,7 +1225,7 @@ extern "C" int vssr_painn_filter_cache_build(const float* weights, int32_t n_mod
   if (rc) return rc;
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(n0, 4), 128, 0, st>>>(
       pos0, atom_ptr, cell, 1, n0, c.rowptr, col, shift, (long long)e_cap0, cutoff, FilterCacheView{}, c.nvalid, erec, nmemo, mrec,
-      evex, grad0));
+      evex, grad0, nullptr));
   VSSR_PROF(VSSR_K_GEOM, st, cache_slot_kernel<<<1, 32, 0, st>>>(erec, c.rowptr, c.nvalid, fixed0, n0, c.key, c.slot, c.d, c.counter));
   VSSR_PROF(VSSR_K_GEOM, st, cache_fill_kernel<<<dim3((unsigned)e_cap0, n_models * NCONV), 128, 0, st>>>(
       weights, erec, c.slot, (int)e_cap0, c.wc, c.qc));
@@ -1164,7 +1234,7 @@ extern "C" int vssr_painn_filter_cache_build(const float* weights, int32_t n_mod
     const FilterCacheView self = cache_view(cache, n_models, n0, e_cap0);
     VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(n0, 4), 128, 0, st>>>(
         pos0, atom_ptr, cell, 1, n0, c.rowptr, col, shift, (long long)e_cap0, cutoff, self, deg, erec, c.nmemo0, c.mrec0,
-        evex, grad0));
+        evex, grad0, nullptr));
     VSSR_PROF(VSSR_K_GEOM, st, row_order_kernel<<<1, 128, (size_t)2 * n0 * sizeof(int32_t), st>>>(
         atom_ptr, c.nmemo0, c.nmemo0, c.order0, nmemo, 0, nullptr, nullptr));
   }
