@@ -337,10 +337,20 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = int(lib.vssr_launch_count())
     io["h2d"] = io["d2h"] = 0
+    hostprof = None
+    if os.environ.get("VSSR_BENCH_HOSTPROF"):      # where does the host spend the e2e step? (stderr, rank 0)
+        import cProfile
+        hostprof = cProfile.Profile()
+        hostprof.enable()
     ev0.record()
     for _ in range(args.steps):
         pipe.advance()
     ev1.record()
+    if hostprof is not None:
+        hostprof.disable()
+        if rank == 0:
+            import pstats
+            pstats.Stats(hostprof, stream=sys.stderr).sort_stats("tottime").print_stats(18)
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
     e2e_launches = int(lib.vssr_launch_count()) - l0
