@@ -916,8 +916,14 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const size_t smem_fwd0 = st_fwd0 + MSG_PIPE_BYTES_FWD, smem_fwd = st_fwd + MSG_PIPE_BYTES_FWD;
   const size_t smem_bwd0 = st_bwd0 + MSG_PIPE_BYTES, smem_bwd = st_bwd + MSG_PIPE_BYTES;
   const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
-  const bool memo = staged && fc.n0 > 0;   // two passes: memoised edges (light kernels), then direct edges
-  const bool constrained = memo && (fc_flags & VSSR_FC_CONSTRAINED_GRAD);   // no dE/dx wanted on frozen atoms
+  // full-gradient memo backward: staged rows + a 3-stage (w,q) ring per warp
+  const size_t memo6_ring = (size_t)(MEMO_THREADS_BWD / 32) * MEMO6_STAGES * MEMO6_STAGE_FLOATS * 4;
+  const size_t sm_bwdm0 = st_bwd0 + memo6_ring, sm_bwdm = st_bwd + memo6_ring;
+  const bool want_constrained = (fc_flags & VSSR_FC_CONSTRAINED_GRAD) != 0;
+  // two passes: memoised edges (light kernels), then direct edges; a full-gradient evaluation of structures too
+  // large for the (w,q) ring simply runs without the memo
+  const bool memo = staged && fc.n0 > 0 && (want_constrained || sm_bwdm <= 227 * 1024);
+  const bool constrained = memo && want_constrained;   // no dE/dx wanted on frozen atoms
   // direct edges: optional variant with one kernel per filter block (k-block kernels, VSSR_MSG_KB=1).  OFF by
   // default: parity-green and 16 warps/SM instead of 8, but measured slower than the fused kernels (fwd 22.1 ->
   // 24.6 ms, bwd 31.6 -> 34.6-38.1 ms): the per-edge ring / shuffle / address overhead is paid three times and
@@ -959,8 +965,10 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if (memo) {
       if ((rc0 = want(4, (const void*)message_fwd_memo<true>, sm_fwd0))) return rc0;
       if ((rc0 = want(5, (const void*)message_fwd_memo<false>, sm_fwd))) return rc0;
-      if ((rc0 = want(6, (const void*)message_bwd_memo<true>, st_bwd0))) return rc0;
-      if ((rc0 = want(7, (const void*)message_bwd_memo<false>, st_bwd))) return rc0;
+      if (!constrained) {
+        if ((rc0 = want(6, (const void*)message_bwd_memo<true>, sm_bwdm0))) return rc0;
+        if ((rc0 = want(7, (const void*)message_bwd_memo<false>, sm_bwdm))) return rc0;
+      }
       if ((rc0 = want(8, (const void*)message_bwd_memo_state, sm_state))) return rc0;
       if (pair_fwd0 && (rc0 = want(9, (const void*)message_fwd_memo_group<true, G_FWD0, T_FWD0>, sp_fwd0))) return rc0;
       if (pair_fwd && (rc0 = want(10, (const void*)message_fwd_memo_group<false, G_FWD, T_FWD>, sp_fwd))) return rc0;
@@ -969,7 +977,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   }
 
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(
-      pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, staged ? fc : FilterCacheView{},
+      pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, memo ? fc : FilterCacheView{},
       w.nvalid, w.erec, w.nmemo, w.mrec, w.evex, w.grad0, kb_on ? w.crec : nullptr));
   if (staged)
     VSSR_PROF(VSSR_K_GEOM, st, row_order_kernel<<<n_struct, 128, (size_t)2 * nmax * sizeof(int32_t), st>>>(
@@ -1100,7 +1108,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       // accum bit 0: dphi/dv_in were started by a memo pass; bit 1: so was gradp
       if (l == 0) {
         if (memo && !constrained)
-          VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<true><<<memo_grid, MEMO_THREADS_BWD, st_bwd0, st>>>(
+          VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<true><<<memo_grid, MEMO_THREADS_BWD, sm_bwdm0, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp));
         if (kb_on) {
           const int acc = (memo && !constrained) ? 1 : 0;   // the full-gradient memo pass started state and gradp
@@ -1122,7 +1130,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt,
               pair_state ? w.canonical : nullptr, n_struct, G_STATE));
         else if (memo)
-          VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<false><<<memo_grid, MEMO_THREADS_BWD, st_bwd, st>>>(
+          VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<false><<<memo_grid, MEMO_THREADS_BWD, sm_bwdm, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));
         if (kb_on) {
           const int acc = memo ? 1 : 0;                        // a memo pass started the state outputs

@@ -31,7 +31,7 @@ constexpr int MSG_PIPE_BYTES = MSG_WARPS * MSG_STAGES * REC * 4;
 constexpr int MSG_STAGES_FWD = 4;    // direct forward pass: two edges per iteration, two more in flight
 constexpr int MSG_PIPE_BYTES_FWD = MSG_WARPS * MSG_STAGES_FWD * REC * 4;
 constexpr int MEMO_THREADS_FWD = 768;   // memo pass: 24 warps share one staged structure
-constexpr int MEMO_THREADS_BWD = 512;
+constexpr int MEMO_THREADS_BWD = 384;   // full-gradient memo backward: 12 warps, (w,q) rows through a 3-stage ring
 
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
@@ -200,6 +200,47 @@ __device__ __forceinline__ void memo_walk_ring(const float4* __restrict__ mr, in
       const int j = __shfl_sync(0xffffffffu, __float_as_int(jl.x), e);
       const float inv_d = __shfl_sync(0xffffffffu, jl.z, e);
       body(g, j, inv_d, ring + (e % MEMO_STAGES) * MEMO_STAGE_FLOATS + 2 * lane);
+    }
+  }
+}
+
+// Six-row variant for the full-gradient backward: w0,w1,w2 and their d-derivatives q0,q1,q2 (1536 B per edge).
+constexpr int MEMO6_STAGES = 3;
+constexpr int MEMO6_STAGE_FLOATS = 6 * MSG_FC;
+template <bool ROW0, typename Body>
+__device__ __forceinline__ void memo_walk_ring6(const float4* __restrict__ mr, int ne, int lane, const float* __restrict__ wbase,
+                                                const float* __restrict__ qbase, float* __restrict__ ring, Body body) {
+  const int grp = lane >> 4, c4 = (lane & 15) * 4;
+  auto cp16 = [](float* dst, const float* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+  };
+  for (int base = 0; base < ne; base += 32) {
+    const int cnt = min(32, ne - base);
+    float4 gl = make_float4(0.f, 0.f, 0.f, 1.f), jl = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (lane < cnt) { gl = __ldg(mr + 2 * (base + lane)); jl = __ldg(mr + 2 * (base + lane) + 1); }
+    auto issue = [&](int e) {   // e is warp-uniform
+      if (e < cnt) {
+        const long long so = (long long)__shfl_sync(0xffffffffu, __float_as_int(jl.y), e) * F3 + c4;
+        float* dst = ring + (e % MEMO6_STAGES) * MEMO6_STAGE_FLOATS + c4;
+        cp16(dst + (1 + grp) * MSG_FC, wbase + so + (1 + grp) * F);
+        cp16(dst + (4 + grp) * MSG_FC, qbase + so + (1 + grp) * F);
+        if (ROW0) cp16(dst + 3 * grp * MSG_FC, (grp ? qbase : wbase) + so);
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < MEMO6_STAGES - 1; ++p) issue(p);
+    for (int e = 0; e < cnt; ++e) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(MEMO6_STAGES - 2));
+      __syncwarp();
+      issue(e + MEMO6_STAGES - 1);
+      const float4 g = make_float4(__shfl_sync(0xffffffffu, gl.x, e), __shfl_sync(0xffffffffu, gl.y, e),
+                                   __shfl_sync(0xffffffffu, gl.z, e), __shfl_sync(0xffffffffu, gl.w, e));
+      const int j = __shfl_sync(0xffffffffu, __float_as_int(jl.x), e);
+      const float inv_d = __shfl_sync(0xffffffffu, jl.z, e);
+      body(g, j, inv_d, ring + (e % MEMO6_STAGES) * MEMO6_STAGE_FLOATS + 2 * lane);
     }
   }
 }
@@ -523,10 +564,11 @@ __global__ void __launch_bounds__(MEMO_THREADS_BWD, 1) message_bwd_memo(
     dv_in += (mA + a0) * 3 * F;
   }
   bwd_stage<FIRST>(smem, phi, v_in, ds, dv, n, tid, MEMO_THREADS_BWD);
+  float* ring = smem + (size_t)n * PER + warp * (MEMO6_STAGES * MEMO6_STAGE_FLOATS);
   const int f0 = h * MSG_FC + 2 * lane;
-  const long long ml = (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + f0;
-  const float* __restrict__ wrow = fc.wc + ml;
-  const float* __restrict__ qrow = fc.qc + ml;
+  const long long ml = (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC;
+  const float* __restrict__ wbase = fc.wc + ml;
+  const float* __restrict__ qbase = fc.qc + ml;
   stage_wait();
   __syncthreads();
   for (int t = next_row(&row_ctr, lane); t < n; t = next_row(&row_ctr, lane)) {
@@ -538,18 +580,11 @@ __global__ void __launch_bounds__(MEMO_THREADS_BWD, 1) message_bwd_memo(
     bwd_load_own<FIRST>(smem + il * PER + 2 * lane, o);
     BwdAcc a;
     a.dp0 = a.dp1 = a.dp2n = a.dvx = a.dvy = a.dvz = a.gnx = a.gny = a.gnz = dup2(0.f);
-    constexpr int NK = FIRST ? 4 : 6;
-    memo_walk<NK>(
-        mr, ne, lane,
-        [&](int slot, float2* dst) {
-          const long long so = (long long)slot * F3;
-          dst[0] = ldg2(wrow + so + F); dst[1] = ldg2(wrow + so + 2 * F);
-          dst[2] = ldg2(qrow + so + F); dst[3] = ldg2(qrow + so + 2 * F);
-          if (!FIRST) { dst[NK - 2] = ldg2(wrow + so); dst[NK - 1] = ldg2(qrow + so); }
-        },
-        [&](const float4 g, int j, float inv_d, const float2* r) {
-          bwd_edge<FIRST>(g, inv_d, smem + (j - a0) * PER + 2 * lane, o, r[NK - 2], r[0], r[1], r[NK - 1], r[2], r[3], a);
-        });
+    memo_walk_ring6<!FIRST>(mr, ne, lane, wbase, qbase, ring, [&](const float4 g, int j, float inv_d, const float* r) {
+      const float2 z2 = dup2(0.f);
+      bwd_edge<FIRST>(g, inv_d, smem + (j - a0) * PER + 2 * lane, o, FIRST ? z2 : ld2(r), ld2(r + MSG_FC), ld2(r + 2 * MSG_FC),
+                      FIRST ? z2 : ld2(r + 3 * MSG_FC), ld2(r + 4 * MSG_FC), ld2(r + 5 * MSG_FC), a);
+    });
     bwd_store<FIRST>(o, a, il, i, f0, lane, m, h, n_atoms, dphi, dv_in, gradp, 0);
   }
 }
