@@ -296,15 +296,22 @@ def main():
         """Asynchronous engine call: the 8 scalars per chain are copied to pinned host memory behind the
         relaxation on the same stream; result() waits for that copy only."""
 
+        pool = {}      # pinned staging buffers are recycled: cudaHostAlloc costs milliseconds
+
         def __init__(self, out_dev):
-            self.host = torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
+            key = (tuple(out_dev.shape), out_dev.dtype)
+            free = Pending.pool.setdefault(key, [])
+            self.key = key
+            self.host = free.pop() if free else torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
             self.host.copy_(out_dev, non_blocking=True)
             self.done = torch.cuda.Event()
             self.done.record()
 
         def result(self):
             self.done.synchronize()
-            return self.host.numpy()
+            out = self.host.numpy().copy()
+            Pending.pool[self.key].append(self.host)
+            return out
 
     def relax_fn(pos_l, num_l, fix_l):
         b = engine.Batch.from_arrays(pos_l, [to_species(zz) for zz in num_l], [cell] * len(pos_l), [pbc] * len(pos_l), fix_l)

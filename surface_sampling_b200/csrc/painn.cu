@@ -944,10 +944,16 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   // group kernels: G canonical structures per CTA (as many as fit in shared memory), no ring
   constexpr int G_FWD0 = 4, T_FWD0 = 512, G_FWD = 2, T_FWD = 832, G_STATE = 2, T_STATE = 512;
   const bool group_on = memo && !(fc_flags & VSSR_FC_NO_PAIR);
-  const size_t sp_fwd0 = G_FWD0 * st_fwd0, sp_fwd = G_FWD * st_fwd, sp_state = (size_t)G_STATE * nmax * MEMO_STATE_PER * 4;
-  const bool pair_fwd0 = group_on && n_struct >= G_FWD0 && sp_fwd0 <= 227 * 1024;
-  const bool pair_fwd = group_on && n_struct >= G_FWD && sp_fwd <= 227 * 1024;
-  const bool pair_state = group_on && constrained && n_struct >= G_STATE && sp_state <= 227 * 1024;
+  // a group is taken when its structures are canonical AND its atoms fit the staging area (the budget is what G
+  // structures of the batch's largest size would need, capped by the 227 KB of an SM; both kernels apply the same test)
+  const size_t kSmemCap = 226 * 1024;   // 227 KB per SM minus the kernels' few bytes of static shared memory
+  auto cap = [&](size_t want_bytes) { return want_bytes < kSmemCap ? want_bytes : kSmemCap; };
+  const size_t sp_fwd0 = cap(G_FWD0 * st_fwd0), sp_fwd = cap(G_FWD * st_fwd), sp_state = cap((size_t)G_STATE * nmax * MEMO_STATE_PER * 4);
+  const int ga_fwd0 = (int)(sp_fwd0 / (MsgFwdLayout<true>::PER * 4)), ga_fwd = (int)(sp_fwd / (MsgFwdLayout<false>::PER * 4)),
+            ga_state = (int)(sp_state / (MEMO_STATE_PER * 4));
+  const bool pair_fwd0 = group_on && n_struct >= G_FWD0;
+  const bool pair_fwd = group_on && n_struct >= G_FWD;
+  const bool pair_state = group_on && constrained && n_struct >= G_STATE;
   if (staged) {
     static size_t cfg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     auto want = [&](int k, const void* fn, size_t bytes) -> int {
@@ -1001,11 +1007,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       if (l == 0) {
         if (pair_fwd0)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo_group<true, G_FWD0, T_FWD0><<<dim3(n_struct / G_FWD0, F / MSG_FC, M), T_FWD0, sp_fwd0, st>>>(
-              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
+              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l], n_struct, ga_fwd0));
         if (memo)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<true><<<memo_grid, MEMO_THREADS_FWD, sm_fwd0, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l],
-              pair_fwd0 ? w.canonical : nullptr, n_struct, G_FWD0));
+              pair_fwd0 ? w.canonical : nullptr, n_struct, G_FWD0, ga_fwd0));
         if (kb_on) {
           if ((rc = kb_launch_fwd<1, true, KB_T>(kb_smem(kb_fwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
                                                  w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
@@ -1018,11 +1024,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       } else {
         if (pair_fwd)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo_group<false, G_FWD, T_FWD><<<dim3(n_struct / G_FWD, F / MSG_FC, M), T_FWD, sp_fwd, st>>>(
-              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
+              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l], n_struct, ga_fwd));
         if (memo)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<false><<<memo_grid, MEMO_THREADS_FWD, sm_fwd, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l],
-              pair_fwd ? w.canonical : nullptr, n_struct, G_FWD));
+              pair_fwd ? w.canonical : nullptr, n_struct, G_FWD, ga_fwd));
         if (kb_on) {
           if ((rc = kb_launch_fwd<1, false, KB_T>(kb_smem(kb_fwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
                                                   w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
@@ -1124,11 +1130,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       } else {
         if (pair_state)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo_state_group<G_STATE, T_STATE><<<dim3(n_struct / G_STATE, F / MSG_FC, M), T_STATE, sp_state, st>>>(
-              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt));
+              l, A, atom_ptr, w.canonical, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, n_struct, ga_state));
         if (constrained)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo_state<<<memo_grid, MEMO_THREADS_FWD, sm_state, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt,
-              pair_state ? w.canonical : nullptr, n_struct, G_STATE));
+              pair_state ? w.canonical : nullptr, n_struct, G_STATE, ga_state));
         else if (memo)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<false><<<memo_grid, MEMO_THREADS_BWD, sm_bwdm, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));

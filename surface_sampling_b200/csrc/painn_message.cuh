@@ -86,13 +86,14 @@ __device__ __forceinline__ int next_row(int* ctr, int lane) {
 }
 
 // is structure b handled by a group kernel (G consecutive canonical structures per CTA)?
-__device__ __forceinline__ bool in_canonical_group(const int32_t* __restrict__ canonical, int b, int n_struct, int G) {
+__device__ __forceinline__ bool in_canonical_group(const int32_t* __restrict__ canonical, const int32_t* __restrict__ atom_ptr,
+                                                   int b, int n_struct, int G, int max_atoms) {
   if (!canonical) return false;
   const int q = (b / G) * G;
   if (q + G > n_struct) return false;
   for (int s = 0; s < G; ++s)
     if (!__ldg(canonical + q + s)) return false;
-  return true;
+  return __ldg(atom_ptr + q + G) - __ldg(atom_ptr + q) <= max_atoms;   // the group's rows must fit the CTA's staging area
 }
 
 // order[a0 + rank] = local index of the row with that rank (cost descending, index ascending on ties).
@@ -271,10 +272,11 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
     int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ rowptr,
     const int32_t* __restrict__ order, const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
     const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
-    float* __restrict__ cat, float* __restrict__ v_mid, const int32_t* __restrict__ canonical, int n_struct, int group) {
+    float* __restrict__ cat, float* __restrict__ v_mid, const int32_t* __restrict__ canonical, int n_struct, int group,
+    int group_atoms) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int row_ctr;
-  if (in_canonical_group(canonical, blockIdx.x, n_struct, group)) return;   // done by message_fwd_memo_group
+  if (in_canonical_group(canonical, atom_ptr, blockIdx.x, n_struct, group, group_atoms)) return;   // done by message_fwd_memo_group
   if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MsgFwdLayout<FIRST>::PER;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -600,10 +602,10 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_bwd_memo_state(
     const int32_t* __restrict__ order, const int32_t* __restrict__ nmemo, const float* __restrict__ mrec, FilterCacheView fc,
     const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
     const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in,
-    const int32_t* __restrict__ canonical, int n_struct, int group) {
+    const int32_t* __restrict__ canonical, int n_struct, int group, int group_atoms) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int row_ctr;
-  if (in_canonical_group(canonical, blockIdx.x, n_struct, group)) return;   // done by message_bwd_memo_state_group
+  if (in_canonical_group(canonical, atom_ptr, blockIdx.x, n_struct, group, group_atoms)) return;   // done by message_bwd_memo_state_group
   if (threadIdx.x == 0) row_ctr = 0;
   constexpr int PER = MEMO_STATE_PER;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -846,15 +848,13 @@ template <bool FIRST, int G, int T>
 __global__ void __launch_bounds__(T, 1) message_fwd_memo_group(
     int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ canonical,
     FilterCacheView fc, const float* __restrict__ phi, const float* __restrict__ s_in,
-    const float* __restrict__ v_in, float* __restrict__ cat, float* __restrict__ v_mid) {
+    const float* __restrict__ v_in, float* __restrict__ cat, float* __restrict__ v_mid, int n_struct, int group_atoms) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int row_ctr;
   constexpr int PER = MsgFwdLayout<FIRST>::PER;
   const int tid = threadIdx.x, lane = tid & 31;
   const int b0 = G * blockIdx.x, h = blockIdx.y, m = blockIdx.z;
-#pragma unroll
-  for (int s = 0; s < G; ++s)
-    if (!__ldg(canonical + b0 + s)) return;
+  if (!in_canonical_group(canonical, atom_ptr, b0, n_struct, G, group_atoms)) return;   // left to the one-structure kernel
   if (tid == 0) row_ctr = 0;
   const long long mA = (long long)m * n_atoms;
   int a0[G], n[G];
@@ -913,15 +913,14 @@ template <int G, int T>
 __global__ void __launch_bounds__(T, 1) message_bwd_memo_state_group(
     int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ canonical,
     FilterCacheView fc, const float* __restrict__ phi, const float* __restrict__ v_in,
-    const float* __restrict__ ds, const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in) {
+    const float* __restrict__ ds, const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in,
+    int n_struct, int group_atoms) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int row_ctr;
   constexpr int PER = MEMO_STATE_PER;
   const int tid = threadIdx.x, lane = tid & 31;
   const int b0 = G * blockIdx.x, h = blockIdx.y, m = blockIdx.z;
-#pragma unroll
-  for (int s = 0; s < G; ++s)
-    if (!__ldg(canonical + b0 + s)) return;
+  if (!in_canonical_group(canonical, atom_ptr, b0, n_struct, G, group_atoms)) return;   // left to the one-structure kernel
   if (tid == 0) row_ctr = 0;
   const long long mA = (long long)m * n_atoms;
   int a0[G], n[G];

@@ -167,7 +167,10 @@ class _Workspace:
 
     def get(self, nbytes: int, device) -> torch.Tensor:
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
-            self.buf = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=device)
+            # 1.5x head room: MC chains gain adsorbates step by step, and re-allocating a GB-sized workspace
+            # (cudaFree synchronises the device, cudaMalloc takes tens of ms) must stay a rare event
+            self.buf = None
+            self.buf = torch.empty(int(nbytes * 1.5) + 256, dtype=torch.uint8, device=device)
         return self.buf
 
 
