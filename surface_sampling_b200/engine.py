@@ -166,7 +166,8 @@ class _Workspace:
         self.buf = None
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
+        # (an engine lives on one device; comparing torch.device('cuda') with cuda:0 is always unequal)
+        if self.buf is None or self.buf.numel() < nbytes:
             # 1.5x head room: MC chains gain adsorbates step by step, and re-allocating a GB-sized workspace
             # (cudaFree synchronises the device, cudaMalloc takes tens of ms) must stay a rare event
             self.buf = None
@@ -258,6 +259,20 @@ class PainnEngine:
     def clear_framework(self):
         self._fc = None
 
+    RESULT_RING = 4
+
+    def _result_buffers(self, B: int, A: int):
+        ring = self.__dict__.setdefault("_res_ring", {"k": 0, "sets": [None] * self.RESULT_RING})
+        k = ring["k"] = (ring["k"] + 1) % self.RESULT_RING
+        cur = ring["sets"][k]
+        if cur is None or cur[0].shape[0] < B or cur[1].shape[0] < A:
+            capB, capA = int(B * 1.5) + 8, int(A * 1.5) + 64
+            cur = ring["sets"][k] = (torch.empty((capB, 8), dtype=torch.float64, device=self.device),
+                                     torch.empty((capA, 3), dtype=torch.float32, device=self.device),
+                                     torch.empty((capA, 3), dtype=torch.float32, device=self.device),
+                                     torch.zeros(1, dtype=torch.int32, device=self.device))
+        return cur[0][:B], cur[1][:A], cur[2][:A], cur[3]
+
     def _fc_args(self, constrained: bool = True):
         if self._fc is None:
             return None, 0, 0, 0
@@ -341,10 +356,11 @@ class PainnEngine:
         if self.offset_data is not None:
             zh = z_host if z_host is not None else batch.z.cpu().numpy()
             off = torch.from_numpy(self.offsets_ev(zh, batch.atom_ptr_host)).to(dev, non_blocking=True)
-        out = torch.empty((B, 8), dtype=torch.float64, device=dev)
-        forces = torch.empty((A, 3), dtype=torch.float32, device=dev)
-        fstd = torch.empty((A, 3), dtype=torch.float32, device=dev) if want_std else None
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        # result buffers come from a small ring of persistent allocations (no allocator traffic inside MC steps);
+        # a returned dict stays valid until RESULT_RING further relax() calls of this engine
+        out, forces, fstd_buf, status = self._result_buffers(B, A)
+        fstd = fstd_buf if want_std else None
+        status.zero_()
         cell32 = batch.cell32.contiguous()
         _lib.check(lib.vssr_painn_relax(_ptr(self.weights), M, _ptr(batch.pos), _ptr(batch.z), _ptr(batch.fixed),
                                         _ptr(batch.atom_ptr), _ptr(cell32), _ptr(batch.pbc), _ptr(off), B, A,
