@@ -236,7 +236,7 @@ int run_gemm(GemmArgs g, const float* Bkn, int ldb_kn, const float* Bnk, int n_m
 // The pair duplication feeds the packed FFMA2 path (sm_100 fma.rn.f32x2) without register moves.
 // grad0[a] = excluded-volume gradient (same for every model); evex[a] its energy.
 // ------------------------------------------------------------------------------------------
-constexpr int REC = 96, REC_EJ = 4, REC_SLOT = 5, REC_RE = 8, REC_DRE = 52;
+constexpr int REC = 96, REC_EJ = 4, REC_RE = 8, REC_DRE = 52;
 constexpr int MREC = 8;   // memoised-edge record: (ux,uy,uz,d), sender, slot, 1/d, pad
 // compact direct-edge record for the k-block kernels (256 B): [0..3] (u,d) [4] sender [6] key [7] 1/d
 // [8..27] rbf_n*env [28] env [29] denv [32..51] d(rbf_n*env)/dd   (scalars: FFMA2 broadcasts an .F32 operand)

@@ -126,41 +126,11 @@ __global__ void __launch_bounds__(128) row_order_kernel(const int32_t* __restric
   }
 }
 
-// Walk the memoised edges of one receiver.  Lane l loads record base+l (32 records per sweep, coalesced)
-// and the per-edge fields are broadcast by shuffle; the NK filter-row pairs of an edge are fetched into
-// registers MEMO_DEPTH edges ahead, so the L2 latency of the row gather overlaps the arithmetic of the
-// edges in between.  load(slot, dst[NK]) issues the row loads, body(g, j, inv_d, rows[NK]) consumes one edge.
-constexpr int MEMO_DEPTH = 2;
-template <int NK, typename RowLoad, typename Body>
-__device__ __forceinline__ void memo_walk(const float4* __restrict__ mr, int ne, int lane, RowLoad load, Body body) {
-  constexpr int D = MEMO_DEPTH;
-  for (int base = 0; base < ne; base += 32) {
-    const int cnt = min(32, ne - base);
-    float4 gl = make_float4(0.f, 0.f, 0.f, 1.f), jl = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < cnt) { gl = __ldg(mr + 2 * (base + lane)); jl = __ldg(mr + 2 * (base + lane) + 1); }
-    float2 buf[D + 1][NK];
-#pragma unroll
-    for (int p = 0; p < D; ++p)
-      if (p < cnt) load(__shfl_sync(0xffffffffu, __float_as_int(jl.y), p), buf[p]);
-    for (int e0 = 0; e0 < cnt; e0 += D + 1) {
-#pragma unroll
-      for (int u = 0; u <= D; ++u) {
-        const int e = e0 + u;
-        if (e < cnt) {   // warp-uniform
-          if (e + D < cnt) load(__shfl_sync(0xffffffffu, __float_as_int(jl.y), e + D), buf[(u + D) % (D + 1)]);
-          const float4 g = make_float4(__shfl_sync(0xffffffffu, gl.x, e), __shfl_sync(0xffffffffu, gl.y, e),
-                                       __shfl_sync(0xffffffffu, gl.z, e), __shfl_sync(0xffffffffu, gl.w, e));
-          const int j = __shfl_sync(0xffffffffu, __float_as_int(jl.x), e);
-          body(g, j, __shfl_sync(0xffffffffu, jl.z, e), buf[u]);
-        }
-      }
-    }
-  }
-}
-
-// Same walk, but the filter rows (w0,w1,w2 of this feature half: 768 B per edge) travel through a private
-// cp.async ring per warp, MEMO_STAGES deep.  (Register prefetching does not survive ptxas: every LDG of the
-// kernel is tracked by one scoreboard, so waiting for the oldest row also waits for the newest.)
+// Walk the memoised edges of one receiver.  Lane l loads record base+l (32 records per sweep, coalesced) and the
+// per-edge fields are broadcast by shuffle.  The filter rows (w0,w1,w2 of this feature half: 768 B per edge) travel
+// through a private cp.async ring per warp, MEMO_STAGES deep.  (Register prefetching does not survive ptxas: every
+// LDG of the kernel is tracked by one scoreboard, so waiting for the oldest row also waits for the newest;
+// profiles/r2_notes.md section 1.)
 // body(g, j, inv_d, rows) with rows[k * MSG_FC] = w_k pair of this lane.
 constexpr int MEMO_STAGES = 4;
 constexpr int MEMO_STAGE_FLOATS = 3 * MSG_FC;
