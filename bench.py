@@ -22,6 +22,15 @@ Si(111) 5x5, SW, relax per proposal).
 """
 from __future__ import annotations
 
+import os
+import sys
+
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is a CPU measurement "with all the host threads
+# it can use", so undo that before numpy / torch initialise their thread pools
+if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1":
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import argparse
 import json
 import os
