@@ -141,11 +141,18 @@ class ChainState:
         del self.numbers[idx:idx + n]
         del self.positions[idx:idx + n]
         del self.ads_group[idx:idx + n]
-        self.occ = np.where(self.occ >= idx, self.occ - n, self.occ)
-        self.ads_group = [g - n if g >= idx else g for g in self.ads_group]
-        self.occ = np.where(self.occ < 0, 0, self.occ)
-        self.ads_group = [0 if g < 0 else g for g in self.ads_group]
-        self.occ[site_idx] = 0
+        # slab.py:372-395 shifts every index >= idx down by n and clamps negatives to 0.  A group id is the index of
+        # its first atom, so only entries behind the removed block can be >= idx, and idx >= n0 > n keeps them positive.
+        occ = self.occ.copy()
+        occ[occ >= idx] -= n
+        occ[occ < 0] = 0
+        occ[site_idx] = 0
+        self.occ = occ
+        ag = self.ads_group
+        for k in range(idx, len(ag)):
+            g = ag[k]
+            if g >= idx:
+                ag[k] = g - n if g - n > 0 else 0
 
     # ---- proposals ----
     def propose_change(self, adsorbates, site_idx=None):
