@@ -291,8 +291,9 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
 }
 
 // direct pass.  accum = 0: writes s_in + ds / v_in + dv ; accum = 1: adds onto the memo pass' output
+// first layer: 40 weight pairs and 3 staged rows per atom -> two CTAs per SM fit (registers and shared memory)
 template <bool FIRST>
-__global__ void __launch_bounds__(MSG_THREADS, 1) message_fwd_v2(
+__global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
     const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order, const int32_t* __restrict__ nvalid,
     const float* __restrict__ erec,
