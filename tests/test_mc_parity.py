@@ -134,3 +134,19 @@ def test_checkpoint_resume_and_stats_csv(tmp_path):
     lines = (tmp_path / "stats.csv").read_text().splitlines()
     assert lines[0] == "energy,frac_accept,adsorption_count" and len(lines) == 5
     assert lines[1] == "%.3f,%.3f,%d" % (full["energy_hist"][1, 0], full["frac_accept_hist"][1, 0], full["adsorption_count_hist"][1, 0])
+
+
+def test_energy_memo_changes_nothing_but_the_number_of_relaxations():
+    """8f-2: occupancy-keyed energy memo / duplicate-proposal coalescing (opt-in)."""
+    seeds = list(range(9))
+    ref, _ = _driver(seeds)
+    for _ in range(15):
+        ref.step()
+    drv, _ = _driver(seeds)
+    drv.energy_memo, drv.memo_hits = {}, 0
+    for _ in range(15):
+        drv.step()
+    assert drv.decisions == ref.decisions
+    for a, b in zip(drv.chains, ref.chains):
+        assert np.array_equal(a.occ, b.occ)
+    assert drv.memo_hits > 0 and drv.n_relaxed + drv.memo_hits == ref.n_relaxed
