@@ -251,7 +251,7 @@ def main():
     ap.add_argument("--groups", type=int, default=1,
                     help="interleaved chain groups of the e2e driver (MultiChainMC.pipeline); 1 = plain lock step, which is "
                          "fastest here: the host part of a step is ~3 ms and half-size batches cost the GPU more than that")
-    ap.add_argument("--cpu-baseline-proposals", type=int, default=4)
+    ap.add_argument("--cpu-baseline-proposals", type=int, default=16)   # ~15 s of host work
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
