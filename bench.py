@@ -301,6 +301,8 @@ def main():
         def relax_batch(b, zh):
             return eng.relax(b, relax_steps=steps_relax, fmax=0.01, check=False)
 
+    statuses = []
+
     class Pending:
         """Asynchronous engine call: the 8 scalars per chain are copied to pinned host memory behind the
         relaxation on the same stream; result() waits for that copy only."""
@@ -325,6 +327,7 @@ def main():
     def relax_fn(pos_l, num_l, fix_l):
         b = engine.Batch.from_arrays(pos_l, [to_species(zz) for zz in num_l], [cell] * len(pos_l), [pbc] * len(pos_l), fix_l)
         r = relax_batch(b, np.concatenate(num_l))
+        statuses.append(r["status"].clone())          # checked once after the timed regions (no sync here)
         io["h2d"] += b.h2d_bytes() + 8 * b.n_struct
         io["d2h"] += r["out"].numel() * 8
         return Pending(r["out"])
@@ -372,6 +375,8 @@ def main():
     e2e_launches = int(lib.vssr_launch_count()) - l0
     io = {k: v // args.steps for k, v in io.items()}
     pipe.drain()
+    if statuses and int(torch.stack(statuses).max().item()) != 0:
+        raise RuntimeError("a relaxation reported a device-side overflow (edge capacity / neighbour slots): the run is invalid")
 
     # ------------------------------------------------------------ device-resident: relax call only
     # stage the proposal batches (current chain states + one fresh proposal each) in HBM beforehand

@@ -70,7 +70,7 @@ def optimize_slab(slab, optimizer="FIRE", save_traj=True, logger=None, **kwargs)
         calc_slab = slab.copy()
         calc_slab.calc = calc
         if not save_traj:
-            r = engine.relax(batch, relax_steps=relax_steps, fmax=0.01, z_host=num)
+            r = engine.relax(batch, relax_steps=relax_steps, fmax=0.01, z_host=num, check=True)
             out = r["out"].cpu().numpy()[0]
             energy = float(out[2])
             forces = r["forces"].cpu().numpy()

@@ -337,9 +337,23 @@ class PainnEngine:
                 "energy_kcal_per_model": energy, "grad_kcal_per_model": grad, "embedding": emb}
 
     def relax(self, batch: Batch, relax_steps: int = 20, fmax: float = 0.01, z_host: np.ndarray | None = None,
-              want_std: bool = True, e_cap: int | None = None):
+              want_std: bool = True, e_cap: int | None = None, check: bool = False):
         """optimize_slab(optimizer='FIRE') for every structure, no host round trip.  batch.pos is
-        updated in place.  Returns dict(out[B,8], forces, forces_std, status)."""
+        updated in place.  Returns dict(out[B,8], forces, forces_std, status).
+
+        The call is asynchronous; `status` (device int) carries VSSR_STATUS_EDGE_OVERFLOW if the neighbour list
+        needed more than e_cap edges (default: edges_per_atom per atom).  check=True synchronises, and on overflow
+        restores the positions and repeats the relaxation with a doubled capacity."""
+        if check:
+            pos0 = batch.pos.clone()
+            cap_try = int(e_cap) if e_cap else batch.n_atoms * self.edges_per_atom
+            while True:
+                r = self.relax(batch, relax_steps, fmax, z_host, want_std, cap_try, check=False)
+                st = int(r["status"].item())
+                if not (st & 1):
+                    return r
+                batch.pos.copy_(pos0)
+                cap_try *= 2
         lib, dev = self.lib, self.device
         A, B, M = batch.n_atoms, batch.n_struct, self.n_models
         if self._fc is not None and (self._fc[4] & 1) and batch.fixed_host is not None:
