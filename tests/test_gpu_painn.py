@@ -253,3 +253,19 @@ def test_large_structure_global_gather_path(structures):
            "numbers": np.concatenate([base["numbers"], np.array([8, 38, 22, 8] * 8)])}
     assert len(big["numbers"]) == 92
     _compare(eng, ens, [big, base])
+
+
+def test_relax_retries_on_edge_capacity_overflow(structures, potentials, sto_weights):
+    """A too small edge capacity is reported through `status`; check=True restores the positions and repeats
+    the relaxation with a doubled capacity -> same bits as a relaxation that had room from the start."""
+    from surface_sampling_b200 import engine
+    eng = engine.PainnEngine(sto_weights, potentials["offset_data"])
+    s = structures["SrTiO3_001_2x2"]
+    fixed = orelax.fixed_mask_from_surface_depth(s["positions"], s["cell"], 1)
+    b0, b1, b2 = (_batch([s, s], [fixed, fixed]) for _ in range(3))
+    out0 = eng.relax(b0, relax_steps=5)["out"].clone()            # result buffers are a ring of four: keep a copy
+    r1 = eng.relax(b1, relax_steps=5, e_cap=1000)                 # 2 x 3448 edges needed
+    assert int(r1["status"].item()) & 1
+    r2 = eng.relax(b2, relax_steps=5, e_cap=1000, check=True)
+    assert int(r2["status"].item()) == 0
+    assert torch.equal(r2["out"], out0) and torch.equal(b2.pos, b0.pos)
