@@ -259,7 +259,7 @@ class PainnEngine:
     def clear_framework(self):
         self._fc = None
 
-    RESULT_RING = 4
+    RESULT_RING = 16   # ~0.2 MB per set at 128 chains
 
     def _result_buffers(self, B: int, A: int):
         ring = self.__dict__.setdefault("_res_ring", {"k": 0, "sets": [None] * self.RESULT_RING})

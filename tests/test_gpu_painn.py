@@ -263,7 +263,7 @@ def test_relax_retries_on_edge_capacity_overflow(structures, potentials, sto_wei
     s = structures["SrTiO3_001_2x2"]
     fixed = orelax.fixed_mask_from_surface_depth(s["positions"], s["cell"], 1)
     b0, b1, b2 = (_batch([s, s], [fixed, fixed]) for _ in range(3))
-    out0 = eng.relax(b0, relax_steps=5)["out"].clone()            # result buffers are a ring of four: keep a copy
+    out0 = eng.relax(b0, relax_steps=5)["out"].clone()            # result buffers are a ring: keep a copy
     r1 = eng.relax(b1, relax_steps=5, e_cap=1000)                 # 2 x 3448 edges needed
     assert int(r1["status"].item()) & 1
     r2 = eng.relax(b2, relax_steps=5, e_cap=1000, check=True)
