@@ -25,3 +25,17 @@ def test_pack_painn_weights_tf32_split_is_exact_to_22_bits():
     assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)
     err = np.abs((hi.astype(np.float64) + lo.astype(np.float64)) - exact.astype(np.float64))
     assert np.all(err <= np.abs(exact.astype(np.float64)) * 2.0 ** -21 + 1e-45)
+
+
+def test_result_buffer_ring_rotates_and_grows():
+    eng = engine.PainnEngine.__new__(engine.PainnEngine)
+    eng.device = torch.device("cpu")
+    first = eng._result_buffers(4, 100)
+    assert first[0].shape == (4, 8) and first[1].shape == (100, 3) and first[2].shape == (100, 3)
+    seen = {first[0].data_ptr()}
+    for _ in range(engine.PainnEngine.RESULT_RING - 1):
+        seen.add(eng._result_buffers(4, 100)[0].data_ptr())
+    assert len(seen) == engine.PainnEngine.RESULT_RING            # distinct sets until the ring wraps
+    assert eng._result_buffers(4, 100)[0].data_ptr() == first[0].data_ptr()
+    big = eng._result_buffers(40, 5000)                           # a larger batch re-allocates that set only
+    assert big[0].shape == (40, 8) and big[1].shape == (5000, 3)
