@@ -99,8 +99,15 @@ class ChainState:
 
     def symbols_at_site(self, site_idx):
         """get_start_ads (slab.py:277-289): all atoms whose ads_group == occ[site]."""
-        idx = self.occ[site_idx]
-        return [SYMBOLS[self.numbers[a]] for a in range(len(self)) if self.ads_group[a] == idx]
+        idx = int(self.occ[site_idx])
+        if idx == 0:      # empty site: the reference's comparison then matches the slab atoms (group 0)
+            return [SYMBOLS[self.numbers[a]] for a in range(len(self)) if self.ads_group[a] == 0]
+        # an adsorbate group is a contiguous block starting at the atom whose index is the group id
+        ag, out, a = self.ads_group, [], idx
+        while a < len(ag) and ag[a] == idx:
+            out.append(SYMBOLS[self.numbers[a]])
+            a += 1
+        return out
 
     # ---- slab.py:235-395 ----
     def change_site(self, site_idx, end_ads):
