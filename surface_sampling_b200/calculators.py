@@ -76,7 +76,13 @@ class Calculator:
             raise PropertyNotImplementedError(f"{name} property not implemented")
         if atoms is None:
             atoms = self.atoms
-        if self.check_state(atoms) or name not in self.results:
+        changed = self.check_state(atoms)
+        if changed:
+            # ASE: a changed structure invalidates EVERY cached property (Calculator.get_property -> self.reset()),
+            # otherwise a stale surface_energy / energy_std of the previous structure would be served
+            self.results = {}
+            self._cache_key = None
+        if changed or name not in self.results:
             if not allow_calculation:
                 return None
             self.calculate(atoms, [name], ALL_CHANGES)
@@ -93,8 +99,11 @@ class Calculator:
 
     def calculate(self, atoms=None, properties=("energy",), system_changes=ALL_CHANGES):
         if atoms is not None:
+            key = self._key(atoms)
+            if key != self._cache_key:
+                self.results = {}      # nothing computed for another structure survives a direct calculate() either
             self.atoms = atoms.copy() if hasattr(atoms, "copy") else atoms
-            self._cache_key = self._key(atoms)
+            self._cache_key = key
 
 
 def _equal(a, b):
@@ -119,8 +128,10 @@ class EnsembleNFF(Calculator):
     def __init__(self, models, device="cuda", model_units="kcal/mol", prediction_units="eV", offset_data=None,
                  cutoff=5.0, cutoff_skin=1.0, **kwargs):
         super().__init__()
-        # `models`: list of PaiNN state dicts (checkpoint keys)
-        self.models = list(models)
+        # `models`: what scripts/sample_surface.py:164-175 passes -- loaded PaiNN modules -- or state dicts
+        # (checkpoint keys) or `best_model` paths; all end up as validated state dicts
+        from .loaders import as_state_dict
+        self.models = [as_state_dict(m) for m in models]
         self.device = device
         self.model_units, self.prediction_units = model_units, prediction_units
         self._stoich = offset_data
@@ -409,7 +420,7 @@ class LAMMMPSCalc(Calculator):
     def calculate(self, atoms=None, properties=implemented_properties, system_changes=ALL_CHANGES):
         atoms = self.atoms if atoms is None else atoms
         Calculator.calculate(self, atoms, properties, system_changes)
-        if "energy" in properties or "forces" in properties:
+        if "energy" in properties or "forces" in properties or "per_atom_energies" in properties:
             _, e, pe = self.run_lammps_energy(atoms, run_dir=self.run_dir)
             self.results["energy"] = e
             self.results["per_atom_energies"] = pe
@@ -424,15 +435,17 @@ class LAMMPSSurfCalc(LAMMMPSCalc):
     implemented_properties = (*LAMMMPSCalc.implemented_properties, "surface_energy")
 
     def get_surface_energy(self, atoms=None) -> float:
-        return self.get_potential_energy(atoms=self.atoms if atoms is None else atoms)
+        """calculators.py:712-727: the potential energy of `atoms`, always evaluated on `atoms` itself."""
+        atoms = self.atoms if atoms is None else atoms
+        _, e, _ = self.run_lammps_energy(atoms, run_dir=self.run_dir)
+        return e
 
     def calculate(self, atoms=None, properties=implemented_properties, system_changes=ALL_CHANGES):
         atoms = self.atoms if atoms is None else atoms
         LAMMMPSCalc.calculate(self, atoms, properties, system_changes)
         if "surface_energy" in properties:
-            if "energy" not in self.results:
-                LAMMMPSCalc.calculate(self, atoms, ("energy",), system_changes)
-            self.results["surface_energy"] = self.results["energy"]
+            self.results["surface_energy"] = (self.results["energy"] if "energy" in self.results
+                                              else self.get_surface_energy(atoms=atoms))
 
 
 # ----------------------------------------------------------------------------------------------

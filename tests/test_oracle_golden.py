@@ -126,3 +126,53 @@ def test_pourbaix_formula_product_vs_oracle():
             got = -(calc.get_delta_G1(atoms, slab_energy=e_slab) + calc.get_delta_G2(atoms))
             ref = pourbaix_potential(symbols, e_slab, table, phi, pH, 0.0257, corr)
             assert abs(got - ref) < 1e-10, (symbols, phi, pH, got, ref)
+
+
+@pytest.mark.parametrize("name", ["O44Sr12Ti16", "O36Sr12Ti12", "O40Sr16Ti12"])
+def test_bfgs_logs_of_the_reference_slabs(structures, potentials, golden_values, sto_weights, name):
+    """tests/test_SrTiO3_terms.ipynb:201-230,272-274: three more BFGS logs (6, 3 and 14 lines) and the relaxed surface
+    energies 35.931 / 12.478 / -4.876 eV.  Pins ensemble + FixAtoms + CatKit layer tags + BFGS + irun + mu-offset, both
+    for the oracle's BFGS and for the PRODUCT's host BFGS (dynamics.HostBFGS, free-atom subspace) driven by the
+    oracle's forces."""
+    from surface_sampling_b200 import dynamics, engine
+    gold = golden_values["bfgs_logs_ref_slabs"][name]
+    s = structures[name]
+    ens = EnsembleOracle(sto_weights, potentials["offset_data"], dtype=torch.float32)
+    fixed = relax.fixed_mask_from_surface_depth(s["positions"], s["cell"], 1)
+    assert np.where(~fixed)[0].tolist() == gold["free"]
+    nb = ens.build_nbrs(s["positions"], s["cell"], PBC3)
+
+    def calc(x):
+        r = ens.calculate(x, s["numbers"], s["cell"], PBC3, nb)
+        return r["energy"][0], r["forces"]
+
+    log = []
+    out = relax.relax(calc, s["positions"], fixed, optimizer="BFGS", relax_steps=20, log=log)
+    assert out["converged"] and len(log) == len(gold["energy"])
+    # CIF coordinates carry 5 decimals (SURVEY.md App. B.3): ~1e-4 eV, ~1e-4 eV/A noise against the printed log
+    assert np.allclose([l[1] for l in log], gold["energy"], atol=2.5e-4)
+    assert np.allclose([l[2] for l in log], gold["fmax"], atol=1e-4)
+    chem = golden_values["pristine_sto_surface_energy"]["chem_pots"]
+    assert abs(surface_energy(out["energy"], s["numbers"], potentials["offset_data"], chem) - gold["surface_energy"]) < 1e-3
+
+    class OracleEngine:      # stands in for PainnEngine: same call, oracle physics (this is a CPU test)
+        cutoff, skin = 5.0, 1.0
+
+        def energy_forces(self, batch, z_host=None, nbrs=None):
+            r = ens.calculate(batch.pos.numpy(), s["numbers"], s["cell"], PBC3, nb)
+            return {"energy": torch.tensor(r["energy"]), "energy_std": torch.tensor(r["energy_std"]),
+                    "forces": torch.tensor(r["forces"])}
+
+    b = engine.Batch.from_arrays([s["positions"]], [s["numbers"]], [s["cell"]], [PBC3], [fixed], device="cpu", pinned=False)
+    plog = []
+    orig = dynamics.eng.neighbor_list
+    dynamics.eng.neighbor_list = lambda *a, **k: None
+    try:
+        o2, f2 = dynamics.relax_host_batch(OracleEngine(), b, s["numbers"], "BFGS", 20, 0.01,
+                                           observer=lambda st, e, f, p: plog.append((st, float(e))))
+    finally:
+        dynamics.eng.neighbor_list = orig
+    assert [q[0] for q in plog] == list(range(len(gold["energy"])))
+    assert np.allclose([q[1] for q in plog], [l[1] for l in log], atol=2e-5)       # fp32 energies, different eigh sizes
+    assert o2[0, 4] == out["nsteps"] and o2[0, 5] == 1.0 and abs(o2[0, 2] - out["raw_energy"]) < 2e-5
+    assert np.abs(b.pos.numpy() - out["pos"]).max() < 1e-5
