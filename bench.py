@@ -1,24 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — relaxed VSSR-MC proposals/s (headline: SrTiO3(001) 2x2, PaiNN 3-model ensemble).
+"""bench.py — relaxed VSSR-MC proposals/s (headline: SrTiO3(001) 2x2, PaiNN 3-model ensemble, BASELINE configs[3]).
 
-A "step" is one MC iteration of every chain on this GPU: propose (host, reference RNG order) ->
-ideal-site structure -> H2D -> neighbour list + FIRE relaxation with ensemble force evaluations
-(GPU, no host round trip) -> 8 scalars per chain D2H -> Metropolis accept/reject.
+A "step" is one MC iteration of every chain on this GPU: propose (host, reference RNG order) -> ideal-site structure ->
+H2D -> neighbour list + FIRE relaxation with ensemble force evaluations (GPU, no host round trip) -> 8 scalars per chain
+D2H -> Metropolis accept/reject.  Chains are first BURNT IN (--burn-in MC steps through the same public driver) so that
+the timed region sees the adsorbate coverage of a running chain, not a pristine slab; the coverage is printed in `config`.
 
-  value   = relaxed proposals/s with the step's inputs already resident in HBM (relax call only)
-  e2e     = the same metric through the public API (MultiChainMC.step) with HOST buffers:
-            pinned H2D of positions/species/masks and D2H of the result inside the timed region
-  roofline= dominant kernel class, timed live with CUDA-event pairs on the launching stream
-  cpu_baseline = the CPU oracle (torch fp32 PaiNN + autograd forces + numpy FIRE) on the host cores
+  value        relaxed proposals/s with the step's inputs already resident in HBM (relax call only)
+  e2e          the same metric through the public API (MultiChainMC.pipeline) with HOST buffers: pinned H2D of
+               positions/species/masks and D2H of the result inside the timed region
+  roofline     dominant kernel class, timed live with CUDA-event pairs on the launching stream; per class both the
+               ALGORITHMIC work and the work the kernels EXECUTE (memoised edges skip the filter) against
+               the peak of the pipe they run on
+  cpu_baseline the CPU oracle port of the reference path on the host cores (bounded sample)
+  reference_equivalent_gpu   the same torch restatement run eagerly on this B200, single chain
+  workloads    short runs of the other BASELINE configs (GaN Tersoff, Si SW, SrTiO3 Pourbaix grid), each with its own
+               value / e2e / roofline / cpu_baseline (skipped with --no-extra-workloads or an explicit --workload)
 
-`--impl reference` times the reference path's CPU restatement (the oracle: the reference's own
-stack — ASE/NFF/LAMMPS — is not installable here) on the same config.
-Weak scaling: --chains-per-gpu chains on every rank (128 -> 1024 chains on 8 GPUs, BASELINE
-config 4); chains never interact, NCCL only gathers per-chain scalars.
-
-Other BASELINE configs (parity-test cases, not the headline line): --workload gan_tersoff
-(config 2: GaN(0001) Tersoff, canonical 12 Ga, relax_steps 100) and --workload si_sw (config 3:
-Si(111) 5x5, SW, relax per proposal).
+`--impl reference` times the reference path's CPU restatement (the oracle: the reference's own stack -- ASE/NFF/LAMMPS --
+is not installable here) on the same config.  Weak scaling: --chains-per-gpu chains on every rank; chains
+(and the (pH, U, chain) units of the Pourbaix grid) never interact, NCCL only gathers per-chain scalars.
 """
 from __future__ import annotations
 
@@ -33,9 +34,7 @@ if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1":
 
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 from pathlib import Path
@@ -48,21 +47,54 @@ GOLD = ROOT / "tests" / "golden"
 
 CHEM_POTS = {"Sr": -2, "Ti": 0, "O": 0}
 FREE = [7, 8, 22, 23, 37, 38, 52, 53]   # surface_depth=1 (tutorials/SrTiO3_001.ipynb cell 7 log)
-FFMA2_PEAK = 65.8   # TFLOP/s, packed fp32x2 FMA measured on this pool's B200 (profiles/microbench/ffma2.cu)
+FFMA2_PEAK = 65.8    # TFLOP/s, packed fp32x2 FMA measured on this pool's B200 (profiles/microbench/ffma2.cu)
+FP64_PEAK = 37.0     # TFLOP/s nominal B200 FP64 (148 SMs x 64 DFMA/clk x 2 x 1.965 GHz); not in MEASURED_PEAKS.json
+# packed fp32 issue slots (FFMA2 / FMUL2 / FADD2) per edge and lane (= feature pair) of the message kernels, counted in
+# csrc/painn_message.cuh: 60 (fwd) / 120 (bwd: w and dw/dd) of them are the radial filter W_d . rbf
+MSG_SLOTS = {"direct_fwd": 72, "direct_bwd": 180, "direct_bwd_frozen_receiver": 73, "memo_fwd": 12, "memo_bwd_state": 13,
+             "memo_bwd_full": 60}
+GEMM_FLOP_PER_ATOM = 2 * 1491072.0   # node MLPs, forward; the backward (no dW) is the same again
+FILTER_FLOP_PER_EDGE = 46080.0       # 3 layers x 2 x 20 x 384, forward; same again for dw/dd
+
+# pH x U grid of BASELINE configs[4]: 8 x 7 = 56 points
+PH_VALUES = [0.0, 2.0, 4.0, 6.0, 8.0, 10.0, 12.0, 14.0]
+U_VALUES = [-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]
+# PourbaixAtom table: Sr / O / H rows are the literals of the reference's tests/pourbaix/test_pourbaix_atoms.py:44-86
+# (phi=1, pH=0 case); the Ti row is synthetic (TiO2: 4 e-, 4 H+), pymatgen being unavailable
+POURBAIX_TABLE = {
+    "Sr": dict(species_conc=1e-6, num_e=2, num_H=0, atom_std_state_energy=-1.68949, delta_G2_std=-5.79807),
+    "Ti": dict(species_conc=1.0, num_e=4, num_H=4, atom_std_state_energy=-7.8955, delta_G2_std=-9.20),
+    "O": dict(species_conc=1.0, num_e=-2, num_H=-2, atom_std_state_energy=-5.26469, delta_G2_std=-2.45830),
+    "H": dict(species_conc=1.0, num_e=1, num_H=1, atom_std_state_energy=-4.0356, delta_G2_std=0.0),
+}
+
+# single-chain rates the reference's own notebooks print (other hardware, other optimiser settings)
+REFERENCE_PUBLISHED = {
+    "sto_painn": {"value": 0.0825, "unit": "proposals/s", "what": "SrTiO3(001) 2x2, PaiNN 3-model ensemble, BFGS 20 steps, 1 chain, RTX 2080 Ti",
+                  "source": "tutorials/SrTiO3_001.ipynb:1558"},
+    "gan_tersoff": {"value": 31.8, "unit": "proposals/s", "what": "GaN(0001) 3x3, Tersoff, LAMMPS CG <=100 its, 1 chain, CPU",
+                    "source": "tutorials/GaN_0001.ipynb:6356"},
+}
 
 WORKLOADS = {
     "sto_painn": dict(slab="SrTiO3_001_2x2", n_sites=64, adsorbates=["Sr", "Ti", "O"], relax_steps=20, canonical=False,
-                      num_ads=0, height=1.5, chains=128,
+                      num_ads=0, height=1.5, chains=128, temp=1.0, burn_in=200, cpu_props=16, models=3,
                       desc="SrTiO3(001) 2x2 VSSR-MC, PaiNN 3-model ensemble (random-init weights seeds 0,1,2), semigrand "
                            "Sr/Ti/O on 64 virtual sites, FIRE relax_steps=20 fmax=0.01 (BASELINE.json configs[3])"),
     "gan_tersoff": dict(slab="GaN_0001_3x3", n_sites=107, adsorbates=["Ga"], relax_steps=100, canonical=True, num_ads=12,
-                        height=1.8, chains=256,
+                        height=1.8, chains=256, temp=1.0, burn_in=20, cpu_props=2, models=0,
                         desc="GaN(0001) 3x3 VSSR-MC, Tersoff (Nord 2003), canonical 12 Ga adatoms on 107 virtual sites, "
                              "FIRE relax_steps=100 fmax=0.01, bulk ids<=36 frozen (BASELINE.json configs[1])"),
     "si_sw": dict(slab="Si_111_5x5", n_sites=100, adsorbates=["Si"], relax_steps=100, canonical=False, num_ads=0,
-                  height=2.0, chains=256,
+                  height=2.0, chains=256, temp=1.0, burn_in=20, cpu_props=3, models=0,
                   desc="Si(111) 5x5 VSSR-MC, Stillinger-Weber (SW-1985 literature parameters, parity unpinned), semigrand "
                        "Si on 100 virtual sites, FIRE relax_steps=100 fmax=0.01, ids<=75 frozen (BASELINE.json configs[2])"),
+    "sto_pourbaix": dict(slab="SrTiO3_001_2x2", n_sites=64, adsorbates=["Sr", "Ti", "O", "HO"], relax_steps=20,
+                         canonical=False, num_ads=0, height=1.5, chains=112, temp=0.257, burn_in=60, cpu_props=3, models=1,
+                         desc="SrTiO3(001) 2x2 Pourbaix VSSR-MC (sample_pourbaix_surface.py): single PaiNN model (random-init, "
+                              "seed 0) + NFFPourbaix grand potential, 8 pH x 7 U grid points x chains sharded as (pH,U,chain) "
+                              "units, semigrand Sr/Ti/O/HO on 64 sites, HO correction 0.23 eV, kT=0.0257, T=0.257, FIRE "
+                              "relax_steps=20 (BASELINE.json configs[4])"),
 }
 
 
@@ -72,7 +104,7 @@ def load_workload(name):
     pots = json.loads((GOLD / "potentials.json").read_text())
     n = w["slab"]
     pos, num, cell, pbc = z[f"{n}/positions"], z[f"{n}/numbers"], z[f"{n}/cell"], z[f"{n}/pbc"]
-    if name == "sto_painn":
+    if name in ("sto_painn", "sto_pourbaix"):
         fixed = np.ones(len(num), bool)
         fixed[FREE] = False
         pbc = np.array([True, True, True])
@@ -86,10 +118,12 @@ def load_workload(name):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.proc, self.lines, self.enabled = index, None, [], enabled
 
     def start(self):
+        if not self.enabled:
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -106,7 +140,8 @@ class ClockSampler:
 
     def stop(self) -> dict:
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled on this rank" if not self.enabled
+                                                                     else "nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -125,24 +160,74 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_oracle_relax_fn(name, evals):
-    """Single-chain CPU restatement of the hot path for `name` (oracle physics + oracle FIRE)."""
+# ---------------------------------------------------------------------------------------------- host scalars
+def pourbaix_calc():
+    """Host-only NFFPourbaix (no engine): the table / temperature / corrections of the Pourbaix workload."""
+    from surface_sampling_b200.calculators import NFFPourbaix, PourbaixAtom
+    calc = NFFPourbaix.__new__(NFFPourbaix)
+    calc.parameters, calc.results, calc.atoms, calc._cache_key = {}, {}, None, None
+    calc.pourbaix_atoms = {k: PourbaixAtom(k, **v) for k, v in POURBAIX_TABLE.items()}
+    calc.temp, calc.phi, calc.pH, calc.adsorbate_corrections = 0.0257, 0.0, 7.0, {"HO": 0.23}
+    return calc
+
+
+def grid_units(name, C, rank, world):
+    """(pH, U, chain) units of this rank for the Pourbaix grid (parallel.shard_grid); None for the other workloads."""
+    if name != "sto_pourbaix":
+        return None
+    from surface_sampling_b200.parallel import shard_grid
+    n_points = len(PH_VALUES) * len(U_VALUES)
+    cpp = max(1, round(C * world / n_points))           # chains per grid point over the whole job
+    units = [(ph, u, c) for ph in PH_VALUES for u in U_VALUES for c in range(cpp)]
+    mine = shard_grid(PH_VALUES, U_VALUES, cpp, rank, world)
+    seeds = [units.index(t) for t in mine]              # global unit id = chain seed
+    return mine, seeds, cpp
+
+
+def surface_energy_fns(name, pots, units):
+    if name in ("gan_tersoff", "si_sw"):
+        return lambda e, sym: e           # LAMMPSSurfCalc: surface energy = potential energy
+    if name == "sto_pourbaix":
+        calc = pourbaix_calc()
+        return [calc.surface_energy_fn(phi=u, pH=ph) for ph, u, _ in units]
+    from surface_sampling_b200.calculators import surface_energy_from
+    od = pots["offset_data"]
+    return lambda e, sym: surface_energy_from(e, sym, od, CHEM_POTS)
+
+
+def build_driver(name, relax_fn, seeds, units=None):
+    from surface_sampling_b200 import mc
+    pos, num, cell, pbc, fixed, pots = load_workload(name)
+    w = WORKLOADS[name]
+    sites = mc.make_site_grid(pos, cell, w["n_sites"], w["height"])
+    drv = mc.MultiChainMC(num, pos, fixed, sites, w["adsorbates"], relax_fn, surface_energy_fns(name, pots, units), seeds,
+                          canonical=w["canonical"], num_ads_atoms=w["num_ads"])
+    drv.temp = w["temp"]
+    return drv
+
+
+# ---------------------------------------------------------------------------------------------- CPU / torch baselines
+def make_oracle_relax_fn(name, evals, device="cpu"):
+    """Single-chain restatement of the hot path for `name` (oracle physics + oracle FIRE); device='cuda' runs the same
+    eager torch code on the GPU (the "reference-equivalent GPU path")."""
     import torch
     from oracle import classical as ocl
     from oracle import relax as orelax
-    from oracle.painn import EnsembleOracle, init_random_weights
+    from oracle.painn import EnsembleOracle
+    from surface_sampling_b200.loaders import init_random_weights
 
     pos0, num0, cell, pbc, fixed0, pots = load_workload(name)
     w = WORKLOADS[name]
-    if name == "sto_painn":
-        ens = EnsembleOracle([init_random_weights(s) for s in (0, 1, 2)], pots["offset_data"], dtype=torch.float32)
+    if w["models"]:
+        ens = EnsembleOracle([init_random_weights(s) for s in range(w["models"])],
+                             pots["offset_data"] if name == "sto_painn" else None, dtype=torch.float32, device=device)
 
         def energy_forces_factory(p, zz):
             nb = ens.build_nbrs(p, cell, pbc)
 
             def calc(x):
                 r = ens.calculate(x, zz, cell, pbc, nb)
-                evals[0] += 3 * len(zz)
+                evals[0] += w["models"] * len(zz)
                 return r["energy"][0], r["forces"]
             return calc
     elif name == "gan_tersoff":
@@ -164,122 +249,107 @@ def make_oracle_relax_fn(name, evals):
     return relax_fn
 
 
-def surface_energy_fn(name, pots):
-    if name != "sto_painn":
-        return lambda e, sym: e           # LAMMPSSurfCalc: surface energy = potential energy
-    from surface_sampling_b200.calculators import surface_energy_from
-    od = pots["offset_data"]
-    return lambda e, sym: surface_energy_from(e, sym, od, CHEM_POTS)
-
-
-def build_driver(name, relax_fn, seeds):
-    from surface_sampling_b200 import mc
-    pos, num, cell, pbc, fixed, pots = load_workload(name)
-    w = WORKLOADS[name]
-    sites = mc.make_site_grid(pos, cell, w["n_sites"], w["height"])
-    return mc.MultiChainMC(num, pos, fixed, sites, w["adsorbates"], relax_fn, surface_energy_fn(name, pots), seeds,
-                           canonical=w["canonical"], num_ads_atoms=w["num_ads"])
-
-
-def cpu_oracle_proposals(name: str, n_proposals: int, threads: int, seed0: int = 0):
-    """Reference-path CPU restatement: single chain.  Returns (proposals, seconds, atom_model_evals)."""
+def oracle_proposals(name: str, n_proposals: int, threads: int, seed0: int = 0, device="cpu", burn_occ=None):
+    """Reference-path restatement, single chain.  Returns (proposals, seconds, atom_model_evals).  `burn_occ` seeds the
+    chain with an adsorbate coverage (list of (site, adsorbate)) so the sample is taken in the benched regime."""
     import torch
     torch.set_num_threads(threads)
     evals = [0]
-    drv = build_driver(name, make_oracle_relax_fn(name, evals), [seed0])
+    units = [(PH_VALUES[3], U_VALUES[2], 0)] if name == "sto_pourbaix" else None
+    drv = build_driver(name, make_oracle_relax_fn(name, evals, device), [seed0], units)
+    for site, ads in (burn_occ or []):
+        drv.chains[0].change_site(site, ads)
     if WORKLOADS[name]["canonical"]:
         drv.prepare_canonical()
     drv._ensure_prev(drv.chains)   # the initial-state energy is not a proposal
     drv.n_relaxed, evals[0] = 0, 0
+    if device != "cpu":
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(n_proposals):
         drv.step()
+    if device != "cpu":
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return drv.n_relaxed, dt, evals[0]
 
 
-def workload_config(args, chains):
-    return {"workload": WORKLOADS[args.workload]["desc"], "chains_per_gpu": chains,
-            "l2": "per-evaluation working set (activations ~48 KB/atom/model, >1 GB) exceeds the 126 MB L2; no explicit flush"
-                  if args.workload == "sto_painn" else "whole relaxation is shared-memory resident; L2 is not on the path",
-            "parallelism": f"chains sharded, {args.gpus} rank(s), no data-path collective",
-            "e2e_driver": f"MultiChainMC.pipeline, {max(1, args.groups)} chain group(s) per GPU; value = one batch of all chains per step",
-            "engine_options": ({"filter_memo": not os.environ.get("VSSR_NO_FILTER_MEMO"),
-                                "constrained_gradients": not (os.environ.get("VSSR_FULL_GRAD") or os.environ.get("VSSR_NO_FILTER_MEMO")),
-                                "note": "every evaluation runs the full 3-layer forward and backward of all 3 models; the memo holds the "
-                                        "radial filter rows w(d), dw/dd of frozen-frozen pairs (functions of weights and the frozen "
-                                        "geometry only), and dE/dx of FixAtoms atoms -- which the optimiser discards -- is not formed "
-                                        "during FIRE steps; energies, positions and accept/reject are bit-identical to the plain mode "
-                                        "(tests/test_gpu_painn.py); VSSR_FULL_GRAD=1 / VSSR_NO_FILTER_MEMO=1 switch them off"}
-                               if args.workload == "sto_painn" else None)}
+def typical_occupancy(drv, k=0):
+    """(site, adsorbate) list of the chain whose adsorbate count is the median of the burnt-in population."""
+    from surface_sampling_b200.mc import hill_formula
+    order = np.argsort([c.num_adsorbates for c in drv.chains])
+    c = drv.chains[int(order[len(order) // 2])]
+    return [(int(s), hill_formula(c.symbols_at_site(int(s)))) for s in np.flatnonzero(c.occ)]
+
+
+def workload_config(name, args, chains, world, extra=None):
+    cfg = {"workload": WORKLOADS[name]["desc"], "chains_per_gpu": chains,
+           "l2": "per-evaluation working set (activations ~48 KB/atom/model, >1 GB) exceeds the 126 MB L2; no explicit flush"
+                 if WORKLOADS[name]["models"] else "whole relaxation is shared-memory resident; L2 is not on the path",
+           "parallelism": f"chains sharded, {world} rank(s), no data-path collective",
+           "e2e_driver": f"MultiChainMC.pipeline, {max(1, args.groups)} chain group(s) per GPU; value = one batch of all chains per step"}
+    if WORKLOADS[name]["models"]:
+        cfg["engine_options"] = {
+            "filter_memo": not os.environ.get("VSSR_NO_FILTER_MEMO"),
+            "constrained_gradients": not (os.environ.get("VSSR_FULL_GRAD") or os.environ.get("VSSR_NO_FILTER_MEMO")),
+            "note": "every evaluation runs the full 3-layer forward and backward of all models; the memo holds the radial filter "
+                    "rows w(d), dw/dd of frozen-frozen pairs (functions of weights and the frozen geometry only), and dE/dx of "
+                    "FixAtoms atoms -- which the optimiser discards -- is not formed during FIRE steps; energies, positions and "
+                    "accept/reject are bit-identical to the plain mode (tests/test_gpu_painn.py)"}
+    cfg.update(extra or {})
+    return cfg
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    name = args.workload
     threads = os.cpu_count() or 1
     for _ in range(min(args.warmup, 1)):
-        cpu_oracle_proposals(args.workload, 1, threads)
+        oracle_proposals(name, 1, threads)
     n, dt, evals = 0, 0.0, 0
     for s in range(args.steps):
-        a, b, c = cpu_oracle_proposals(args.workload, 1, threads, seed0=s)
+        a, b, c = oracle_proposals(name, 1, threads, seed0=s)
         n, dt, evals = n + a, dt + b, evals + c
     val = n / dt
     print(json.dumps({
         "impl": "reference", "metric": "relaxed_proposals_per_sec", "value": val, "unit": "proposals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.workload == "sto_painn" else "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "dtype": "f32" if WORKLOADS[name]["models"] else "f64", "data": "synthetic",
+        "config": workload_config(name, args, 1, 1),
         "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} single-chain relaxed proposals (1 per step), oracle port of the reference path "
-                                   "(torch-CPU physics + numpy FIRE); the reference stack itself is not installable here"},
+                         "sample": f"{n} single-chain relaxed proposals (1 per step, from the pristine slab), oracle port of the "
+                                   "reference path (torch-CPU physics + numpy FIRE); the reference stack itself is not installable here"},
         "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "painn_atom_model_evals_per_sec": evals / dt if evals else None,
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sto_painn", choices=list(WORKLOADS))
-    ap.add_argument("--chains-per-gpu", type=int, default=0)
-    ap.add_argument("--groups", type=int, default=1,
-                    help="interleaved chain groups of the e2e driver (MultiChainMC.pipeline); 1 = plain lock step, which is "
-                         "fastest here: the host part of a step is ~3 ms and half-size batches cost the GPU more than that")
-    ap.add_argument("--cpu-baseline-proposals", type=int, default=16)   # ~15 s of host work
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-
+# ---------------------------------------------------------------------------------------------- the B200 arm
+def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
+    """One workload on this rank's GPU; returns the JSON line (dict) on every rank (timings are max over ranks)."""
     import torch
     import torch.distributed as dist
-    from surface_sampling_b200 import _lib, engine
+    from surface_sampling_b200 import engine, loaders
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1) // 2))   # host threads are for launching, not for BLAS
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = _lib.load()
-    name = args.workload
+    lib, world, rank, local = ctx["lib"], ctx["world"], ctx["rank"], ctx["local"]
     w = WORKLOADS[name]
-    C = args.chains_per_gpu or w["chains"]
+    C = args.chains_per_gpu if (args.chains_per_gpu and headline) else w["chains"]
     steps_relax = w["relax_steps"]
     pos, num, cell, pbc, fixed, pots = load_workload(name)
+    grid = grid_units(name, C, rank, world)
+    units = None
+    seeds = [rank * C + c for c in range(C)]
+    if grid is not None:
+        units, seeds, cpp = grid
+        C = len(units)
     io = {"h2d": 0, "d2h": 0}
 
-    if name == "sto_painn":
-        from oracle.painn import init_random_weights   # weight INIT only (random-init per BASELINE.json); not timed
-        eng = engine.PainnEngine([init_random_weights(s) for s in (0, 1, 2)], pots["offset_data"])
-        e_cap = C * 72 * 96
+    if w["models"]:
+        states = [loaders.init_random_weights(s) for s in range(w["models"])]     # random-init per BASELINE.json; untimed
+        eng = engine.PainnEngine(states, pots["offset_data"] if name == "sto_painn" else None)
         to_species = lambda zz: zz
         if not os.environ.get("VSSR_NO_FILTER_MEMO"):
             # radial-filter memo for the frozen bulk (one-time, untimed); the relaxation holds those atoms with
@@ -287,7 +357,7 @@ def main():
             eng.set_framework(pos, cell, pbc, fixed, constrained_forces=not os.environ.get("VSSR_FULL_GRAD"))
 
         def relax_batch(b, zh):
-            return eng.relax(b, relax_steps=steps_relax, fmax=0.01, z_host=zh, want_std=False, e_cap=e_cap)
+            return eng.relax(b, relax_steps=steps_relax, fmax=0.01, z_host=zh, want_std=False)
     else:
         if name == "gan_tersoff":
             tmap = {31: 0, 7: 1}
@@ -296,7 +366,10 @@ def main():
         else:
             tmap = {14: 0}
             eng = engine.ClassicalEngine(engine.POT_SW, engine.sw_param_table(), 1, n_max=128, max_nbr=32)
-        to_species = lambda zz: np.array([tmap[int(q)] for q in zz], np.int32)
+        lut = np.zeros(120, np.int32)
+        for zz_, t_ in tmap.items():
+            lut[zz_] = t_
+        to_species = lambda zz: lut[zz]
 
         def relax_batch(b, zh):
             return eng.relax(b, relax_steps=steps_relax, fmax=0.01, check=False)
@@ -327,12 +400,17 @@ def main():
     def relax_fn(pos_l, num_l, fix_l):
         b = engine.Batch.from_arrays(pos_l, [to_species(zz) for zz in num_l], [cell] * len(pos_l), [pbc] * len(pos_l), fix_l)
         r = relax_batch(b, np.concatenate(num_l))
-        statuses.append(r["status"].clone())          # checked once after the timed regions (no sync here)
+        statuses.append(r["status"])              # checked once after the timed regions (no sync here)
         io["h2d"] += b.h2d_bytes() + 8 * b.n_struct
         io["d2h"] += r["out"].numel() * 8
         return Pending(r["out"])
 
-    drv = build_driver(name, relax_fn, [rank * C + c for c in range(C)])
+    def check_statuses():
+        if statuses and int(torch.stack(statuses).max().item()) != 0:
+            raise RuntimeError("a relaxation reported a device-side overflow (edge capacity / neighbour slots): the run is invalid")
+        statuses.clear()
+
+    drv = build_driver(name, relax_fn, seeds, units)
     if w["canonical"]:
         drv.prepare_canonical()
     drv._ensure_prev(drv.chains)
@@ -342,46 +420,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ------------------------------------------------------------ e2e: public API, host buffers
-    # MultiChainMC.pipeline with `--groups` interleaved chain groups (with >1, the host applies Metropolis to /
-    # proposes for one group while the GPU relaxes the other).  One step = one iteration of EVERY chain.
+    # ------------------------------------------------------------ burn-in (untimed) + e2e: public API, host buffers
     pipe = drv.pipeline(n_groups=max(1, args.groups))
-    for _ in range(args.warmup):
+    t_burn = time.perf_counter()
+    for k in range(burn_in):
         pipe.advance()
-    sampler = ClockSampler(local)
-    if rank != 0:
-        sampler.start = lambda: None      # one nvidia-smi poller per job (rank 0's GPU): N pollers contend for the driver
+        if k % 50 == 49:
+            check_statuses()
+    torch.cuda.synchronize()
+    t_burn = time.perf_counter() - t_burn
+    n_ads = np.array([c.num_adsorbates for c in drv.chains])
+    n_atoms = np.array([len(c) for c in drv.chains])
+    coverage = {"burn_in_mc_steps": burn_in, "burn_in_seconds": round(t_burn, 2),
+                "adsorbates_per_chain": {"mean": float(n_ads.mean()), "min": int(n_ads.min()), "max": int(n_ads.max())},
+                "atoms_per_structure": {"mean": float(n_atoms.mean()), "max": int(n_atoms.max())},
+                "accept_rate_burn_in": float(np.mean([d[0] for ch in drv.decisions for d in ch])) if burn_in else None}
+    for _ in range(warmup):
+        pipe.advance()
+    sampler = ClockSampler(local, enabled=(rank == 0 and headline))   # one poller per job: N pollers contend for the driver
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = int(lib.vssr_launch_count())
     io["h2d"] = io["d2h"] = 0
-    hostprof = None
-    if os.environ.get("VSSR_BENCH_HOSTPROF"):      # where does the host spend the e2e step? (stderr, rank 0)
-        import cProfile
-        hostprof = cProfile.Profile()
-        hostprof.enable()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         pipe.advance()
     ev1.record()
-    if hostprof is not None:
-        hostprof.disable()
-        if rank == 0:
-            import pstats
-            pstats.Stats(hostprof, stream=sys.stderr).sort_stats("tottime").print_stats(18)
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
     e2e_launches = int(lib.vssr_launch_count()) - l0
-    io = {k: v // args.steps for k, v in io.items()}
+    io = {k: v // steps for k, v in io.items()}
     pipe.drain()
-    if statuses and int(torch.stack(statuses).max().item()) != 0:
-        raise RuntimeError("a relaxation reported a device-side overflow (edge capacity / neighbour slots): the run is invalid")
+    check_statuses()
+    n_ads_end = float(np.mean([c.num_adsorbates for c in drv.chains]))
 
     # ------------------------------------------------------------ device-resident: relax call only
     # stage the proposal batches (current chain states + one fresh proposal each) in HBM beforehand
     staged, staged_host, atoms_total = [], [], 0
-    for k in range(args.steps + args.warmup):
+    for k in range(steps + warmup):
         pl, nl, fl = [], [], []
         for c in drv.chains:
             snap = c.snapshot()
@@ -392,34 +469,38 @@ def main():
             fl.append(np.concatenate([fixed, np.zeros(len(zz) - len(fixed), bool)]))
         b = engine.Batch.from_arrays(pl, [to_species(zz) for zz in nl], [cell] * C, [pbc] * C, fl)
         staged.append((b, np.concatenate(nl)))
-        if k >= args.warmup:
+        if k >= warmup:
             atoms_total += b.n_atoms
             if len(staged_host) < 2:
                 staged_host.append((pl, nl, fl))
-    for b, zh in staged[:args.warmup]:
-        relax_batch(b, zh)
+    for b, zh in staged[:warmup]:
+        statuses.append(relax_batch(b, zh)["status"])
     barrier()
     l0 = int(lib.vssr_launch_count())
     ev0.record()
-    for b, zh in staged[args.warmup:]:
-        relax_batch(b, zh)
+    for b, zh in staged[warmup:]:
+        statuses.append(relax_batch(b, zh)["status"])
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = int(lib.vssr_launch_count()) - l0
     clocks = sampler.stop()
+    check_statuses()
 
-    # ------------------------------------------------------------ per-kernel-class profile (same region again)
+    # ------------------------------------------------------------ per-kernel-class profile (two relaxations again)
     ncls = int(lib.vssr_kernel_class_count())
     ms = np.zeros(ncls); cnt = np.zeros(ncls, np.int64)
-    lib.vssr_profile_enable(1)
     fresh = [engine.Batch.from_arrays(pl, [to_species(zz) for zz in nl], [cell] * C, [pbc] * C, fl) for pl, nl, fl in staged_host]
-    for b, (_, zh) in zip(fresh, staged[args.warmup:][:2]):
+    torch.cuda.synchronize()
+    lib.vssr_profile_enable(1)
+    edge_stats = []
+    for b, (_, zh) in zip(fresh, staged[warmup:][:2]):
         relax_batch(b, zh)
+        if w["models"]:
+            edge_stats.append(eng.last_relax_edge_stats(b))
     lib.vssr_profile_collect(ms.ctypes.data, cnt.ctypes.data, ncls)
     lib.vssr_profile_enable(0)
-    gemm_name = "gemm_fp32_ffma2" if os.environ.get("VSSR_GEMM", "tc").startswith("f") else "gemm_tcgen05_3xtf32"
-    names = ["nbr", "edge_geometry", gemm_name, "message_fwd", "message_bwd", "elementwise", "readout",
+    names = ["nbr", "edge_geometry", "gemm_tcgen05_3xtf32", "message_fwd", "message_bwd", "elementwise", "readout",
              "ensemble_stats", "fire", "classical_relax", "message_fwd_memo", "message_bwd_memo"]
     breakdown = {names[k]: {"ms": round(float(ms[k]), 3), "launches": int(cnt[k])} for k in range(ncls) if cnt[k]}
     a_prof = sum(b.n_atoms for b in fresh)
@@ -429,80 +510,207 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms, dev_ms = t.tolist()
-    total_props = C * args.steps * world
+    c_tot = torch.tensor([float(C)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(c_tot, op=dist.ReduceOp.SUM)
+    total_props = c_tot.item() * steps
     value = total_props / (dev_ms * 1e-3)
     e2e = total_props / (e2e_ms * 1e-3)
 
-    # ------------------------------------------------------------ roofline of the dominant kernel class
-    dom = max(breakdown, key=lambda k: breakdown[k]["ms"]) if breakdown else None
-    if dom and dom.endswith("_memo"):
-        dom = dom[:-5]
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else None
-    roof = None
     extra = {}
-    if name == "sto_painn":
-        bf16 = peaks["bf16_tflops_sustained"] if peaks else 1400.0
-        peak_src = "measured (MEASURED_PEAKS.json: sustained bf16 / 2 = TF32 dense)" if peaks else "fallback (1.4 PF / 2)"
-        evals_per_prop = (steps_relax + 1) * 3      # model force evaluations per proposal (3-model ensemble)
-        extra["painn_atom_model_evals_per_sec"] = atoms_total * evals_per_prop * world / (dev_ms * 1e-3)
-        E_per_atom = 2504 / 60.0
-        flops = {   # algorithmic FLOPs per model force-evaluation per atom (DESIGN.md section 2 / SURVEY.md 8d)
-            gemm_name: 2 * 1491072.0,
-            "message_fwd": 3 * E_per_atom * 2 * (3 * 20 * 128 + 12 * 128),
-            "message_bwd": 3 * E_per_atom * 2 * (6 * 20 * 128 + 60 * 128),
-        }
-
-        def tflops(k):
-            if k not in breakdown or breakdown[k]["ms"] <= 0:
-                return None
-            t_ms = breakdown[k]["ms"] + breakdown.get(k + "_memo", {"ms": 0.0})["ms"]   # both passes of a layer
-            return flops[k] * 3 * a_prof * (steps_relax + 1) / (t_ms * 1e-3) / 1e12
-
-        if dom in flops and tflops(dom):
-            achieved = tflops(dom)
-            is_gemm = dom == gemm_name
-            # DRAM bytes per launch of the dominant kernel class from the committed ncu --set full capture
-            traffic, traffic_src = None, None
-            caps = sorted((ROOT / "profiles").glob("r*_ncu_traffic.json"))
-            if caps:
-                cap = json.loads(caps[-1].read_text())
-                if dom in cap["classes"]:
-                    traffic = cap["classes"][dom]["dram_bytes_per_launch"]
-                    traffic_src = f"profiles/{caps[-1].name} (mean dram__bytes_read+write per launch, {cap['classes'][dom]['launches_captured']} launches)"
-            roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": bf16 / 2, "unit": "TFLOP/s",
-                    "frac": achieved / (bf16 / 2), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                    "achieved_algorithmic_tflops": {k: tflops(k) for k in flops},
-                    "frac_of_measured_ffma2_peak": None if is_gemm else achieved / FFMA2_PEAK,
-                    "note": ("3xTF32 on tcgen05: 3 tensor-core MACs per algorithmic MAC" if is_gemm else
-                             "message passing runs on the fp32 FMA pipe (packed FFMA2, measured peak 65.8 TFLOP/s); the "
-                             "tensor-pipe peak is quoted because the schema has no fp32-FMA bound")}
+    if w["models"]:
+        roof = painn_roofline(breakdown, edge_stats, a_prof, steps_relax + 1, w["models"], peaks)
+        extra["painn_atom_model_evals_per_sec"] = atoms_total * (steps_relax + 1) * w["models"] * world / (dev_ms * 1e-3)
     else:
-        hbm = peaks["hbm_gbs"] if peaks else 6650.0
-        algo_bytes = 53.0 * a_prof * (steps_relax + 1)    # 53 B per atom-eval if it streamed
-        if dom and breakdown[dom]["ms"] > 0:
-            achieved = algo_bytes / (breakdown[dom]["ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                    "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                    "note": "persistent one-CTA-per-chain kernel: the slab never leaves shared memory between FIRE steps, so "
-                            "HBM traffic is ~0 and the kernel is FP64/latency-bound; the fraction only shows that"}
+        roof = classical_roofline(breakdown, a_prof, steps_relax + 1, peaks)
+    cfg_extra = {"coverage": {**coverage, "mean_adsorbates_after_timed_region": n_ads_end},
+                 "timed_region_s": {"device": round(dev_ms * 1e-3, 3), "e2e": round(e2e_ms * 1e-3, 3)}}
+    if grid is not None:
+        cfg_extra["grid"] = {"pH": PH_VALUES, "U_V": U_VALUES, "chains_per_point": cpp, "units_this_rank": C,
+                             "sharding": "parallel.shard_grid: (pH, U, chain) units round-robin over ranks"}
     out = {
         "metric": "relaxed_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if name == "sto_painn" else "f64", "data": "synthetic",
-        "config": workload_config(args, C),
+        "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if w["models"] else "f64", "data": "synthetic",
+        "config": workload_config(name, args, C, world, cfg_extra),
         "e2e": {"value": e2e, "unit": "proposals/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / steps},
         "gpu_launches": launches, "gpu_launches_e2e": e2e_launches,
         "roofline": roof, "kernel_breakdown_ms": breakdown, "clocks": clocks, **extra,
     }
+    if name in REFERENCE_PUBLISHED:
+        out["reference_published_single_chain"] = REFERENCE_PUBLISHED[name]
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        occ = typical_occupancy(drv)
+        n_cpu = args.cpu_baseline_proposals if (headline and args.cpu_baseline_proposals) else w["cpu_props"]
+        n, dt, ev = oracle_proposals(name, n_cpu, threads, burn_occ=occ)
+        out["cpu_baseline"] = {"value": n / dt, "unit": "proposals/s", "cores": threads, "kind": "port",
+                               "sample": f"{n} single-chain relaxed proposals of the same workload ({dt:.1f} s) starting from the "
+                                         f"burnt-in population's median coverage ({len(occ)} adsorbates), oracle port of the "
+                                         "reference path on the host cores",
+                               "painn_atom_model_evals_per_sec": ev / dt if ev else None}
+        if w["models"] and headline and not args.no_torch_gpu_baseline:
+            n, dt, ev = oracle_proposals(name, 2, threads, device="cuda", burn_occ=occ)       # warm-up (cuDNN/cuBLAS init)
+            n, dt, ev = oracle_proposals(name, args.torch_gpu_proposals, threads, device="cuda", burn_occ=occ)
+            out["reference_equivalent_gpu"] = {
+                "value": n / dt, "unit": "proposals/s", "kind": "torch-eager-on-B200",
+                "sample": f"{n} single-chain relaxed proposals ({dt:.1f} s): the oracle's torch fp32 PaiNN ensemble + autograd forces "
+                          "run eagerly on this GPU, host FIRE, one chain -- how the reference drives its GPU (BASELINE.md section 2)",
+                "painn_atom_model_evals_per_sec": ev / dt if ev else None}
+    return out
+
+
+def painn_roofline(breakdown, edge_stats, a_prof, evals, M, peaks):
+    """Per kernel class: measured ms (CUDA-event pairs, 2 relaxations), ALGORITHMIC FLOPs and EXECUTED
+    work, each against the peak of the pipe the kernels run on.  No class is charged for work it skips."""
+    bf16 = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+    hbm = peaks["hbm_gbs"] if peaks else 6650.0
+    tf32 = bf16 / 2
+    src = "measured (MEASURED_PEAKS.json: sustained bf16 / 2 = TF32 dense; hbm_gbs)" if peaks else "fallback (1.4 PF / 2; 6.65 TB/s)"
+    d = sum(s["direct_edges"] for s in edge_stats)
+    m = sum(s["memo_edges"] for s in edge_stats)
+    df = sum(s["direct_edges_frozen_receiver"] for s in edge_stats)
+    constrained = "message_bwd_memo" in breakdown and not os.environ.get("VSSR_FULL_GRAD")
+    ms = lambda k: breakdown.get(k, {"ms": 0.0})["ms"]
+    slot = lambda n_edges, slots: n_edges * slots * 64 * 4 * 3 * M     # 64 lanes x (2 features x 2 flop) x 3 layers x models
+    # (evals-1) constrained evaluations + 1 full-gradient evaluation per relaxation
+    ce, fe = (evals - 1, 1) if constrained else (0, evals)
+    ex_fwd = evals * (slot(d, MSG_SLOTS["direct_fwd"]) + slot(m, MSG_SLOTS["memo_fwd"]))
+    ex_bwd = (ce * (slot(d - df, MSG_SLOTS["direct_bwd"]) + slot(df, MSG_SLOTS["direct_bwd_frozen_receiver"])
+                    + slot(m, MSG_SLOTS["memo_bwd_state"]) * 2 / 3)           # constrained: nothing at layer 0
+              + fe * (slot(d, MSG_SLOTS["direct_bwd"]) + slot(m, MSG_SLOTS["memo_bwd_full"])))
+    classes = {}
+
+    def add(key, t_ms, algo_flop, exec_flop, peak, pipe, bytes_algo=None):
+        if t_ms <= 0:
+            return
+        c = {"ms": round(t_ms, 3), "pipe": pipe}
+        if algo_flop is not None:
+            c["algorithmic_tflops"] = algo_flop / (t_ms * 1e-3) / 1e12
+            c["frac_algorithmic_of_tf32_tensor_peak"] = c["algorithmic_tflops"] / tf32
+        if exec_flop is not None:
+            c["executed_tflops"] = exec_flop / (t_ms * 1e-3) / 1e12
+            c["frac_executed_of_pipe_peak"] = c["executed_tflops"] / peak
+            c["pipe_peak_tflops"] = peak
+        if bytes_algo is not None:
+            c["achieved_gbs"] = bytes_algo / (t_ms * 1e-3) / 1e9
+            c["frac_of_hbm_peak"] = c["achieved_gbs"] / hbm
+        classes[key] = c
+
+    E = d + m
+    gemm_algo = 2 * GEMM_FLOP_PER_ATOM * M * a_prof * evals                 # forward + backward
+    add("gemm", ms("gemm_tcgen05_3xtf32"), gemm_algo, 3 * gemm_algo, tf32, "tensor (tcgen05 kind::tf32, 3 MMAs per algorithmic MAC)")
+    add("message_fwd", ms("message_fwd") + ms("message_fwd_memo"), FILTER_FLOP_PER_EDGE * E * M * evals, ex_fwd, FFMA2_PEAK,
+        "fp32 FMA (packed FFMA2)")
+    add("message_bwd", ms("message_bwd") + ms("message_bwd_memo"), FILTER_FLOP_PER_EDGE * E * M * evals, ex_bwd, FFMA2_PEAK,
+        "fp32 FMA (packed FFMA2)")
+    # element-wise glue: ~ (2..12 floats per atom-feature) per kernel; algorithmic bytes of the un-fused dataflow
+    ew_bytes = 4.0 * 128 * M * a_prof * evals * 3 * (8 + 16 + 19 + 9)        # nrm, update_fwd, update_bwd, nrm_bwd per layer
+    add("elementwise", ms("elementwise"), None, None, None, "HBM", bytes_algo=ew_bytes)
+    if not classes:
+        return None
+    dom = max(classes, key=lambda k: classes[k]["ms"])
+    c = classes[dom]
+    traffic, traffic_src, per_eval = None, None, None
+    caps = sorted((ROOT / "profiles").glob("r*_ncu_traffic.json"))
+    if caps:
+        cap = json.loads(caps[-1].read_text())
+        key = {"gemm": "gemm_tcgen05_3xtf32"}.get(dom, dom)
+        if key in cap.get("classes", {}):
+            traffic = cap["classes"][key]["dram_bytes_per_launch"]
+            traffic_src = f"profiles/{caps[-1].name} (mean dram__bytes_read+write per launch, {cap['classes'][key]['launches_captured']} launches)"
+        per_eval = cap.get("dram_bytes_per_evaluation")
+    is_tensor = dom == "gemm"
+    total_ms = sum(v["ms"] for v in breakdown.values())
+    algo_all = (gemm_algo + 2 * FILTER_FLOP_PER_EDGE * E * M * evals)
+    return {"bound": "tensor" if is_tensor else "fma", "kernel": dom,
+            "achieved": c["algorithmic_tflops"] if is_tensor else c["executed_tflops"],
+            "peak": tf32 if is_tensor else FFMA2_PEAK, "unit": "TFLOP/s",
+            "frac": c["frac_algorithmic_of_tf32_tensor_peak"] if is_tensor else c["frac_executed_of_pipe_peak"],
+            "frac_algorithmic_of_tf32_tensor_peak": c["frac_algorithmic_of_tf32_tensor_peak"],
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": src + f"; FFMA2 {FFMA2_PEAK} TFLOP/s measured (profiles/microbench/ffma2.cu)",
+            "classes": classes,
+            "whole_step": {"algorithmic_tflops": algo_all / (total_ms * 1e-3) / 1e12,
+                           "frac_of_tf32_tensor_peak": algo_all / (total_ms * 1e-3) / 1e12 / tf32,
+                           "class_ms_sum": round(total_ms, 2)},
+            "edges_per_evaluation": {"direct": d // max(len(edge_stats), 1), "memoised": m // max(len(edge_stats), 1),
+                                     "direct_with_frozen_receiver": df // max(len(edge_stats), 1),
+                                     "canonical_structures": edge_stats[0]["canonical_structures"] if edge_stats else None,
+                                     "structures": edge_stats[0]["structures"] if edge_stats else None},
+            "dram_bytes_per_evaluation": {"measured_ncu": per_eval, "fused_ideal": 320.0 * a_prof / max(len(edge_stats), 1),
+                                          "note": "SURVEY.md 8d: 320 B per atom-evaluation if the whole model were one fused kernel"},
+            "note": "message kernels run on the fp32 FMA pipe: `frac` = executed packed-FMA issue slots / measured FFMA2 peak; the "
+                    "north star's tensor-core bound for the K=20 filter contraction is reported as frac_algorithmic_of_tf32_tensor_peak"
+                    if not is_tensor else "3xTF32 on tcgen05: `frac` = algorithmic FLOPs / TF32 peak (x3 in issued tensor MACs)"}
+
+
+def classical_roofline(breakdown, a_prof, evals, peaks):
+    """Persistent one-CTA-per-chain kernel: the slab never leaves shared memory between FIRE steps, so HBM traffic is ~0
+    and the kernel is FP64-pipe / latency bound.  Reported: the algorithmic HBM figure of SURVEY.md 8d (53 B per
+    atom-evaluation if it streamed) and atom-evaluations/s."""
+    hbm = peaks["hbm_gbs"] if peaks else 6650.0
+    k = "classical_relax"
+    if k not in breakdown or breakdown[k]["ms"] <= 0:
+        return None
+    t = breakdown[k]["ms"] * 1e-3
+    achieved = 53.0 * a_prof * evals / t / 1e9
+    return {"bound": "hbm", "kernel": k, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+            "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+            "atom_evals_per_sec": a_prof * evals / t,
+            "note": "upper bound on evaluations: converged chains stop early inside the kernel. The kernel keeps the whole relaxation "
+                    "in shared memory (0 B of HBM traffic between FIRE steps), so the HBM fraction only shows that it is not "
+                    "bandwidth-bound; it is FP64/SFU-latency bound with one 128-thread CTA per chain"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--chains-per-gpu", type=int, default=0)
+    ap.add_argument("--burn-in", type=int, default=-1, help="untimed MC steps before the timed region (default: per workload)")
+    ap.add_argument("--groups", type=int, default=1,
+                    help="interleaved chain groups of the e2e driver (MultiChainMC.pipeline); 1 = plain lock step, which is "
+                         "fastest here: the host part of a step is ~3 ms and half-size batches cost the GPU more than that")
+    ap.add_argument("--cpu-baseline-proposals", type=int, default=0)
+    ap.add_argument("--torch-gpu-proposals", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true")
+    args = ap.parse_args()
+    explicit = args.workload is not None
+    args.workload = args.workload or "sto_painn"
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from surface_sampling_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1) // 2))   # host threads are for launching, not for BLAS
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = {"lib": _lib.load(), "world": world, "rank": rank, "local": local}
+    name = args.workload
+    burn = args.burn_in if args.burn_in >= 0 else WORKLOADS[name]["burn_in"]
+    out = run_workload(name, args, ctx, args.steps, args.warmup, burn, headline=True)
+    if not explicit and not args.no_extra_workloads:
+        # the other BASELINE configs, short runs (their own value / e2e / roofline / cpu_baseline)
+        out["workloads"] = []
+        for other in ("gan_tersoff", "si_sw", "sto_pourbaix"):
+            o = run_workload(other, args, ctx, min(args.steps, 10), 3, WORKLOADS[other]["burn_in"], headline=False)
+            out["workloads"].append({k: o[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "dtype", "config",
+                                                       "e2e", "gpu_launches", "roofline", "kernel_breakdown_ms", "reference_published_single_chain") if k in o}
+                                    | ({"cpu_baseline": o["cpu_baseline"]} if "cpu_baseline" in o else {}))
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
-            n, dt, ev = cpu_oracle_proposals(name, args.cpu_baseline_proposals, threads)
-            out["cpu_baseline"] = {"value": n / dt, "unit": "proposals/s", "cores": threads, "kind": "port",
-                                   "sample": f"{n} single-chain relaxed proposals of the same workload ({dt:.1f} s), "
-                                             "oracle port of the reference path on the host cores",
-                                   "painn_atom_model_evals_per_sec": ev / dt if ev else None}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -161,6 +161,18 @@ int vssr_painn_relax(const float* weights, int32_t n_models, double* pos /*[A,3]
                      void* workspace, size_t workspace_bytes, double* out /*[B,8]*/, float* forces /*[A,3]*/,
                      float* forces_std /*[A,3] or NULL*/, int32_t* status, void* stream);
 
+/* Work actually done by the LAST evaluation that used a workspace (bench.py: executed-work roofline; no counterpart in
+ * the reference).  out5 (device, 5 x int64) = [direct edges (filter evaluated), memoised edges, direct edges whose
+ * receiver is a frozen framework atom, canonical structures (group memo kernels), edges of the cutoff+skin list].
+ * `workspace` is the buffer given to vssr_painn_energy_grad / vssr_painn_relax with the SAME (n_models, n_atoms,
+ * e_cap); `rowptr` the neighbour list used (the relax variant finds it inside its own workspace). */
+int vssr_painn_edge_stats(const void* workspace, int32_t n_models, int32_t n_atoms, int64_t e_cap,
+                          const int32_t* atom_ptr, int32_t n_struct, const int32_t* rowptr,
+                          const void* filter_cache, int32_t fc_n0, int64_t fc_e_cap0, int64_t* out5, void* stream);
+int vssr_painn_relax_edge_stats(const void* relax_workspace, int32_t n_models, int32_t n_atoms, int64_t e_cap,
+                                const int32_t* atom_ptr, int32_t n_struct, const void* filter_cache,
+                                int32_t fc_n0, int64_t fc_e_cap0, int64_t* out5, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Classical many-body potentials (fp64): LAMMPS `pair_style tersoff` and `pair_style sw` forms.
  * One CTA per structure; the structure (<= n_max atoms) lives in shared memory for the whole
@@ -168,9 +180,13 @@ int vssr_painn_relax(const float* weights, int32_t n_models, double* pos /*[A,3]
  *   Tersoff: [ntypes^3, 14] doubles in LAMMPS file order (m gamma lambda3 c d costheta0 n beta
  *            lambda2 B R D lambda1 A), index ((t_i*ntypes)+t_j)*ntypes+t_k.
  *   SW     : [ntypes^3, 10] doubles (epsilon sigma a lambda gamma costheta0 A B p q), same index.
+ *   EAM    : [nrho, drho, nr, dr, rc, 0, 0, 0] then the three 7-coefficient spline tables of LAMMPS
+ *            PairEAM::interpolate, rows 0..n (row 0 unused): F(rho) (nrho+1 rows), rho(r) (nr+1), r*phi(r) (nr+1).
  * ---------------------------------------------------------------------------------------- */
 #define VSSR_POT_TERSOFF 0
 #define VSSR_POT_SW 1
+#define VSSR_POT_EAM 2   /* LAMMPS `pair_style eam`, single-element funcfl (LAMMPSRunSurfCalc: mcmc/calculators/
+                            calculators.py:755-811, tests/test_Cu.py, tests/test_Au.py); ntypes must be 1 */
 size_t vssr_classical_smem_bytes(int32_t n_max, int32_t max_nbr);
 int vssr_classical_energy_forces(int32_t kind, const double* params, int32_t ntypes,
                                  const double* pos /*[A,3]*/, const int32_t* types /*[A]*/,

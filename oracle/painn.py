@@ -88,10 +88,13 @@ def load_golden_weights(path) -> list[dict[str, np.ndarray]]:
 class PainnOracle:
     """One PaiNN model; ``energy_and_grad`` returns kcal/mol like the NFF module does."""
 
-    def __init__(self, state: dict[str, np.ndarray], dtype=torch.float32, cutoff: float = CUTOFF):
+    def __init__(self, state: dict[str, np.ndarray], dtype=torch.float32, cutoff: float = CUTOFF, device="cpu"):
+        # device="cuda": the same eager torch code on the GPU -- bench.py's "reference-equivalent GPU path" baseline
+        # (BASELINE.md section 2, config 4); everything else in the repo uses the CPU default
         self.dtype = dtype
         self.cutoff = cutoff
-        self.w = {k: torch.tensor(np.asarray(v), dtype=dtype) for k, v in state.items()}
+        self.device = torch.device(device)
+        self.w = {k: torch.tensor(np.asarray(v), dtype=dtype, device=self.device) for k, v in state.items()}
 
     # -- pieces -------------------------------------------------------------------------
     def _edge_geometry(self, xyz, nbr_i, nbr_j, offsets):
@@ -109,7 +112,7 @@ class PainnOracle:
         dist = ((r_ij ** 2 + 1e-10).sum(-1)) ** 0.5
         unit = r_ij / dist.reshape(-1, 1)
         # PainnRadialBasis: sin(n pi d / cutoff) / d, zero for d >= cutoff
-        n = torch.arange(1, N_RBF + 1, dtype=self.dtype)
+        n = torch.arange(1, N_RBF + 1, dtype=self.dtype, device=xyz.device)
         shape_d = dist.unsqueeze(-1)
         coef = n * math.pi / self.cutoff
         denom = torch.where(shape_d == 0, torch.ones_like(shape_d), shape_d)
@@ -120,7 +123,7 @@ class PainnOracle:
         env = torch.where(dist >= self.cutoff, torch.zeros_like(env), env)
 
         s = w["embed_block.atom_embed.weight"][z]            # [N,F]
-        v = torch.zeros(n_atoms, FEAT, 3, dtype=self.dtype)  # [N,F,3]
+        v = torch.zeros(n_atoms, FEAT, 3, dtype=self.dtype, device=xyz.device)  # [N,F,3]
         for l in range(N_CONV):
             p = f"message_blocks.{l}.inv_message."
             h = swish(s @ w[p + "inv_dense.layers.0.weight"].T + w[p + "inv_dense.layers.0.bias"])
@@ -167,14 +170,15 @@ class PainnOracle:
         return e_atom.sum()
 
     def energy_and_grad(self, pos, numbers, nbr_i, nbr_j, offsets):
-        xyz = torch.tensor(np.asarray(pos), dtype=self.dtype, requires_grad=True)
-        z = torch.as_tensor(np.asarray(numbers), dtype=torch.long)
-        off = torch.tensor(np.asarray(offsets), dtype=self.dtype)
-        ni = torch.as_tensor(np.asarray(nbr_i), dtype=torch.long)
-        nj = torch.as_tensor(np.asarray(nbr_j), dtype=torch.long)
+        dev = self.device
+        xyz = torch.tensor(np.asarray(pos), dtype=self.dtype, device=dev, requires_grad=True)
+        z = torch.as_tensor(np.asarray(numbers), dtype=torch.long).to(dev)
+        off = torch.tensor(np.asarray(offsets), dtype=self.dtype, device=dev)
+        ni = torch.as_tensor(np.asarray(nbr_i), dtype=torch.long).to(dev)
+        nj = torch.as_tensor(np.asarray(nbr_j), dtype=torch.long).to(dev)
         e = self.forward_energy(xyz, z, ni, nj, off)
         (g,) = torch.autograd.grad(e, xyz)
-        return e.detach(), g.detach()
+        return e.detach().cpu(), g.detach().cpu()
 
 
 def stoich_offset_kcal(numbers, stoidict: dict) -> float:
@@ -190,8 +194,8 @@ class EnsembleOracle:
     mean and population std over models (SURVEY.md App. A.2 'Units/offset')."""
 
     def __init__(self, states, offset_data: dict | None, dtype=torch.float32, cutoff=CUTOFF,
-                 skin=SKIN):
-        self.models = [PainnOracle(s, dtype=dtype, cutoff=cutoff) for s in states]
+                 skin=SKIN, device="cpu"):
+        self.models = [PainnOracle(s, dtype=dtype, cutoff=cutoff, device=device) for s in states]
         self.offset_data = offset_data
         self.dtype = dtype
         self.cutoff = cutoff

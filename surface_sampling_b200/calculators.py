@@ -299,6 +299,14 @@ class NFFPourbaix(EnsembleNFF):
         atoms = self.atoms if atoms is None else atoms
         return -(self.get_delta_G1(atoms=atoms) + self.get_delta_G2(atoms=atoms))
 
+    def surface_energy_fn(self, phi=None, pH=None):
+        """Host scalar for the batched MC driver: (slab energy, symbols) -> grand potential at this calculator's table,
+        temperature and corrections, at the given (phi, pH) grid point (default: the calculator's own)."""
+        phi = self.phi if phi is None else phi
+        pH = self.pH if pH is None else pH
+        table, temp, corr = self.pourbaix_atoms, self.temp, self.adsorbate_corrections
+        return lambda e, symbols: pourbaix_potential_from(e, symbols, table, phi, pH, temp, corr)
+
     def set(self, **kwargs) -> dict:
         changed = EnsembleNFF.set(self, **kwargs)
         p = self.parameters
@@ -323,6 +331,24 @@ class NFFPourbaix(EnsembleNFF):
             self.results["pourbaix_potential"] = v
         if hasattr(atoms, "results"):
             atoms.results.update(self.results)
+
+
+def pourbaix_potential_from(energy, symbols, pourbaix_atoms: dict, phi: float, pH: float, temp: float,
+                            adsorbate_corrections: dict | None = None) -> float:
+    """H7 scalar (calculators.py:197-305) on plain inputs: the grand potential of one structure whose slab energy is
+    already known.  NFFPourbaix.get_pourbaix_potential evaluates exactly this; the multi-chain driver calls it once per
+    chain with that chain's (pH, phi) grid point (BASELINE config 5)."""
+    cnt = Counter(symbols)
+    sum_std = 0
+    for sym, c in cnt.items():
+        sum_std += c * pourbaix_atoms[sym].atom_std_state_energy
+    slab_energy = energy + adsorbate_correction(dict(cnt), adsorbate_corrections or {})
+    dg1 = sum_std - slab_energy
+    dg2 = 0
+    for sym in symbols:
+        a = pourbaix_atoms[sym]
+        dg2 += a.delta_G2_std + (-a.num_e * phi - np.log(10) * a.num_H * temp * pH + temp * np.log(a.species_conc))
+    return -(dg1 + dg2)
 
 
 def adsorbate_correction(counts: dict, corrections: dict) -> float:
@@ -446,6 +472,64 @@ class LAMMPSSurfCalc(LAMMMPSCalc):
         if "surface_energy" in properties:
             self.results["surface_energy"] = (self.results["energy"] if "energy" in self.results
                                               else self.get_surface_energy(atoms=atoms))
+
+
+class LAMMPSRunSurfCalc(Calculator):
+    """``LAMMPSRunSurfCalc`` (calculators.py:755-811): ASE's file-based LAMMPS runner with ``surface_energy`` =
+    potential energy, as used by the Cu(100) / Au(110) toy runs (tutorials/example.ipynb, tests/test_Cu.py,
+    tests/test_Au.py) with ``pair_style eam`` and a single-element funcfl file.  Served by the EAM branch of the
+    classical CUDA kernel instead of an ``lmp`` subprocess per call; no relaxation on this path (the reference runs it
+    with ``relax_atoms`` unset)."""
+    name = "lammpsrun"
+    implemented_properties = ("energy", "free_energy", "forces", "energies", "surface_energy")
+
+    def __init__(self, files=None, funcfl=None, n_max=32, max_nbr=128, device="cuda", **kwargs):
+        super().__init__()
+        self.files = [str(f) for f in (files or [])]
+        self._funcfl = funcfl                 # parsed table (loaders.load_eam_funcfl) or None -> read from `files`
+        self._engine_cfg = (n_max, max_nbr, device)
+        self._engine = None
+        self.run_dir = kwargs.get("tmp_dir", ".")
+        self.logger = kwargs.get("logger", logging.getLogger(__name__))
+
+    @property
+    def engine(self) -> eng.ClassicalEngine:
+        if self._engine is None:
+            style = self.parameters.get("pair_style", "eam")
+            if style != "eam":
+                raise NotImplementedError(f"pair_style {style!r}: LAMMPSRunSurfCalc serves `eam` (funcfl) on the B200 engine")
+            tab = self._funcfl
+            if tab is None:
+                from .loaders import load_eam_funcfl
+                coeff = self.parameters.get("pair_coeff", ["* * "])[0].split()[-1]      # "* * Cu_u3.eam"
+                match = [f for f in self.files if f.endswith(coeff)] or self.files
+                if not match:
+                    raise FileNotFoundError("no EAM potential file: pass files=[...] or funcfl=")
+                tab = load_eam_funcfl(match[0])
+            n_max, max_nbr, device = self._engine_cfg
+            self._engine = eng.ClassicalEngine(eng.POT_EAM, eng.eam_param_block(tab), 1, n_max=n_max, max_nbr=max_nbr,
+                                               device=device)
+        return self._engine
+
+    def get_surface_energy(self, atoms=None) -> float:
+        return self.get_potential_energy(atoms=self.atoms if atoms is None else atoms)
+
+    def calculate(self, atoms=None, properties=implemented_properties, system_changes=ALL_CHANGES):
+        atoms = self.atoms if atoms is None else atoms
+        Calculator.calculate(self, atoms, properties, system_changes)
+        pos, num, cell, pbc, _ = as_arrays(atoms)
+        if len(set(num.tolist())) > 1:
+            raise NotImplementedError("funcfl EAM is a single-element potential")
+        b = eng.Batch.from_arrays([pos], [np.zeros(len(num), np.int32)], [cell], [pbc])
+        if len(num) > self._engine_cfg[0]:          # structure outgrew the shared-memory budget: re-size the engine
+            self._engine_cfg = (int(len(num) * 1.25) + 8, *self._engine_cfg[1:])
+            self._engine = None
+        r = self.engine.energy_forces(b)
+        e = float(r["energy"].item())
+        self.results.update({"energy": e, "free_energy": e, "forces": r["forces"].cpu().numpy(),
+                             "energies": r["per_atom_energies"].cpu().numpy()})
+        if "surface_energy" in properties:
+            self.results["surface_energy"] = e
 
 
 # ----------------------------------------------------------------------------------------------

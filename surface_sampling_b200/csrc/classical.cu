@@ -31,6 +31,7 @@ struct Smem {
   unsigned char* rev;  // [n_max][max_nbr]
   unsigned char* fixed;  // [n_max]
   double* red;    // [4][3]
+  double* aux;    // [n_max] EAM: dF/drho of every atom between the two passes
 };
 
 __host__ __device__ inline size_t smem_layout(int n_max, int max_nbr, char* base, Smem* s) {
@@ -54,7 +55,9 @@ __host__ __device__ inline size_t smem_layout(int n_max, int max_nbr, char* base
   unsigned char* rev = (unsigned char*)take((size_t)n_max * max_nbr);
   unsigned char* fixed = (unsigned char*)take((size_t)n_max);
   double* red = (double*)take(4 * 3 * 8);
+  double* aux = (double*)take((size_t)n_max * 8);
   if (s) {
+    s->aux = aux;
     s->x = x; s->f = f; s->v = v; s->x0 = x0; s->G = G; s->eat = eat; s->own = own; s->type = type; s->cnt = cnt;
     s->nj = nj; s->ns = ns; s->rev = rev; s->fixed = fixed; s->red = red;
   }
@@ -392,11 +395,89 @@ __device__ void sw_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, c
   }
 }
 
+// ---------------------------------------------------------------------------------- EAM (funcfl, one element)
+// LAMMPS `pair_style eam` (oracle/eam.py): the potential behind LAMMPSRunSurfCalc's Cu / Au toy
+// runs (mcmc/calculators/calculators.py:755-811, tests/test_Cu.py, tests/test_Au.py).  `params` =
+// [nrho, drho, nr, dr, rc, 0, 0, 0 | frho spline (nrho+1) x 7 | rhor spline (nr+1) x 7 | z2r spline (nr+1) x 7],
+// the 7-coefficient splines of PairEAM::interpolate, built on the host (engine.eam_param_block).
+constexpr int EAM_HDR = 8;
+__device__ __forceinline__ void eam_lookup(const double* __restrict__ spl, double x, double rdx, int n, double& val,
+                                           double& der) {
+  double p = x * rdx + 1.0;
+  int m = (int)p;
+  m = m < 1 ? 1 : (m > n - 1 ? n - 1 : m);
+  p -= (double)m;
+  p = fmin(p, 1.0);
+  const double* c = spl + (size_t)m * 7;
+  val = ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6);
+  der = (__ldg(c) * p + __ldg(c + 1)) * p + __ldg(c + 2);
+}
+
+__device__ void eam_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, const double* __restrict__ params,
+                           double rcut) {
+  const int nrho = (int)params[0], nr = (int)params[2];
+  const double rdrho = 1.0 / params[1], rdr = 1.0 / params[3];
+  const double* frho = params + EAM_HDR;
+  const double* rhor = frho + (size_t)(nrho + 1) * 7;
+  const double* z2r = rhor + (size_t)(nr + 1) * 7;
+  const double rhomax = (double)(nrho - 1) * params[1];
+  // pass A: host electron density of every atom -> embedding energy F(rho_i) and F'(rho_i)
+  for (int i = threadIdx.x; i < n; i += NT) {
+    double rho = 0.0;
+    const int cn = s.cnt[i];
+    for (int t = 0; t < cn; ++t) {
+      double x, y, z;
+      edge_vec(s, ci, i, s.nj[i * max_nbr + t], s.ns[i * max_nbr + t], x, y, z);
+      const double r = sqrt(x * x + y * y + z * z);
+      if (r < rcut) {
+        double v, d;
+        eam_lookup(rhor, r, rdr, nr, v, d);
+        rho += v;
+      }
+    }
+    double F, dF;
+    eam_lookup(frho, rho, rdrho, nrho, F, dF);
+    if (rho > rhomax) F += dF * (rho - rhomax);      // linear extrapolation beyond the table
+    s.eat[i] = F;
+    s.aux[i] = dF;
+  }
+  __syncthreads();
+  // pass B: pair term (half per direction) and the gradient of both terms along every directed edge i <- j
+  for (int i = threadIdx.x; i < n; i += NT) {
+    const int cn = s.cnt[i];
+    const double dFi = s.aux[i];
+    double gix = 0.0, giy = 0.0, giz = 0.0, ei = s.eat[i];
+    double* Gi = s.G + (size_t)i * max_nbr * 3;
+    for (int t = 0; t < cn; ++t) {
+      const int j = s.nj[i * max_nbr + t];
+      double x, y, z;
+      edge_vec(s, ci, i, j, s.ns[i * max_nbr + t], x, y, z);
+      const double r = sqrt(x * x + y * y + z * z);
+      double gx = 0.0, gy = 0.0, gz = 0.0;
+      if (r < rcut) {
+        double rho_e, drho_e, z2, dz2;
+        eam_lookup(rhor, r, rdr, nr, rho_e, drho_e);
+        eam_lookup(z2r, r, rdr, nr, z2, dz2);
+        const double ir = 1.0 / r;
+        const double phi = z2 * ir, dphi = dz2 * ir - phi * ir;
+        ei += 0.5 * phi;
+        const double fpair = (dFi + s.aux[j]) * drho_e * 0.5 + 0.5 * dphi;
+        gx = fpair * x * ir; gy = fpair * y * ir; gz = fpair * z * ir;
+      }
+      Gi[3 * t] = gx; Gi[3 * t + 1] = gy; Gi[3 * t + 2] = gz;
+      gix -= gx; giy -= gy; giz -= gz;
+    }
+    s.own[3 * i] = gix; s.own[3 * i + 1] = giy; s.own[3 * i + 2] = giz;
+    s.eat[i] = ei;
+  }
+}
+
 // phase 1 (centre terms) + phase 2 (gather through reverse map) -> s.f = -dE/dx ; returns E (all threads)
 __device__ double eval_forces(int kind, const Smem& s, const Cell64& ci, int n, int max_nbr,
                               const double* __restrict__ params, int ntypes, double rcut, int32_t* status) {
   if (kind == VSSR_POT_TERSOFF) tersoff_phase1(s, ci, n, max_nbr, params, ntypes, rcut, status);
-  else sw_phase1(s, ci, n, max_nbr, params, ntypes, rcut, status);
+  else if (kind == VSSR_POT_SW) sw_phase1(s, ci, n, max_nbr, params, ntypes, rcut, status);
+  else eam_phase1(s, ci, n, max_nbr, params, rcut);
   __syncthreads();
   double e = 0.0, z0 = 0.0, z1 = 0.0;
   for (int j = threadIdx.x; j < n; j += NT) {
@@ -445,6 +526,7 @@ __device__ __forceinline__ double block_max(double a, double* red) {
 }
 
 __device__ double max_cut(int kind, const double* __restrict__ params, int ntypes) {
+  if (kind == VSSR_POT_EAM) return params[4];
   double c = 0.0;
   const int np = ntypes * ntypes * ntypes;
   for (int q = 0; q < np; ++q) {
@@ -485,7 +567,8 @@ __global__ void __launch_bounds__(NT) classical_kernel(int kind, const double* _
   __syncthreads();
   // potential parameters: shared-memory copy when they fit (ntypes <= 3)
   __shared__ double sprm_buf[27 * 14];
-  const int nprm = ntypes * ntypes * ntypes * (kind == VSSR_POT_TERSOFF ? 14 : 10);
+  // (the EAM spline tables, ~84 KB, stay in global memory: read-only, L1/L2 resident)
+  const int nprm = kind == VSSR_POT_EAM ? (1 << 30) : ntypes * ntypes * ntypes * (kind == VSSR_POT_TERSOFF ? 14 : 10);
   const double* sprm = params;
   if (nprm <= 27 * 14) {
     for (int q = threadIdx.x; q < nprm; q += NT) sprm_buf[q] = params[q];
@@ -613,7 +696,8 @@ extern "C" int vssr_classical_energy_forces(int32_t kind, const double* params, 
                                             double* energy, double* forces, double* per_atom_energy, int32_t* status,
                                             void* stream) {
   if (!params || !pos || !types || !atom_ptr || !cell || !pbc || !energy || !forces || !status) return VSSR_ERR_ARG;
-  if (kind != VSSR_POT_TERSOFF && kind != VSSR_POT_SW) return VSSR_ERR_UNSUPPORTED;
+  if (kind != VSSR_POT_TERSOFF && kind != VSSR_POT_SW && kind != VSSR_POT_EAM) return VSSR_ERR_UNSUPPORTED;
+  if (kind == VSSR_POT_EAM && ntypes != 1) return VSSR_ERR_UNSUPPORTED;   // funcfl: one element
   if (n_struct <= 0 || n_max <= 0 || n_max > 32767 || max_nbr <= 0 || max_nbr > 254) return VSSR_ERR_ARG;
   const size_t smem = smem_layout(n_max, max_nbr, nullptr, nullptr);
   if (smem > 227 * 1024) return VSSR_ERR_ARG;
@@ -631,7 +715,8 @@ extern "C" int vssr_classical_relax(int32_t kind, const double* params, int32_t 
                                     int32_t max_nbr, int32_t relax_steps, double fmax, double skin, double* out,
                                     double* forces, int32_t* status, void* stream) {
   if (!params || !pos || !types || !fixed || !atom_ptr || !cell || !pbc || !out || !status) return VSSR_ERR_ARG;
-  if (kind != VSSR_POT_TERSOFF && kind != VSSR_POT_SW) return VSSR_ERR_UNSUPPORTED;
+  if (kind != VSSR_POT_TERSOFF && kind != VSSR_POT_SW && kind != VSSR_POT_EAM) return VSSR_ERR_UNSUPPORTED;
+  if (kind == VSSR_POT_EAM && ntypes != 1) return VSSR_ERR_UNSUPPORTED;
   if (n_struct <= 0 || n_max <= 0 || n_max > 32767 || max_nbr <= 0 || max_nbr > 254 || relax_steps < 0 || skin < 0)
     return VSSR_ERR_ARG;
   const size_t smem = smem_layout(n_max, max_nbr, nullptr, nullptr);
@@ -650,7 +735,8 @@ extern "C" int vssr_classical_relax_host(int32_t kind, const double* params, int
                                          int32_t n_max, int32_t max_nbr, int32_t relax_steps, double fmax, double skin,
                                          double* out, double* forces, int32_t* status) {
   if (!params || !pos || !types || !fixed || !atom_ptr || !cell || !pbc || !out || !status) return VSSR_ERR_ARG;
-  const int np = ntypes * ntypes * ntypes * (kind == VSSR_POT_TERSOFF ? 14 : 10);
+  const int np = kind == VSSR_POT_EAM ? EAM_HDR + (((int)params[0] + 1) + 2 * ((int)params[2] + 1)) * 7
+                                      : ntypes * ntypes * ntypes * (kind == VSSR_POT_TERSOFF ? 14 : 10);
   const size_t b_par = (size_t)np * 8, b_pos = (size_t)n_atoms * 24, b_typ = (size_t)n_atoms * 4, b_fix = n_atoms;
   const size_t b_ptr = (size_t)(n_struct + 1) * 4, b_cell = (size_t)n_struct * 72, b_pbc = (size_t)n_struct * 3;
   const size_t b_out = (size_t)n_struct * 64;

@@ -304,6 +304,15 @@ extern "C" size_t vssr_painn_relax_workspace_bytes(int32_t n_models, int32_t n_a
   return carve_relax(nullptr, n_models, n_atoms, n_atoms, e_cap).bytes;
 }
 
+extern "C" int vssr_painn_relax_edge_stats(const void* relax_workspace, int32_t n_models, int32_t n_atoms, int64_t e_cap,
+                                           const int32_t* atom_ptr, int32_t n_struct, const void* filter_cache,
+                                           int32_t fc_n0, int64_t fc_e_cap0, int64_t* out5, void* stream) {
+  if (!relax_workspace) return VSSR_ERR_ARG;
+  const RelaxWs w = carve_relax(const_cast<void*>(relax_workspace), n_models, n_atoms, n_atoms, e_cap);
+  return vssr_painn_edge_stats(w.painn, n_models, n_atoms, e_cap, atom_ptr, n_struct, w.rowptr, filter_cache, fc_n0,
+                               fc_e_cap0, out5, stream);
+}
+
 extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* pos, const int32_t* z,
                                 const uint8_t* fixed, const int32_t* atom_ptr, const float* cell, const uint8_t* pbc,
                                 const double* offset_ev, int32_t n_struct, int32_t n_atoms,

@@ -944,16 +944,16 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   // group kernels: G canonical structures per CTA (as many as fit in shared memory), no ring
   constexpr int G_FWD0 = 4, T_FWD0 = 512, G_FWD = 2, T_FWD = 832, G_STATE = 2, T_STATE = 512;
   const bool group_on = memo && !(fc_flags & VSSR_FC_NO_PAIR);
-  // a group is taken when its structures are canonical AND its atoms fit the staging area (the budget is what G
-  // structures of the batch's largest size would need, capped by the 227 KB of an SM; both kernels apply the same test)
+  // a group is taken when its structures are canonical AND the FRAMEWORK rows of G structures (n0 atoms each -- the only
+  // rows a memoised edge can touch) fit the 227 KB of an SM: independent of how many adsorbates the chains carry
   const size_t kSmemCap = 226 * 1024;   // 227 KB per SM minus the kernels' few bytes of static shared memory
-  auto cap = [&](size_t want_bytes) { return want_bytes < kSmemCap ? want_bytes : kSmemCap; };
-  const size_t sp_fwd0 = cap(G_FWD0 * st_fwd0), sp_fwd = cap(G_FWD * st_fwd), sp_state = cap((size_t)G_STATE * nmax * MEMO_STATE_PER * 4);
-  const int ga_fwd0 = (int)(sp_fwd0 / (MsgFwdLayout<true>::PER * 4)), ga_fwd = (int)(sp_fwd / (MsgFwdLayout<false>::PER * 4)),
-            ga_state = (int)(sp_state / (MEMO_STATE_PER * 4));
-  const bool pair_fwd0 = group_on && n_struct >= G_FWD0;
-  const bool pair_fwd = group_on && n_struct >= G_FWD;
-  const bool pair_state = group_on && constrained && n_struct >= G_STATE;
+  const size_t sp_fwd0 = (size_t)G_FWD0 * fc.n0 * MsgFwdLayout<true>::PER * 4, sp_fwd = (size_t)G_FWD * fc.n0 * MsgFwdLayout<false>::PER * 4,
+               sp_state = (size_t)G_STATE * fc.n0 * MEMO_STATE_PER * 4;
+  const int ga_fwd0 = sp_fwd0 <= kSmemCap ? G_FWD0 * fc.n0 : 0, ga_fwd = sp_fwd <= kSmemCap ? G_FWD * fc.n0 : 0,
+            ga_state = sp_state <= kSmemCap ? G_STATE * fc.n0 : 0;
+  const bool pair_fwd0 = group_on && n_struct >= G_FWD0 && ga_fwd0 > 0;
+  const bool pair_fwd = group_on && n_struct >= G_FWD && ga_fwd > 0;
+  const bool pair_state = group_on && constrained && n_struct >= G_STATE && ga_state > 0;
   if (staged) {
     static size_t cfg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     auto want = [&](int k, const void* fn, size_t bytes) -> int {
@@ -1179,6 +1179,43 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   if (constrained)
     VSSR_PROF(VSSR_K_ELEMWISE, st, zero_frozen_grad_kernel<<<dim3(ceil_div(A, 256), M), 256, 0, st>>>(
         atom_ptr, n_struct, A, fc.n0, fc.frozen, grad));
+  return VSSR_OK;
+}
+
+namespace {
+// out[0] direct edges, [1] memoised edges, [2] direct edges whose receiver is a frozen framework atom,
+// [3] canonical structures, [4] edges of the 6 A list -- of the LAST evaluation that used this workspace
+__global__ void edge_stats_kernel(const int32_t* __restrict__ atom_ptr, int n_struct, int n_atoms,
+                                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nvalid,
+                                  const int32_t* __restrict__ nmemo, const int32_t* __restrict__ canonical, int n0,
+                                  const uint8_t* __restrict__ frozen, unsigned long long* __restrict__ out) {
+  unsigned long long d = 0, m = 0, df = 0, c = 0;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_atoms; a += gridDim.x * blockDim.x) {
+    const int il = a - __ldg(atom_ptr + struct_of_atom(atom_ptr, n_struct, a));
+    const int nv = __ldg(nvalid + a);
+    d += nv;
+    m += nmemo ? __ldg(nmemo + a) : 0;
+    if (frozen && il < n0 && frozen[il]) df += nv;
+    if (canonical && a < n_struct) c += __ldg(canonical + a) != 0;
+  }
+  atomicAdd(out, d); atomicAdd(out + 1, m); atomicAdd(out + 2, df); atomicAdd(out + 3, c);
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[4] = (unsigned long long)__ldg(rowptr + n_atoms);
+}
+}  // namespace
+
+extern "C" int vssr_painn_edge_stats(const void* workspace, int32_t n_models, int32_t n_atoms, int64_t e_cap,
+                                     const int32_t* atom_ptr, int32_t n_struct, const int32_t* rowptr,
+                                     const void* filter_cache, int32_t fc_n0, int64_t fc_e_cap0, int64_t* out5,
+                                     void* stream) {
+  if (!workspace || !atom_ptr || !rowptr || !out5 || n_atoms <= 0 || n_struct <= 0) return VSSR_ERR_ARG;
+  const Workspace w = carve(const_cast<void*>(workspace), n_models, n_atoms, e_cap);
+  const FilterCacheView fc = cache_view(filter_cache, n_models, fc_n0, fc_e_cap0);
+  cudaStream_t st = (cudaStream_t)stream;
+  VSSR_CUDA(cudaMemsetAsync(out5, 0, 5 * sizeof(int64_t), st));
+  edge_stats_kernel<<<ceil_div(n_atoms, 256), 256, 0, st>>>(atom_ptr, n_struct, n_atoms, rowptr, w.nvalid,
+                                                            fc.n0 > 0 ? w.nmemo : nullptr, fc.n0 > 0 ? w.canonical : nullptr,
+                                                            fc.n0, fc.frozen, reinterpret_cast<unsigned long long*>(out5));
+  VSSR_LAUNCH_CHECK();
   return VSSR_OK;
 }
 

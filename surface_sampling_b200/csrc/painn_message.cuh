@@ -86,14 +86,18 @@ __device__ __forceinline__ int next_row(int* ctr, int lane) {
 }
 
 // is structure b handled by a group kernel (G consecutive canonical structures per CTA)?
+// (A memoised edge joins two frozen FRAMEWORK atoms, so a group kernel only ever stages the first n0 rows of each
+// structure: whether a group fits shared memory is decided on the host from n0 alone -- `max_atoms` >= G*n0 -- and does
+// not change when the chains collect adsorbates.)
 __device__ __forceinline__ bool in_canonical_group(const int32_t* __restrict__ canonical, const int32_t* __restrict__ atom_ptr,
                                                    int b, int n_struct, int G, int max_atoms) {
-  if (!canonical) return false;
+  (void)atom_ptr;
+  if (!canonical || max_atoms <= 0) return false;
   const int q = (b / G) * G;
   if (q + G > n_struct) return false;
   for (int s = 0; s < G; ++s)
     if (!__ldg(canonical + q + s)) return false;
-  return __ldg(atom_ptr + q + G) - __ldg(atom_ptr + q) <= max_atoms;   // the group's rows must fit the CTA's staging area
+  return true;
 }
 
 // order[a0 + rank] = local index of the row with that rank (cost descending, index ascending on ties).
@@ -832,13 +836,13 @@ __global__ void __launch_bounds__(T, 1) message_fwd_memo_group(
   float* sm[G];
 #pragma unroll
   for (int s = 0; s < G; ++s) { a0[s] = __ldg(atom_ptr + b0 + s); n[s] = __ldg(atom_ptr + b0 + s + 1) - a0[s]; }
-  sm[0] = smem;
+  const int nst = fc.n0;      // staged rows per structure: the framework atoms (senders of every memoised edge)
 #pragma unroll
-  for (int s = 1; s < G; ++s) sm[s] = sm[s - 1] + (size_t)n[s - 1] * PER;
+  for (int s = 0; s < G; ++s) sm[s] = smem + (size_t)s * nst * PER;
 #pragma unroll
   for (int s = 0; s < G; ++s) {
-    stage_rows(sm[s], PER, 0, phi + (mA + a0[s]) * F3 + h * MSG_FC, F3, F, 3, n[s], tid, T);
-    if (!FIRST) stage_rows(sm[s], PER, 3 * MSG_FC, v_in + (mA + a0[s]) * 3 * F + h * MSG_FC, 3 * F, F, 3, n[s], tid, T);
+    stage_rows(sm[s], PER, 0, phi + (mA + a0[s]) * F3 + h * MSG_FC, F3, F, 3, nst, tid, T);
+    if (!FIRST) stage_rows(sm[s], PER, 3 * MSG_FC, v_in + (mA + a0[s]) * 3 * F + h * MSG_FC, 3 * F, F, 3, nst, tid, T);
   }
   const int f0 = h * MSG_FC + 2 * lane;
   const float* __restrict__ wlane = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + f0;
@@ -867,10 +871,15 @@ __global__ void __launch_bounds__(T, 1) message_fwd_memo_group(
       *reinterpret_cast<float2*>(cat + i * 2 * F + f0) = __fadd2_rn(s0, ds[s]);
       float2 ox = dvx[s], oy = dvy[s], oz = dvz[s];
       if (!FIRST) {
-        const float* si = sm[s] + il * PER + 2 * lane;
-        ox = __fadd2_rn(ox, ld2(si + 3 * MSG_FC));
-        oy = __fadd2_rn(oy, ld2(si + 4 * MSG_FC));
-        oz = __fadd2_rn(oz, ld2(si + 5 * MSG_FC));
+        if (il < nst) {
+          const float* si = sm[s] + il * PER + 2 * lane;
+          ox = __fadd2_rn(ox, ld2(si + 3 * MSG_FC));
+          oy = __fadd2_rn(oy, ld2(si + 4 * MSG_FC));
+          oz = __fadd2_rn(oz, ld2(si + 5 * MSG_FC));
+        } else {      // adsorbate row: not staged, nothing memoised -> v_mid = v_in + 0 (same bits as the staged path)
+          const float* vg = v_in + i * 3 * F + f0;
+          ox = __fadd2_rn(ox, ldg2(vg)); oy = __fadd2_rn(oy, ldg2(vg + F)); oz = __fadd2_rn(oz, ldg2(vg + 2 * F));
+        }
       }
       float* vo = v_mid + i * 3 * F + f0;
       *reinterpret_cast<float2*>(vo) = ox;
@@ -898,13 +907,13 @@ __global__ void __launch_bounds__(T, 1) message_bwd_memo_state_group(
   float* sm[G];
 #pragma unroll
   for (int s = 0; s < G; ++s) { a0[s] = __ldg(atom_ptr + b0 + s); n[s] = __ldg(atom_ptr + b0 + s + 1) - a0[s]; }
-  sm[0] = smem;
+  const int nst = fc.n0;
 #pragma unroll
-  for (int s = 1; s < G; ++s) sm[s] = sm[s - 1] + (size_t)n[s - 1] * PER;
+  for (int s = 0; s < G; ++s) sm[s] = smem + (size_t)s * nst * PER;
 #pragma unroll
   for (int s = 0; s < G; ++s) {
-    stage_rows(sm[s], PER, 0, ds + (mA + a0[s]) * F + h * MSG_FC, F, F, 1, n[s], tid, T);
-    stage_rows(sm[s], PER, MSG_FC, dv + (mA + a0[s]) * 3 * F + h * MSG_FC, 3 * F, F, 3, n[s], tid, T);
+    stage_rows(sm[s], PER, 0, ds + (mA + a0[s]) * F + h * MSG_FC, F, F, 1, nst, tid, T);
+    stage_rows(sm[s], PER, MSG_FC, dv + (mA + a0[s]) * 3 * F + h * MSG_FC, 3 * F, F, 3, nst, tid, T);
   }
   const int f0 = h * MSG_FC + 2 * lane;
   const float* __restrict__ wlane = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + f0;
@@ -948,15 +957,22 @@ __global__ void __launch_bounds__(T, 1) message_bwd_memo_state_group(
     for (int s = 0; s < G; ++s) {
       if (il >= n[s]) continue;
       const long long i = mA + a0[s] + il;
-      const float* si = sm[s] + il * PER + 2 * lane;
       float* dpo = dphi + i * F3 + f0;
       float* dvo = dv_in + i * 3 * F + f0;
       *reinterpret_cast<float2*>(dpo) = dp0[s];
       *reinterpret_cast<float2*>(dpo + F) = dp1[s];
       *reinterpret_cast<float2*>(dpo + 2 * F) = neg2(dp2n[s]);
-      *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ld2(si + MSG_FC), dvx[s]);
-      *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ld2(si + 2 * MSG_FC), dvy[s]);
-      *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ld2(si + 3 * MSG_FC), dvz[s]);
+      float2 ox, oy, oz;      // own dv row: staged for framework atoms, from global memory for adsorbate rows
+      if (il < nst) {
+        const float* si = sm[s] + il * PER + 2 * lane;
+        ox = ld2(si + MSG_FC); oy = ld2(si + 2 * MSG_FC); oz = ld2(si + 3 * MSG_FC);
+      } else {
+        const float* dg = dv + i * 3 * F + f0;
+        ox = ldg2(dg); oy = ldg2(dg + F); oz = ldg2(dg + 2 * F);
+      }
+      *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ox, dvx[s]);
+      *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(oy, dvy[s]);
+      *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(oz, dvz[s]);
     }
   }
 }

@@ -259,19 +259,21 @@ class PainnEngine:
     def clear_framework(self):
         self._fc = None
 
-    RESULT_RING = 16   # ~0.2 MB per set at 128 chains
-
-    def _result_buffers(self, B: int, A: int):
-        ring = self.__dict__.setdefault("_res_ring", {"k": 0, "sets": [None] * self.RESULT_RING})
-        k = ring["k"] = (ring["k"] + 1) % self.RESULT_RING
-        cur = ring["sets"][k]
-        if cur is None or cur[0].shape[0] < B or cur[1].shape[0] < A:
-            capB, capA = int(B * 1.5) + 8, int(A * 1.5) + 64
-            cur = ring["sets"][k] = (torch.empty((capB, 8), dtype=torch.float64, device=self.device),
-                                     torch.empty((capA, 3), dtype=torch.float32, device=self.device),
-                                     torch.empty((capA, 3), dtype=torch.float32, device=self.device),
-                                     torch.zeros(1, dtype=torch.int32, device=self.device))
-        return cur[0][:B], cur[1][:A], cur[2][:A], cur[3]
+    def _result_buffers(self, B: int, A: int, into: dict | None):
+        """Output tensors of one relax() call: caller-owned when `into` is given (keys out[B,8] f64, forces[A,3] f32,
+        forces_std[A,3] f32, status[1] i32 -- validated here), else freshly allocated per call (torch's caching
+        allocator: no cudaMalloc after the first MC steps).  A result is never aliased by a later call."""
+        dev = self.device
+        if into is None:
+            return (torch.empty((B, 8), dtype=torch.float64, device=dev), torch.empty((A, 3), dtype=torch.float32, device=dev),
+                    torch.empty((A, 3), dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.int32, device=dev))
+        want = {"out": ((B, 8), torch.float64), "forces": ((A, 3), torch.float32), "forces_std": ((A, 3), torch.float32),
+                "status": ((1,), torch.int32)}
+        for k, (shape, dt) in want.items():
+            t = into.get(k)
+            if t is None or tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device.type != dev.type:
+                raise _lib.VssrError(f"relax(into=...): `{k}` must be a contiguous {dt} tensor of shape {shape} on {dev}")
+        return into["out"], into["forces"], into["forces_std"], into["status"]
 
     def _fc_args(self, constrained: bool = True):
         if self._fc is None:
@@ -337,7 +339,7 @@ class PainnEngine:
                 "energy_kcal_per_model": energy, "grad_kcal_per_model": grad, "embedding": emb}
 
     def relax(self, batch: Batch, relax_steps: int = 20, fmax: float = 0.01, z_host: np.ndarray | None = None,
-              want_std: bool = True, e_cap: int | None = None, check: bool = False):
+              want_std: bool = True, e_cap: int | None = None, check: bool = False, into: dict | None = None):
         """optimize_slab(optimizer='FIRE') for every structure, no host round trip.  batch.pos is
         updated in place.  Returns dict(out[B,8], forces, forces_std, status).
 
@@ -348,7 +350,7 @@ class PainnEngine:
             pos0 = batch.pos.clone()
             cap_try = int(e_cap) if e_cap else batch.n_atoms * self.edges_per_atom
             while True:
-                r = self.relax(batch, relax_steps, fmax, z_host, want_std, cap_try, check=False)
+                r = self.relax(batch, relax_steps, fmax, z_host, want_std, cap_try, check=False, into=into)
                 st = int(r["status"].item())
                 if not (st & 1):
                     return r
@@ -370,9 +372,7 @@ class PainnEngine:
         if self.offset_data is not None:
             zh = z_host if z_host is not None else batch.z.cpu().numpy()
             off = torch.from_numpy(self.offsets_ev(zh, batch.atom_ptr_host)).to(dev, non_blocking=True)
-        # result buffers come from a small ring of persistent allocations (no allocator traffic inside MC steps);
-        # a returned dict stays valid until RESULT_RING further relax() calls of this engine
-        out, forces, fstd_buf, status = self._result_buffers(B, A)
+        out, forces, fstd_buf, status = self._result_buffers(B, A, into)
         fstd = fstd_buf if want_std else None
         status.zero_()
         cell32 = batch.cell32.contiguous()
@@ -381,12 +381,26 @@ class PainnEngine:
                                         batch.max_atoms, self.cutoff, self.skin, int(relax_steps), float(fmax), cap,
                                         *self._fc_args(), _ptr(ws), ws.numel(), _ptr(out), _ptr(forces), _ptr(fstd), _ptr(status), _stream()),
                    "vssr_painn_relax")
+        self._last_relax = (A, cap, M, ws)
         return {"out": out, "forces": forces, "forces_std": fstd, "status": status}
+
+    def last_relax_edge_stats(self, batch: Batch) -> dict:
+        """Work done by the LAST evaluation of the most recent relax() on `batch` (same atom count): numbers of direct
+        and memoised edges etc. (vssr_painn_relax_edge_stats).  For bench.py's executed-work roofline; synchronises."""
+        A, cap, M, ws = self._last_relax
+        assert A == batch.n_atoms, "edge stats refer to the most recent relax() call"
+        out = torch.zeros(5, dtype=torch.int64, device=self.device)
+        fcp, n0, ecap0, _ = self._fc_args()
+        _lib.check(self.lib.vssr_painn_relax_edge_stats(_ptr(ws), M, A, cap, _ptr(batch.atom_ptr), batch.n_struct, fcp, n0,
+                                                        ecap0, _ptr(out), _stream()), "vssr_painn_relax_edge_stats")
+        d, m, df, c, e6 = (int(x) for x in out.cpu().tolist())
+        return {"direct_edges": d, "memo_edges": m, "direct_edges_frozen_receiver": df, "canonical_structures": c,
+                "skin_list_edges": e6, "atoms": A, "structures": batch.n_struct}
 
 
 RELAX_COLS = ("energy", "energy_std", "raw_energy", "max_abs_force", "nsteps", "converged", "energy_oob", "n_evals")
 
-POT_TERSOFF, POT_SW = 0, 1
+POT_TERSOFF, POT_SW, POT_EAM = 0, 1, 2
 
 
 def tersoff_param_table(pot_json: dict, elements: list[str]) -> np.ndarray:
@@ -410,8 +424,42 @@ def sw_param_table(eps=2.1683, sigma=2.0951, a=1.80, lam=21.0, gamma=1.20, costh
     return np.array([[eps, sigma, a, lam, gamma, costheta0, A, B, p, q]], dtype=np.float64)
 
 
+def _eam_spline(f: np.ndarray, delta: float) -> np.ndarray:
+    """The 7-coefficient cubic-spline table LAMMPS builds for every EAM function (PairEAM::interpolate; SURVEY.md
+    App. A.4): rows 1..n, row 0 unused.  Columns 6..3 = value and cubic coefficients in the reduced coordinate,
+    columns 2..0 = the derivative polynomial (already divided by the grid spacing)."""
+    n = len(f)
+    c = np.zeros((n + 1, 7))
+    c[1:, 6] = f
+    c[1, 5] = c[2, 6] - c[1, 6]
+    c[2, 5] = 0.5 * (c[3, 6] - c[1, 6])
+    c[n - 1, 5] = 0.5 * (c[n, 6] - c[n - 2, 6])
+    c[n, 5] = c[n, 6] - c[n - 1, 6]
+    k = np.arange(3, n - 1)
+    c[k, 5] = ((c[k - 2, 6] - c[k + 2, 6]) + 8.0 * (c[k + 1, 6] - c[k - 1, 6])) / 12.0
+    k = np.arange(1, n)
+    rise = c[k + 1, 6] - c[k, 6]
+    c[k, 4] = 3.0 * rise - 2.0 * c[k, 5] - c[k + 1, 5]
+    c[k, 3] = c[k, 5] + c[k + 1, 5] - 2.0 * rise
+    c[1:, 2] = c[1:, 5] / delta
+    c[1:, 1] = 2.0 * c[1:, 4] / delta
+    c[1:, 0] = 3.0 * c[1:, 3] / delta
+    return c
+
+
+def eam_param_block(funcfl: dict) -> np.ndarray:
+    """Parameter block of VSSR_POT_EAM (include/vssr_b200.h) from a parsed single-element funcfl file
+    (loaders.load_eam_funcfl): header + spline tables of F(rho), rho(r) and z2r(r) = 27.2*0.529*Z(r)^2 = r*phi(r)."""
+    nrho, drho, nr, dr, rc = int(funcfl["nrho"]), float(funcfl["drho"]), int(funcfl["nr"]), float(funcfl["dr"]), float(funcfl["rc"])
+    zr = np.asarray(funcfl["zr"], dtype=np.float64)
+    tabs = [_eam_spline(np.asarray(funcfl["frho"], dtype=np.float64), drho),
+            _eam_spline(np.asarray(funcfl["rhor"], dtype=np.float64), dr),
+            _eam_spline(27.2 * 0.529 * zr * zr, dr)]
+    return np.concatenate([np.array([nrho, drho, nr, dr, rc, 0.0, 0.0, 0.0])] + [t.reshape(-1) for t in tabs])
+
+
 class ClassicalEngine:
-    """Tersoff / Stillinger-Weber energy, forces and FIRE relaxation, one CTA per chain."""
+    """Tersoff / Stillinger-Weber / EAM energy, forces and FIRE relaxation, one CTA per chain."""
 
     def __init__(self, kind: int, params: np.ndarray, ntypes: int, n_max: int = 128, max_nbr: int = 32,
                  skin: float = 0.5, device: str = "cuda"):

@@ -193,5 +193,18 @@ def load_slab_pickle(path):
     return a
 
 
+def load_eam_funcfl(path) -> dict:
+    """LAMMPS single-element `funcfl` EAM file (mcmc/potentials/{Cu,Au}_u3.eam):
+    line 2 = Z mass a0 lattice, line 3 = Nrho drho Nr dr rc, then F(rho)[Nrho], Z(r)[Nr], rho(r)[Nr]."""
+    lines = Path(path).read_text().splitlines()
+    head, grid = lines[1].split(), lines[2].split()
+    nrho, drho, nr, dr, rc = int(grid[0]), float(grid[1]), int(grid[2]), float(grid[3]), float(grid[4])
+    vals = np.array(" ".join(lines[3:]).split(), dtype=np.float64)
+    if vals.size != nrho + 2 * nr:
+        raise ValueError(f"{path}: expected {nrho + 2 * nr} table values, found {vals.size}")
+    return {"Z": int(head[0]), "mass": float(head[1]), "a0": float(head[2]), "nrho": nrho, "drho": drho, "nr": nr,
+            "dr": dr, "rc": rc, "frho": vals[:nrho], "zr": vals[nrho:nrho + nr], "rhor": vals[nrho + nr:]}
+
+
 def load_offset_data(path) -> dict:
     return json.loads(Path(path).read_text())

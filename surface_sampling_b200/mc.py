@@ -239,10 +239,13 @@ class MultiChainMC:
     """C independent chains in lock step over one batched engine.
 
     ``relax_fn(pos_list, num_list, fixed_list) -> out[C,8]`` is the hot-path call (engine relax);
-    ``surface_energy_fn(energy, symbols) -> float`` is the host scalar (H6/H7)."""
+    ``surface_energy_fn(energy, symbols) -> float`` is the host scalar (H6/H7) -- one callable for every chain, or a
+    list with one callable per chain (Pourbaix runs: every chain carries its own (pH, U) grid point, BASELINE
+    config 5 / scripts/sample_pourbaix_surface.py:253-259).  ``occ0`` / ``ads_group0`` start the chains from sampled
+    surface atoms (``sample_surface_atoms``, scripts/sample_pourbaix_surface.py:218-236)."""
 
     def __init__(self, numbers0, positions0, fixed0, ads_coords, adsorbates, relax_fn, surface_energy_fn, seeds,
-                 canonical=False, num_ads_atoms=0, occ0=None, energy_memo=False):
+                 canonical=False, num_ads_atoms=0, occ0=None, energy_memo=False, ads_group0=None):
         # energy_memo (SURVEY 8f-2, off by default and never used by bench.py): the relaxed result is a pure
         # function of the unrelaxed structure, and the engine is batch-invariant, so identical structures -- across
         # chains in one step or revisited later -- are relaxed once and their 8 scalars reused bit for bit
@@ -251,7 +254,12 @@ class MultiChainMC:
         self.adsorbates = list(adsorbates)
         self.relax_fn, self.surface_energy_fn = relax_fn, surface_energy_fn
         self.fixed0 = np.asarray(fixed0, dtype=bool)
-        self.chains = [ChainState(numbers0, positions0, ads_coords, occ=occ0, seed=s) for s in seeds]
+        self.chains = [ChainState(numbers0, positions0, ads_coords, occ=occ0, seed=s, ads_group0=ads_group0) for s in seeds]
+        self._se_per_chain = isinstance(surface_energy_fn, (list, tuple))
+        if self._se_per_chain:
+            assert len(surface_energy_fn) == len(self.chains), "one surface_energy_fn per chain"
+        for k, c in enumerate(self.chains):
+            c.index = k
         self.canonical, self.num_ads_atoms = canonical, num_ads_atoms
         if canonical:
             assert num_ads_atoms > 0, "for canonical runs, need number of adsorbed atoms greater than 0"
@@ -269,11 +277,12 @@ class MultiChainMC:
             pos.append(p)
             num.append(z)
             fix.append(np.concatenate([self.fixed0, np.zeros(len(z) - len(self.fixed0), dtype=bool)]))
+        fns = [self.surface_energy_fn[c.index] for c in chains] if self._se_per_chain else None
         if self.energy_memo is not None:
-            return self._launch_memo(pos, num, fix), num
+            return self._launch_memo(pos, num, fix), num, fns
         handle = self.relax_fn(pos, num, fix)
         self.n_relaxed += len(chains)
-        return handle, num
+        return handle, num, fns
 
     def _launch_memo(self, pos, num, fix):
         keys = [(z.tobytes(), p.tobytes()) for p, z in zip(pos, num)]
@@ -298,10 +307,12 @@ class MultiChainMC:
         return Joined()
 
     def _collect(self, launched):
-        handle, num = launched
+        handle, num, fns = launched
         out = handle.result() if hasattr(handle, "result") else handle
         # the OOB clamp of optimize_slab is invisible to Metropolis (system.py:466-469): raw energy is used
-        return [self.surface_energy_fn(float(out[k, 2]), _SYMBOLS_ARR[num[k]].tolist()) for k in range(len(num))]
+        if fns is None:
+            return [self.surface_energy_fn(float(out[k, 2]), _SYMBOLS_ARR[num[k]].tolist()) for k in range(len(num))]
+        return [fns[k](float(out[k, 2]), _SYMBOLS_ARR[num[k]].tolist()) for k in range(len(num))]
 
     def _energies(self, chains):
         return self._collect(self._launch(chains))
@@ -380,6 +391,8 @@ class MultiChainMC:
 
     def load_state_dict(self, sd: dict):
         self.chains = [ChainState.fromdict(d) for d in sd["chains"]]
+        for k, c in enumerate(self.chains):
+            c.index = k
         self.temp, self.n_relaxed = sd["temp"], sd["n_relaxed"]
         self.decisions = [list(d) for d in sd["decisions"]]
 

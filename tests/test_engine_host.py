@@ -27,15 +27,20 @@ def test_pack_painn_weights_tf32_split_is_exact_to_22_bits():
     assert np.all(err <= np.abs(exact.astype(np.float64)) * 2.0 ** -21 + 1e-45)
 
 
-def test_result_buffer_ring_rotates_and_grows():
+def test_relax_outputs_are_caller_owned_or_fresh():
+    """relax() results are never recycled behind the caller's back (round 1 used a 16-deep ring): fresh tensors per
+    call, or the caller's own buffers after validation."""
+    import pytest
+    from surface_sampling_b200 import _lib
     eng = engine.PainnEngine.__new__(engine.PainnEngine)
     eng.device = torch.device("cpu")
-    first = eng._result_buffers(4, 100)
-    assert first[0].shape == (4, 8) and first[1].shape == (100, 3) and first[2].shape == (100, 3)
-    seen = {first[0].data_ptr()}
-    for _ in range(engine.PainnEngine.RESULT_RING - 1):
-        seen.add(eng._result_buffers(4, 100)[0].data_ptr())
-    assert len(seen) == engine.PainnEngine.RESULT_RING            # distinct sets until the ring wraps
-    assert eng._result_buffers(4, 100)[0].data_ptr() == first[0].data_ptr()
-    big = eng._result_buffers(40, 5000)                           # a larger batch re-allocates that set only
-    assert big[0].shape == (40, 8) and big[1].shape == (5000, 3)
+    a, b = eng._result_buffers(4, 100, None), eng._result_buffers(4, 100, None)
+    assert a[0].shape == (4, 8) and a[1].shape == (100, 3) and a[3].dtype == torch.int32
+    assert a[0].data_ptr() != b[0].data_ptr() and a[1].data_ptr() != b[1].data_ptr()
+    mine = {"out": torch.empty((4, 8), dtype=torch.float64), "forces": torch.empty((100, 3)),
+            "forces_std": torch.empty((100, 3)), "status": torch.zeros(1, dtype=torch.int32)}
+    got = eng._result_buffers(4, 100, mine)
+    assert got[0] is mine["out"] and got[3] is mine["status"]
+    mine["forces"] = torch.empty((99, 3))
+    with pytest.raises(_lib.VssrError):
+        eng._result_buffers(4, 100, mine)

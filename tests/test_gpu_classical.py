@@ -123,3 +123,80 @@ def test_host_buffer_entry_matches_device_entry(structures, potentials):
     assert rc == 0 and status[0] == 0
     assert np.array_equal(out, ref)
     assert np.array_equal(pos, b.pos.cpu().numpy())
+
+
+def _eam(el):
+    from surface_sampling_b200 import engine
+    from oracle.eam import EAMFuncfl
+    from conftest import GOLDEN
+    z = np.load(GOLDEN / "eam_funcfl.npz")
+    tab = {k.split("/")[1]: z[k] for k in z.files if k.startswith(el + "/")}
+    return engine.ClassicalEngine(engine.POT_EAM, engine.eam_param_block(tab), 1, n_max=32, max_nbr=128), EAMFuncfl(tab), tab
+
+
+def test_eam_au_golden_and_oracle(structures, golden_values):
+    """BASELINE config 1 family (LAMMPSRunSurfCalc, `pair_style eam`): the 28 canonical Au(110) states of the reference's
+    tests/test_Au.py in ONE batch through the CUDA kernel: min = -79.03490823689619 (tests/test_Au.py:19), and every
+    state's energy / forces / per-atom energies vs the oracle."""
+    import itertools
+    eng, au, _ = _eam("Au")
+    slab = structures["Au_110_2x2"]
+    ads = structures["Au_110_2x2_proper_adsorbed"]["positions"][16:24]
+    structs = [{"positions": np.concatenate([slab["positions"], ads[list(keep)]]), "cell": slab["cell"], "pbc": slab["pbc"]}
+               for keep in itertools.combinations(range(8), 6)]
+    rng = np.random.default_rng(3)
+    structs.append({**structs[0], "positions": structs[0]["positions"] + rng.normal(0, 0.1, structs[0]["positions"].shape)})
+    b = _batch(structs, [np.zeros(len(s["positions"]), np.int32) for s in structs])
+    r = eng.energy_forces(b)
+    e = r["energy"].cpu().numpy()
+    f = b.split_host(r["forces"].cpu().numpy())
+    eat = b.split_host(r["per_atom_energies"].cpu().numpy())
+    assert abs(e[:28].min() - golden_values["eam_au"]["energy"]) < 1e-5      # CIF adatoms carry 5 decimals
+    for k, s in enumerate(structs):
+        e0, f0 = au.energy_forces(s["positions"], s["cell"], s["pbc"])
+        assert abs(e[k] - e0) < 1e-9 * abs(e0), (k, e[k], e0)
+        assert np.abs(f[k] - f0).max() < 1e-8, (k, np.abs(f[k] - f0).max())
+        assert abs(eat[k].sum() - e[k]) < 1e-10
+    assert np.abs(f[28]).max() > 0.1                                          # the perturbed state has real forces
+
+
+def test_eam_cu_calculator_and_toy_mc(golden_values):
+    """BASELINE config 1: Cu(100) toy VSSR-MC through the reference-named calculator.  tests/test_Cu.py:19 asserts
+    min(energy_hist) = -25.2893, which is the slab + one bridge Cu; the product calculator reproduces it, and a short
+    unrelaxed MC run over {ontop, bridge} sites makes the oracle loop's decisions."""
+    from test_oracle_golden import cu100_slab
+    from oracle import mc as omc
+    from surface_sampling_b200 import mc
+    from surface_sampling_b200.atoms import Atoms
+    from surface_sampling_b200.calculators import LAMMPSRunSurfCalc
+    eng, cu, tab = _eam("Cu")
+    g = golden_values["eam_cu"]
+    pos, cell, pbc = cu100_slab(g["a"])
+    d, zt = g["a"] / np.sqrt(2), pos[:, 2].max() + g["planar_distance"]
+    calc = LAMMPSRunSurfCalc(funcfl=tab, keep_tmp_files=False, keep_alive=False)
+    assert set(calc.set(pair_style="eam", pair_coeff=["* * Cu_u3.eam"])) == {"pair_style", "pair_coeff"}
+    slab = Atoms(numbers=[29] * 8, positions=pos, cell=cell, pbc=pbc, calculator=calc)
+    ads = slab.copy(); ads.append("Cu", [0.5 * d, 0.0, zt]); ads.calc = calc
+    e = calc.get_property("surface_energy", atoms=ads)
+    assert np.allclose(e, g["energy"]) and abs(e - g["energy"]) < 1e-4
+    assert calc.get_potential_energy(atoms=slab) != e and calc.results["forces"].shape == (8, 3)   # cache follows the structure
+    assert abs(calc.results["energies"].sum() - calc.results["energy"]) < 1e-10
+    sites = np.array([[0, 0, zt], [d, 0, zt], [0, d, zt], [d, d, zt],
+                      [0.5 * d, 0, zt], [1.5 * d, 0, zt], [0, 0.5 * d, zt], [0, 1.5 * d, zt]])
+
+    def relax_fn(pos_l, num_l, fix_l):      # LAMMPSRunSurfCalc runs unrelaxed: energy only
+        from surface_sampling_b200 import engine
+        b = engine.Batch.from_arrays(pos_l, [np.zeros(len(z), np.int32) for z in num_l], [cell] * len(pos_l), [pbc] * len(pos_l))
+        out = np.zeros((len(pos_l), 8))
+        out[:, 2] = out[:, 0] = eng.energy_forces(b)["energy"].cpu().numpy()
+        return out
+
+    seeds = [0, 1, 2, 3]
+    drv = mc.MultiChainMC([29] * 8, pos, np.ones(8, bool), sites, ["Cu"], relax_fn, lambda e_, sym: e_, seeds)
+    res = drv.run(total_sweeps=10, sweep_size=2, start_temp=1.0, perform_annealing=True, alpha=0.99)   # tests/test_Cu.py:53-61
+    for k, sd in enumerate(seeds):
+        o = omc.run_chain(sd, ["Cu"] * 8, pos, sites, ["Cu"], lambda sym, p: cu.energy_forces(p, cell, pbc)[0], 10, 2,
+                          start_temp=1.0, alpha=0.99)
+        assert [x[0] for x in drv.decisions[k]] == [x[0] for x in o["decisions"]]
+        assert np.allclose([x[1] for x in drv.decisions[k]], [x[1] for x in o["decisions"]], rtol=1e-10, atol=1e-9)
+        assert np.allclose(res["energy_hist"][k], o["energy_hist"], rtol=1e-10, atol=1e-9)

@@ -32,12 +32,15 @@ def _compare(eng, ens, structs):
     for k, s in enumerate(structs):
         o = ens.calculate(s["positions"], s["numbers"], s["cell"], PBC3)
         n = len(s["numbers"])
-        etol = E_TOL_PER_ATOM * n + 1e-6 * abs(o["energy"][0])
+        # north-star tolerance with NO slack for physical structures; only overlapping trial placements (|dE/dx| > 50
+        # eV/A: per-atom energies of 1e3..1e5 eV whose fp32 ulp alone exceeds 1e-5 eV) get fp32-resolution head room
+        fscale = np.abs(o["grads_per_model"]).max()
+        etol = E_TOL_PER_ATOM * n + (2e-7 * np.abs(o["energies_per_model"]).max() if fscale > 50 else 0.0)
         assert abs(e[k] - o["energy"][0]) <= etol, (k, e[k], o["energy"][0])
         assert abs(es[k] - o["energy_std"][0]) <= etol
         # 1e-4 eV/A absolute; fp32 cannot hold that on the >1e3 eV/A forces of overlapping trial
         # placements, so allow 2 ulp-ish relative slack there
-        ftol = F_TOL + 2e-6 * np.abs(o["grads_per_model"]).max()   # scale of the structure's largest force
+        ftol = F_TOL + (2e-6 * fscale if fscale > 50 else 0.0)     # scale of the structure's largest force
         assert (np.abs(f[k] - o["forces"]) <= ftol).all(), (k, np.abs(f[k] - o["forces"]).max())
         assert (np.abs(fs[k] - o["forces_std"]) <= ftol).all()
     return e, f
@@ -263,7 +266,7 @@ def test_relax_retries_on_edge_capacity_overflow(structures, potentials, sto_wei
     s = structures["SrTiO3_001_2x2"]
     fixed = orelax.fixed_mask_from_surface_depth(s["positions"], s["cell"], 1)
     b0, b1, b2 = (_batch([s, s], [fixed, fixed]) for _ in range(3))
-    out0 = eng.relax(b0, relax_steps=5)["out"].clone()            # result buffers are a ring: keep a copy
+    out0 = eng.relax(b0, relax_steps=5)["out"]
     r1 = eng.relax(b1, relax_steps=5, e_cap=1000)                 # 2 x 3448 edges needed
     assert int(r1["status"].item()) & 1
     r2 = eng.relax(b2, relax_steps=5, e_cap=1000, check=True)

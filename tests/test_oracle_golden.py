@@ -126,6 +126,9 @@ def test_pourbaix_formula_product_vs_oracle():
             got = -(calc.get_delta_G1(atoms, slab_energy=e_slab) + calc.get_delta_G2(atoms))
             ref = pourbaix_potential(symbols, e_slab, table, phi, pH, 0.0257, corr)
             assert abs(got - ref) < 1e-10, (symbols, phi, pH, got, ref)
+            # the batched driver's scalar (one chain per (pH, phi) grid point) is the same function
+            assert calc.surface_energy_fn(phi, pH)(e_slab, symbols) == pytest.approx(ref, abs=1e-10)
+            assert calc.surface_energy_fn()(e_slab, symbols) == pytest.approx(got, abs=1e-12)
 
 
 @pytest.mark.parametrize("name", ["O44Sr12Ti16", "O36Sr12Ti12", "O40Sr16Ti12"])
@@ -176,3 +179,30 @@ def test_bfgs_logs_of_the_reference_slabs(structures, potentials, golden_values,
     assert np.allclose([q[1] for q in plog], [l[1] for l in log], atol=2e-5)       # fp32 energies, different eigh sizes
     assert o2[0, 4] == out["nsteps"] and o2[0, 5] == 1.0 and abs(o2[0, 2] - out["raw_energy"]) < 2e-5
     assert np.abs(b.pos.numpy() - out["pos"]).max() < 1e-5
+
+
+def cu100_slab(a=3.6147, vacuum=15.0):
+    """catkit.build.surface(bulk('Cu','fcc',a), size=(2,2,2), miller=(1,0,0), termination=0, vacuum=15) rebuilt
+    geometrically (tests/test_Cu.py:29-38; site coordinates logged in tutorials/example.ipynb cell 7: top layer at
+    z = 16.807, ontop sites (0,0) (2.556,0) (0,2.556) (2.556,2.556) at z = 18.307)."""
+    d, h = a / np.sqrt(2), a / 2
+    bottom = [[(i + 0.5) * d, (j + 0.5) * d, vacuum] for i in range(2) for j in range(2)]
+    top = [[i * d, j * d, vacuum + h] for i in range(2) for j in range(2)]
+    return np.array(bottom + top), np.diag([2 * d, 2 * d, 2 * vacuum + h]), np.array([True, True, False])
+
+
+def test_eam_cu_golden(golden_values):
+    """tests/test_Cu.py:19: min(energy_hist) = -25.2893 is the slab with one Cu on a bridge site."""
+    from pathlib import Path
+    from oracle.eam import EAMFuncfl
+    z = np.load(Path(__file__).resolve().parent / "golden" / "eam_funcfl.npz")
+    cu = EAMFuncfl({k.split("/")[1]: z[k] for k in z.files if k.startswith("Cu/")})
+    g = golden_values["eam_cu"]
+    pos, cell, pbc = cu100_slab(g["a"])
+    d = g["a"] / np.sqrt(2)
+    bridge = np.array([0.5 * d, 0.0, pos[:, 2].max() + g["planar_distance"]])
+    e, _ = cu.energy_forces(np.vstack([pos, bridge]), cell, pbc)
+    assert np.allclose(e, g["energy"])          # the reference's own assertion
+    assert abs(e - g["energy"]) < 1e-4
+    ontop = np.array([0.0, 0.0, pos[:, 2].max() + g["planar_distance"]])
+    assert cu.energy_forces(np.vstack([pos, ontop]), cell, pbc)[0] > e      # ontop at 1.5 A is repulsive
