@@ -129,3 +129,76 @@ def test_accept_reject_parity_tersoff(structures, potentials):
         assert list(drv.chains[k].occ) == o["final"].occ
         # no decision sat inside the energy-tolerance band of its uniform draw
         assert all(abs(np.exp(-(c - p) / 0.5) - u) > 1e-6 or c <= p for _, c, p, u in o["decisions"])
+
+
+POURBAIX_TABLE = {   # Sr / O / H: literals of the reference's tests/pourbaix/test_pourbaix_atoms.py:44-86; Ti synthetic
+    "Sr": dict(E_std=-1.68949, dG2_std=-5.79807, n_e=2, n_H=0, conc=1e-6),
+    "Ti": dict(E_std=-7.8955, dG2_std=-9.20, n_e=4, n_H=4, conc=1.0),
+    "O": dict(E_std=-5.26469, dG2_std=-2.45830, n_e=-2, n_H=-2, conc=1.0),
+    "H": dict(E_std=-4.0356, dG2_std=0.0, n_e=1, n_H=1, conc=1.0),
+}
+
+
+def test_nff_pourbaix_calculator_on_gpu(structures, sto_weights):
+    """H7 through the product calculator on the GPU: NFFPourbaix(models[0]).calculate -> results['surface_energy'] ==
+    results['pourbaix_potential'] == oracle formula on the oracle's single-model energy (scripts/
+    sample_pourbaix_surface.py:253-259, calculators.py:197-361), for a slab carrying an HO group (adsorbate correction +
+    excess-H rule), at several (phi, pH)."""
+    from oracle.pourbaix import pourbaix_potential
+    from surface_sampling_b200.atoms import Atoms
+    from surface_sampling_b200.calculators import NFFPourbaix, PourbaixAtom
+    s = structures["SrTiO3_001_2x2"]
+    ztop = s["positions"][:, 2].max()
+    ads_pos = np.array([[1.0, 1.0, ztop + 1.6], [2.0, 1.0, ztop + 1.6], [5.0, 4.0, ztop + 1.7]])
+    numbers = np.concatenate([s["numbers"], [8, 1, 38]])
+    pos = np.vstack([s["positions"], ads_pos])
+    atoms = Atoms(numbers=numbers, positions=pos, cell=s["cell"], pbc=True)
+    patoms = {k: PourbaixAtom(k, species_conc=v["conc"], num_e=v["n_e"], num_H=v["n_H"], atom_std_state_energy=v["E_std"],
+                              delta_G2_std=v["dG2_std"]) for k, v in POURBAIX_TABLE.items()}
+    calc = NFFPourbaix(sto_weights[0], device="cuda", model_units="kcal/mol", prediction_units="eV")
+    assert len(calc.models) == 1
+    ens1 = EnsembleOracle(sto_weights[:1], None, dtype=torch.float64)
+    e_ref = ens1.calculate(pos, numbers, s["cell"], [True] * 3)["energy"][0]
+    symbols = atoms.get_chemical_symbols()
+    for phi, pH in ((1.0, 12.0), (0.0, 0.0), (-0.5, 7.0)):
+        changed = calc.set(temperature=0.0257, phi=phi, pH=pH, pourbaix_atoms=patoms, adsorbate_corrections={"HO": 0.23})
+        assert "phi" in changed or "pH" in changed or "temperature" in changed
+        atoms.calc = calc
+        calc.calculate(atoms)
+        r = calc.results
+        ref = pourbaix_potential(symbols, e_ref, POURBAIX_TABLE, phi, pH, 0.0257, {"HO": 0.23})
+        assert abs(float(r["energy"][0]) - e_ref) < 1e-5 * len(numbers)
+        assert r["surface_energy"] == r["pourbaix_potential"]
+        assert abs(r["surface_energy"] - ref) < 1e-5 * len(numbers), (phi, pH, r["surface_energy"], ref)
+        assert abs(calc.get_property("surface_energy", atoms=atoms) - r["surface_energy"]) == 0.0       # cached
+        # the batched driver's scalar is the same function of (energy, symbols)
+        assert abs(calc.surface_energy_fn()(float(r["energy"][0]), symbols) - r["surface_energy"]) < 1e-9
+
+
+def test_embedding_values_vs_oracle(structures, potentials, sto_weights):
+    """`embedding` = final scalar features s^(3) (what get_embeddings_single feeds the latent-space
+    clustering), compared VALUE BY VALUE with the oracle's return_features, per model and ensemble mean."""
+    from oracle.painn import PainnOracle
+    from surface_sampling_b200 import engine
+    from surface_sampling_b200.atoms import Atoms
+    from surface_sampling_b200.calculators import EnsembleNFFSurface, get_embeddings_single
+    s = structures["SrTiO3_001_2x2"]
+    eng = engine.PainnEngine(sto_weights, potentials["offset_data"])
+    b = engine.Batch.from_arrays([s["positions"], s["positions"] + 0.01], [s["numbers"]] * 2, [s["cell"]] * 2, [[True] * 3] * 2)
+    emb = eng.energy_forces(b, want_embedding=True)["embedding"].cpu().numpy()        # [M, A, 128]
+    assert emb.shape == (3, 120, 128)
+    ens = EnsembleOracle(sto_weights, None, dtype=torch.float64)
+    i, j, S, off = ens.build_nbrs(s["positions"], s["cell"], [True] * 3)
+    feats = []
+    for m, st in enumerate(sto_weights):
+        o = PainnOracle(st, dtype=torch.float64)
+        _, f, _ = o.forward_energy(torch.tensor(s["positions"]), torch.tensor(s["numbers"]).long(), torch.tensor(i).long(),
+                                   torch.tensor(j).long(), torch.tensor(off), return_features=True)
+        feats.append(f.numpy())
+        scale = np.abs(feats[-1]).max()
+        assert np.abs(emb[m, :60] - feats[-1]).max() < 2e-5 * max(scale, 1.0), (m, np.abs(emb[m, :60] - feats[-1]).max(), scale)
+    calc = EnsembleNFFSurface(sto_weights, offset_data=potentials["offset_data"])
+    atoms = Atoms(numbers=s["numbers"], positions=s["positions"], cell=s["cell"], pbc=True)
+    e = get_embeddings_single(atoms, calc)                  # mean over models, then over atoms -> [128]
+    ref = np.mean(feats, axis=0).mean(axis=0)
+    assert e.shape == (128,) and np.abs(e - ref).max() < 2e-5 * max(np.abs(ref).max(), 1.0)
