@@ -207,6 +207,37 @@ class ChainState:
         return np.concatenate([self._pos0, tail]), np.concatenate([self._num0, np.array(self.numbers[n0:], dtype=np.int64)])
 
 
+def all_distances_mic(positions, cell, pbc) -> np.ndarray:
+    """ase ``Atoms.get_all_distances(mic=True)``: minimum-image distance matrix (general cell: the 27 neighbouring
+    images of the wrapped difference are searched along the periodic directions)."""
+    pos = np.asarray(positions, dtype=float)
+    cell = np.asarray(cell, dtype=float).reshape(3, 3)
+    pbc = np.broadcast_to(np.asarray(pbc, dtype=bool), (3,))
+    d = pos[None, :, :] - pos[:, None, :]
+    if not pbc.any() or abs(np.linalg.det(cell)) < 1e-12:
+        return np.linalg.norm(d, axis=-1)
+    frac = d @ np.linalg.inv(cell)
+    frac[..., pbc] -= np.round(frac[..., pbc])
+    d = frac @ cell
+    rng = [(-1, 0, 1) if p else (0,) for p in pbc]
+    best = np.full(d.shape[:2], np.inf)
+    for i in rng[0]:
+        for j in rng[1]:
+            for k in rng[2]:
+                best = np.minimum(best, np.linalg.norm(d + np.array([i, j, k], float) @ cell, axis=-1))
+    return best
+
+
+def filter_distances(symbols, positions, cell, pbc, ads=("O",), cutoff_distance: float = 1.5) -> bool:
+    """mcmc/utils/misc.py:118-135: True iff no two atoms of the `ads` species are closer than `cutoff_distance`
+    (minimum image).  Pinned by the reference's tests/test_filter_distance.py:40-97 (tests/test_mc_state.py)."""
+    sel = np.isin(np.asarray(symbols, dtype=object), list(ads))
+    if sel.sum() < 2:
+        return True
+    dist = np.triu(all_distances_mic(np.asarray(positions, float)[sel], cell, pbc))
+    return not np.any((dist > 0) & (dist <= cutoff_distance))
+
+
 def create_anneal_schedule(start_temp=1.0, total_sweeps=1000, alpha=0.99):
     """mcmc/utils/sampling.py:10-71 (single-anneal branch)."""
     temps = [start_temp]
@@ -245,7 +276,15 @@ class MultiChainMC:
     surface atoms (``sample_surface_atoms``, scripts/sample_pourbaix_surface.py:218-236)."""
 
     def __init__(self, numbers0, positions0, fixed0, ads_coords, adsorbates, relax_fn, surface_energy_fn, seeds,
-                 canonical=False, num_ads_atoms=0, occ0=None, energy_memo=False, ads_group0=None):
+                 canonical=False, num_ads_atoms=0, occ0=None, energy_memo=False, ads_group0=None, filter_distance=0.0,
+                 filter_adsorbate_types=("Sr", "Ti"), cell=None, pbc=True):
+        # filter_distance > 0 (mcmc/mcmc.py:218-219,253-254): the DistanceCriterion REPLACES Metropolis -- a move is
+        # accepted iff no two atoms of `filter_adsorbate_types` (criterion.py:93-97 default) end up closer than that
+        # distance; no relaxation, no uniform draw; the sweep-end energy is evaluated as usual
+        self.filter_distance, self.filter_adsorbate_types = float(filter_distance), tuple(filter_adsorbate_types)
+        self.cell, self.pbc = cell, pbc
+        if self.filter_distance > 0:
+            assert cell is not None, "filter_distance needs the cell (minimum-image distances)"
         # energy_memo (SURVEY 8f-2, off by default and never used by bench.py): the relaxed result is a pure
         # function of the unrelaxed structure, and the engine is batch-invariant, so identical structures -- across
         # chains in one step or revisited later -- are relaxed once and their 8 scalars reused bit for bit
@@ -330,6 +369,8 @@ class MultiChainMC:
         another (run_pipelined)."""
         idx = list(range(len(self.chains))) if active is None else list(active)
         chains = [self.chains[i] for i in idx]
+        if self.filter_distance > 0:
+            return self._step_distance(idx, chains, force_semigrand)
         snaps, actions = [], []
         for k, c in enumerate(chains):
             semigrand = (not self.canonical) or (force_semigrand is not None and force_semigrand[k])
@@ -343,8 +384,27 @@ class MultiChainMC:
             c.apply(a)
         return idx, chains, snaps, prev, self._launch(chains), self.temp
 
+    def _step_distance(self, idx, chains, force_semigrand):
+        accepts = []
+        for k, c in enumerate(chains):
+            semigrand = (not self.canonical) or (force_semigrand is not None and force_semigrand[k])
+            action = c.propose_change(self.adsorbates) if semigrand else c.propose_switch()
+            snap = c.snapshot()
+            c.apply(action)
+            p, z = c.arrays()
+            acc = filter_distances(_SYMBOLS_ARR[z], p, self.cell, self.pbc, self.filter_adsorbate_types, self.filter_distance)
+            if acc:
+                c.results.pop("surface_energy", None)      # the state changed without an energy: recomputed when needed
+            else:
+                c.restore(snap)
+            self.decisions[idx[k]].append((acc, None, None, None))
+            accepts.append(acc)
+        return ("done", accepts)
+
     def step_end(self, ticket):
         """Second half: read the relaxed energies back and apply Metropolis. Returns accept flags."""
+        if ticket[0] == "done":
+            return ticket[1]
         idx, chains, snaps, prev, launched, temp = ticket
         curr = self._collect(launched)
         accepts = []
@@ -397,11 +457,16 @@ class MultiChainMC:
         self.decisions = [list(d) for d in sd["decisions"]]
 
     def run(self, total_sweeps=10, sweep_size=20, start_temp=1.0, perform_annealing=True, alpha=0.99,
-            anneal_schedule=None, gather=None, starting_iteration=0, history=False):
+            anneal_schedule=None, gather=None, starting_iteration=0, history=False, save_folder=None, save_chains=(0,),
+            relax_detail_fn=None):
         """MCMC.run (mcmc.py:301-390) for every chain; returns per-chain histories
         (energy_hist, frac_accept_hist, adsorption_count_hist) as [C, total_sweeps] arrays.
         `starting_iteration` resumes a run (mcmc.py:313,381) after load_state_dict; `history=True` also returns
-        the per-sweep chain snapshots (`results["history"]`, scripts/sample_surface.py:204-208) as todict()s."""
+        the per-sweep chain snapshots (`results["history"]`, scripts/sample_surface.py:204-208) as todict()s.
+        `save_folder`: after every sweep the chains in `save_chains` are dumped like SurfaceSystem.save_structures
+        (mcmc/system.py:488-534, called from mcmc.py:289): unrelaxed CIF, and -- when `relax_detail_fn(pos_list, num_list,
+        fix_list) -> (out[C,8], relaxed_positions_list)` is given -- the relaxed CIF (one extra batched relaxation per
+        sweep, as the reference spends <= 2 extra evaluations per sweep there)."""
         self.temp = start_temp
         if self.canonical and starting_iteration == 0:
             self.prepare_canonical()
@@ -427,12 +492,35 @@ class MultiChainMC:
             ads_count[:, i] = [c.num_adsorbates for c in self.chains]
             if history:
                 snapshots.append([c.todict() for c in self.chains])
+            if save_folder is not None:
+                self.save_structures(save_folder, i + 1, save_chains, relax_detail_fn)
             if gather is not None:
                 gather(i, energy_hist[:, i], frac_accept[:, i], ads_count[:, i])
         out = {"energy_hist": energy_hist, "frac_accept_hist": frac_accept, "adsorption_count_hist": ads_count}
         if history:
             out["history"] = snapshots
         return out
+
+
+    def save_structures(self, save_folder, sweep_num, chains=(0,), relax_detail_fn=None):
+        """Per-sweep dumps of the selected chains (io.save_structures). Returns the written paths."""
+        from pathlib import Path
+
+        from . import io
+        sel = [self.chains[k] for k in chains]
+        arrs = [c.arrays() for c in sel]
+        fix = [np.concatenate([self.fixed0, np.zeros(len(z) - len(self.fixed0), dtype=bool)]) for _, z in arrs]
+        relaxed, oob = [None] * len(sel), [False] * len(sel)
+        if relax_detail_fn is not None:
+            out, relaxed = relax_detail_fn([p for p, _ in arrs], [z for _, z in arrs], fix)
+            oob = [bool(out[k, 6]) for k in range(len(sel))]
+        written = []
+        for k, c in enumerate(sel):
+            folder = Path(save_folder) if len(self.chains) == 1 else Path(save_folder) / f"chain_{chains[k]:04d}"
+            written += io.save_structures(folder, sweep_num, c.results["surface_energy"], arrs[k][1], arrs[k][0], self.cell,
+                                          relaxed_pos=relaxed[k], energy_oob=oob[k],
+                                          pbc=np.broadcast_to(np.asarray(self.pbc, dtype=bool), (3,)))
+        return written
 
 
 class _Pipeline:

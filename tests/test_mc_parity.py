@@ -150,3 +150,33 @@ def test_energy_memo_changes_nothing_but_the_number_of_relaxations():
     for a, b in zip(drv.chains, ref.chains):
         assert np.array_equal(a.occ, b.occ)
     assert drv.memo_hits > 0 and drv.n_relaxed + drv.memo_hits == ref.n_relaxed
+
+
+def test_per_sweep_structure_dumps(tmp_path):
+    """SurfaceSystem.save_structures (mcmc/system.py:488-534) -- reference file names; the CIFs read back
+    (with the fixture generator's CIF reader) to the dumped coordinates at 5 decimals of the fractional coordinates."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    from make_fixtures import load_cif
+    drv, (sym0, pos0, sites) = _driver([4])
+    drv.cell, drv.pbc = np.diag([6.0, 6.0, 12.0]), True
+
+    def detail(pos_l, num_l, fix_l):
+        out = np.zeros((len(pos_l), 8))
+        return out, [p + 0.01 for p in pos_l]
+
+    res = drv.run(total_sweeps=2, sweep_size=3, start_temp=0.5, save_folder=tmp_path, save_chains=(0,), relax_detail_fn=detail)
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert len(files) == 4 and all(f.startswith("inb_") and f.endswith(".cif") for f in files)
+    e1 = res["energy_hist"][0, 0]
+    un = [f for f in files if f.startswith("inb_unrelaxed_slab_sweep_001_energy_%.3f_" % e1)]
+    assert len(un) == 1
+    back = load_cif(tmp_path / files[-1])                       # unrelaxed, sweep 2 = the final MC state
+    p, z = drv.chains[0].arrays()
+    assert np.array_equal(back["numbers"], z) and np.abs(back["positions"] - p).max() < 12.0 * 1e-5
+    rel = load_cif(tmp_path / [f for f in files if "relaxed_slab_sweep_002" in f and "unrelaxed" not in f][0])
+    assert np.abs(rel["positions"] - (p + 0.01)).max() < 12.0 * 1e-5
+    from surface_sampling_b200 import io
+    out = io.write_traj(tmp_path / "t.traj", [(z, p, -1.0), (z, p + 0.1, -1.5)], drv.cell)
+    txt = open(out).read().splitlines()
+    assert txt[0] == str(len(z)) and "energy=-1.00000000" in txt[1] and len(txt) == 2 * (len(z) + 2)

@@ -93,3 +93,62 @@ def test_anneal_schedule_and_sites(structures):
     g = make_site_grid(s["positions"], s["cell"], 64, 1.5)
     assert g.shape == (64, 3) and np.allclose(g[:, 2], s["positions"][:, 2].max() + 1.5)
     assert len({tuple(np.round(x, 6)) for x in g}) == 64
+
+
+# ---- filter_distances / DistanceCriterion: the reference's tests/test_filter_distance.py:40-97, same vectors ----
+def _sto_2x2x1(structures):
+    u = structures["SrTiO3_unit_cell"]
+    cell = u["cell"].copy()
+    pos, num = [], []
+    for i in range(2):
+        for j in range(2):
+            pos.append(u["positions"] + i * cell[0] + j * cell[1])
+            num.append(u["numbers"])
+    cell[0] *= 2; cell[1] *= 2
+    return np.concatenate(pos), np.concatenate(num), cell, u["pbc"]
+
+
+@pytest.mark.parametrize("ads_pos,expected", [
+    ([[1.96777, 1.99250, 18.59954]], False),                                   # one O at a bridge site: too close
+    ([[5.90331, 0.14832, 19.49200]], True),                                    # one O on top
+    ([[1.96777, 1.99250, 18.59954], [5.90331, 0.14832, 19.49200]], False),     # bridge + top
+    ([[5.90331, 0.14832, 19.49200], [1.96777, 4.13332, 19.49200]], True),      # two tops
+])
+def test_filter_distances_reference_vectors(structures, ads_pos, expected):
+    from surface_sampling_b200.mc import filter_distances
+    pos, num, cell, pbc = _sto_2x2x1(structures)
+    sym = [SYMBOLS[int(z)] for z in num] + ["O"] * len(ads_pos)
+    assert filter_distances(sym, np.vstack([pos, ads_pos]), cell, pbc, ads=["O"], cutoff_distance=1.5) is expected
+
+
+def test_filter_distances_across_the_cell_boundary(structures):
+    """tests/test_filter_distance.py:88-97: two O atoms closer than 1.5 A only through the periodic image."""
+    from surface_sampling_b200.mc import filter_distances
+    s = structures["SrTiO3_001_distance_failed"]
+    sym = [SYMBOLS[int(z)] for z in s["numbers"]]
+    assert not filter_distances(sym, s["positions"], s["cell"], s["pbc"], ads=["O"], cutoff_distance=1.5)
+    assert filter_distances(sym, s["positions"], s["cell"], [False] * 3, ads=["Sr"], cutoff_distance=1.5)
+
+
+def test_distance_criterion_replaces_metropolis():
+    """mcmc/mcmc.py:253-254: with filter_distance > 0 a move is accepted iff the filtered species keep their distance;
+    nothing is relaxed and no uniform is drawn."""
+    from surface_sampling_b200.mc import MultiChainMC
+    calls = []
+
+    def relax_fn(p, z, f):
+        calls.append(len(p))
+        return np.zeros((len(p), 8))
+
+    sites = np.array([[0.0, 0, 2], [1.0, 0, 2], [4.0, 4, 2]])
+    drv = MultiChainMC([NUMBERS["Ga"]] * 2, [[0, 0, 0], [4, 4, 0]], [True, True], sites, ["Sr"], relax_fn, lambda e, s: e, [0, 1],
+                       filter_distance=1.5, filter_adsorbate_types=("Sr",), cell=np.eye(3) * 10, pbc=[True, True, False])
+    for _ in range(12):
+        acc = drv.step()
+        for c, a in zip(drv.chains, acc):
+            occ = np.flatnonzero(c.occ)
+            assert not (0 in occ and 1 in occ)            # sites 0 and 1 are 1.0 A apart: never both filled with Sr
+    assert calls == []                                    # no relaxation inside the criterion
+    assert any(d[0] for ch in drv.decisions for d in ch) and any(not d[0] for ch in drv.decisions for d in ch)
+    drv._ensure_prev(drv.chains)                          # sweep-end energy: evaluated on demand
+    assert calls == [2]
