@@ -461,17 +461,17 @@ class LAMMPSSurfCalc(LAMMMPSCalc):
     implemented_properties = (*LAMMMPSCalc.implemented_properties, "surface_energy")
 
     def get_surface_energy(self, atoms=None) -> float:
-        """calculators.py:712-727: the potential energy of `atoms`, always evaluated on `atoms` itself."""
-        atoms = self.atoms if atoms is None else atoms
-        _, e, _ = self.run_lammps_energy(atoms, run_dir=self.run_dir)
-        return e
+        """calculators.py:712-727: currently the same as the potential energy (served from the cache when `atoms` is
+        the structure the cached results belong to, like ASE's get_potential_energy)."""
+        return self.get_potential_energy(atoms=self.atoms if atoms is None else atoms)
 
     def calculate(self, atoms=None, properties=implemented_properties, system_changes=ALL_CHANGES):
         atoms = self.atoms if atoms is None else atoms
         LAMMMPSCalc.calculate(self, atoms, properties, system_changes)
         if "surface_energy" in properties:
-            self.results["surface_energy"] = (self.results["energy"] if "energy" in self.results
-                                              else self.get_surface_energy(atoms=atoms))
+            if "energy" not in self.results:       # results of ANOTHER structure were dropped by Calculator.calculate
+                LAMMMPSCalc.calculate(self, atoms, ("energy",), system_changes)
+            self.results["surface_energy"] = self.results["energy"]
 
 
 class LAMMPSRunSurfCalc(Calculator):

@@ -240,7 +240,6 @@ constexpr int REC = 96, REC_EJ = 4, REC_RE = 8, REC_DRE = 52;
 constexpr int MREC = 8;   // memoised-edge record: (ux,uy,uz,d), sender, slot, 1/d, pad
 // compact direct-edge record for the k-block kernels (256 B): [0..3] (u,d) [4] sender [6] key [7] 1/d
 // [8..27] rbf_n*env [28] env [29] denv [32..51] d(rbf_n*env)/dd   (scalars: FFMA2 broadcasts an .F32 operand)
-constexpr int CREC = 64, CREC_RE = 8, CREC_DRE = 32;
 
 // Radial-filter memo ("frozen-pair cache").  The filter w(d) = Wd.(rbf(d)*env(d)) + bd*env(d) and its
 // derivative q(d) depend on the edge only through the scalar d.  In VSSR-MC every chain shares the same
@@ -272,7 +271,7 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
     int n_atoms, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const int8_t* __restrict__ shift, long long e_cap, float cutoff, FilterCacheView fc,
     int32_t* __restrict__ nvalid, float* __restrict__ erec, int32_t* __restrict__ nmemo, float* __restrict__ mrec,
-    float* __restrict__ evex, float* __restrict__ grad0, float* __restrict__ crec) {
+    float* __restrict__ evex, float* __restrict__ grad0) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n_atoms) return;
@@ -354,12 +353,6 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
         }
         float2* rrow = reinterpret_cast<float2*>(rec + REC_RE);
         float2* drow = reinterpret_cast<float2*>(rec + REC_DRE);
-        float* cr = crec ? crec + w * CREC : nullptr;
-        if (cr) {
-          *reinterpret_cast<float4*>(cr) = make_float4(ux, uy, uz, d);
-          *reinterpret_cast<float4*>(cr + 4) = make_float4(__int_as_float(j), __int_as_float(-1), __int_as_float(key), inv_d);
-          cr[CREC_RE + 20] = env; cr[CREC_RE + 21] = denv;
-        }
 #pragma unroll
         for (int n = 0; n < NRBF; ++n) {
           float r = 0.f, dr = 0.f;
@@ -373,7 +366,6 @@ __global__ void __launch_bounds__(128) edge_geometry_kernel(
           const float a = r * env, bq = dr * env + r * denv;
           rrow[n] = make_float2(a, a);
           drow[n] = make_float2(bq, bq);
-          if (cr) { cr[CREC_RE + n] = a; cr[CREC_DRE + n] = bq; }
         }
         rrow[20] = make_float2(env, env);
         rrow[21] = make_float2(denv, denv);
@@ -727,22 +719,6 @@ __global__ void __launch_bounds__(128) message_bwd_kernel(
 
 #include "painn_message.cuh"
 
-// launch helpers of the k-block kernels: opt in to the dynamic shared memory once per size, profile, check
-template <int KB, bool FIRST, int T, typename... Args>
-int kb_launch_fwd(size_t smem, dim3 grid, cudaStream_t st, Args... args) {
-  static size_t cfg = 0;
-  if (smem > cfg) { VSSR_CUDA(cudaFuncSetAttribute(msg_fwd_kb<KB, FIRST, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = smem; }
-  VSSR_PROF(VSSR_K_MSG_FWD, st, (msg_fwd_kb<KB, FIRST, T><<<grid, T, smem, st>>>(args...)));
-  return VSSR_OK;
-}
-template <int KB, bool FIRST, int T, typename... Args>
-int kb_launch_bwd(size_t smem, dim3 grid, cudaStream_t st, Args... args) {
-  static size_t cfg = 0;
-  if (smem > cfg) { VSSR_CUDA(cudaFuncSetAttribute(msg_bwd_kb<KB, FIRST, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = smem; }
-  VSSR_PROF(VSSR_K_MSG_BWD, st, (msg_bwd_kb<KB, FIRST, T><<<grid, T, smem, st>>>(args...)));
-  return VSSR_OK;
-}
-
 // ---- filter memo construction (one-time per framework + weights) ----
 struct CacheBlob {
   int32_t* rowptr; int32_t* nvalid; int32_t* key; int32_t* slot; float* d; float* wc; float* qc; int32_t* counter;
@@ -832,7 +808,7 @@ __global__ void __launch_bounds__(128) cache_fill_kernel(const float* __restrict
 
 struct Workspace {
   // edge records (compacted per row by edge_geometry_kernel)
-  int32_t* nvalid; float* erec; float* crec; int32_t* nmemo; float* mrec; float* evex; float* grad0; float* gradp;
+  int32_t* nvalid; float* erec; int32_t* nmemo; float* mrec; float* evex; float* grad0; float* gradp;
   int32_t* order_d; int32_t* order_m;   // per-structure row order, most direct / memoised edges first
   int32_t* canonical;                   // [A] (first n_struct used): structure carries exactly the framework's memo lists
   // activations
@@ -857,7 +833,6 @@ Workspace carve(void* base, int M, int A, long long e_cap) {
   const size_t MA = (size_t)M * (size_t)A;
   w.nvalid = reinterpret_cast<int32_t*>(take(A));
   w.erec = take((size_t)e_cap * REC);
-  w.crec = take((size_t)e_cap * CREC);
   w.nmemo = reinterpret_cast<int32_t*>(take(A));
   w.order_d = reinterpret_cast<int32_t*>(take(A));
   w.order_m = reinterpret_cast<int32_t*>(take(A));
@@ -907,47 +882,43 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const dim3 ew_grid(ceil_div((long long)A * F, 256), M);
   const dim3 msg_grid(ceil_div(A, MSG_APB), M);
 
-  // message kernels: shared-memory staged FFMA2 path when every structure fits, else global-gather path
+  // message kernels: shared-memory staged FFMA2 kernels.  A CTA of the direct pass stages at most cap_* atoms; larger
+  // structures are covered by several launches over "sender windows" (painn_message.cuh: sender_window), so there is
+  // no atom-count cliff any more.  The global-gather kernels only serve callers that do not know max_atoms_per_struct.
   const int nmax = max_atoms_per_struct;
   const FilterCacheView fc = cache_view(filter_cache, n_models, fc_n0, fc_e_cap0);
-  // staged rows of one structure (memo pass) + the per-warp record rings (direct pass)
-  const size_t st_fwd0 = (size_t)nmax * MsgFwdLayout<true>::PER * 4, st_fwd = (size_t)nmax * MsgFwdLayout<false>::PER * 4;
-  const size_t st_bwd0 = (size_t)nmax * MsgBwdLayout<true>::PER * 4, st_bwd = (size_t)nmax * MsgBwdLayout<false>::PER * 4;
-  const size_t smem_fwd0 = st_fwd0 + MSG_PIPE_BYTES_FWD, smem_fwd = st_fwd + MSG_PIPE_BYTES_FWD;
-  const size_t smem_bwd0 = st_bwd0 + MSG_PIPE_BYTES, smem_bwd = st_bwd + MSG_PIPE_BYTES;
-  const bool staged = nmax > 0 && smem_bwd <= 227 * 1024;
-  // full-gradient memo backward: staged rows + a 3-stage (w,q) ring per warp
+  const bool staged = nmax > 0;
+  const size_t kSmemCap = 226 * 1024;   // 227 KB per SM minus the kernels' few bytes of static shared memory
+  // direct pass: staged rows of one window + the per-warp record rings.  The first-layer forward runs two CTAs per SM.
+  constexpr int B_FWD0 = MsgFwdLayout<true>::PER * 4, B_FWD = MsgFwdLayout<false>::PER * 4;
+  constexpr int B_BWD0 = MsgBwdLayout<true>::PER * 4, B_BWD = MsgBwdLayout<false>::PER * 4;
+  const int cap_fwd0 = (int)((kSmemCap / 2 - 1024 - MSG_PIPE_BYTES_FWD) / B_FWD0), cap_fwd = (int)((kSmemCap - MSG_PIPE_BYTES_FWD) / B_FWD);
+  const int cap_bwd0 = (int)((kSmemCap - MSG_PIPE_BYTES) / B_BWD0), cap_bwd = (int)((kSmemCap - MSG_PIPE_BYTES) / B_BWD);
+  auto rows_of = [&](int cap) { return nmax < cap ? nmax : cap; };
+  auto windows_of = [&](int cap) { return (nmax + cap - 1) / cap; };
+  const size_t smem_fwd0 = (size_t)rows_of(cap_fwd0) * B_FWD0 + MSG_PIPE_BYTES_FWD, smem_fwd = (size_t)rows_of(cap_fwd) * B_FWD + MSG_PIPE_BYTES_FWD;
+  const size_t smem_bwd0 = (size_t)rows_of(cap_bwd0) * B_BWD0 + MSG_PIPE_BYTES, smem_bwd = (size_t)rows_of(cap_bwd) * B_BWD + MSG_PIPE_BYTES;
+  // memo pass: only framework rows (the first n0 atoms) are ever gathered, whatever the structure carries on top
+  const int nrows_memo = fc.n0 > 0 ? (nmax < fc.n0 ? nmax : fc.n0) : 0;
   const size_t memo6_ring = (size_t)(MEMO_THREADS_BWD / 32) * MEMO6_STAGES * MEMO6_STAGE_FLOATS * 4;
-  const size_t sm_bwdm0 = st_bwd0 + memo6_ring, sm_bwdm = st_bwd + memo6_ring;
+  const size_t sm_bwdm0 = (size_t)nrows_memo * B_BWD0 + memo6_ring, sm_bwdm = (size_t)nrows_memo * B_BWD + memo6_ring;
+  const size_t memo_ring = (size_t)(MEMO_THREADS_FWD / 32) * MEMO_RING_BYTES_PER_WARP;
+  const size_t sm_fwd0 = (size_t)nrows_memo * B_FWD0 + memo_ring, sm_fwd = (size_t)nrows_memo * B_FWD + memo_ring;
+  const size_t sm_state = (size_t)nrows_memo * MEMO_STATE_PER * 4 + memo_ring;
   const bool want_constrained = (fc_flags & VSSR_FC_CONSTRAINED_GRAD) != 0;
-  // two passes: memoised edges (light kernels), then direct edges; a full-gradient evaluation of structures too
-  // large for the (w,q) ring simply runs without the memo
-  const bool memo = staged && fc.n0 > 0 && (want_constrained || sm_bwdm <= 227 * 1024);
+  // two passes: memoised edges (light kernels), then direct edges; a framework too large for the staging area simply
+  // runs without the memo
+  const bool memo = staged && fc.n0 > 0 && sm_bwdm <= kSmemCap && sm_fwd <= kSmemCap;
   const bool constrained = memo && want_constrained;   // no dE/dx wanted on frozen atoms
-  // direct edges: optional variant with one kernel per filter block (k-block kernels, VSSR_MSG_KB=1).  OFF by
-  // default: parity-green and 16 warps/SM instead of 8, but measured slower than the fused kernels (fwd 22.1 ->
-  // 24.6 ms, bwd 31.6 -> 34.6-38.1 ms): the per-edge ring / shuffle / address overhead is paid three times and
-  // outweighs the occupancy gain (profiles/r2_notes.md section 5).
-  static int kb_env = -1;
-  if (kb_env < 0) { const char* e = getenv("VSSR_MSG_KB"); kb_env = e ? atoi(e) : 0; }
-  constexpr int KB_T = 256, KB_T0 = 512;   // threads: blocks 1, 2 (two CTAs per SM) / block 0 of the backward (one CTA)
-  const bool kb_on = staged && kb_env != 0;
-  auto kb_smem = [&](int per, int threads) { return (size_t)nmax * per * 4 + (size_t)kb_ring_floats(threads) * 4; };
-  static int n_chunks_env = -1;
-  if (n_chunks_env < 0) { const char* e = getenv("VSSR_MSG_CHUNKS"); n_chunks_env = e ? atoi(e) : 2; if (n_chunks_env < 1) n_chunks_env = 2; }
-  const int n_chunks = n_chunks_env;   // CTAs per (structure, feature half, model) in the direct pass
+  constexpr int n_chunks = 2;   // CTAs per (structure, feature half, model) in the direct pass
   const dim3 v2_grid(n_struct * n_chunks, F / MSG_FC, M);
   const dim3 memo_grid(n_struct, F / MSG_FC, M);
-  const size_t memo_ring = (size_t)(MEMO_THREADS_FWD / 32) * MEMO_RING_BYTES_PER_WARP;
-  const size_t sm_fwd0 = st_fwd0 + memo_ring, sm_fwd = st_fwd + memo_ring;
-  const size_t sm_state = (size_t)nmax * MEMO_STATE_PER * 4 + memo_ring;
   // group kernels: G canonical structures per CTA (as many as fit in shared memory), no ring
   constexpr int G_FWD0 = 4, T_FWD0 = 512, G_FWD = 2, T_FWD = 832, G_STATE = 2, T_STATE = 512;
   const bool group_on = memo && !(fc_flags & VSSR_FC_NO_PAIR);
   // a group is taken when its structures are canonical AND the FRAMEWORK rows of G structures (n0 atoms each -- the only
   // rows a memoised edge can touch) fit the 227 KB of an SM: independent of how many adsorbates the chains carry
-  const size_t kSmemCap = 226 * 1024;   // 227 KB per SM minus the kernels' few bytes of static shared memory
-  const size_t sp_fwd0 = (size_t)G_FWD0 * fc.n0 * MsgFwdLayout<true>::PER * 4, sp_fwd = (size_t)G_FWD * fc.n0 * MsgFwdLayout<false>::PER * 4,
+  const size_t sp_fwd0 = (size_t)G_FWD0 * fc.n0 * B_FWD0, sp_fwd = (size_t)G_FWD * fc.n0 * B_FWD,
                sp_state = (size_t)G_STATE * fc.n0 * MEMO_STATE_PER * 4;
   const int ga_fwd0 = sp_fwd0 <= kSmemCap ? G_FWD0 * fc.n0 : 0, ga_fwd = sp_fwd <= kSmemCap ? G_FWD * fc.n0 : 0,
             ga_state = sp_state <= kSmemCap ? G_STATE * fc.n0 : 0;
@@ -955,7 +926,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const bool pair_fwd = group_on && n_struct >= G_FWD && ga_fwd > 0;
   const bool pair_state = group_on && constrained && n_struct >= G_STATE && ga_state > 0;
   if (staged) {
-    static size_t cfg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: cache what was configured per device
+    static size_t cfg_dev[64][12] = {};
+    int dev = 0;
+    VSSR_CUDA(cudaGetDevice(&dev));
+    size_t* cfg = cfg_dev[dev & 63];
     auto want = [&](int k, const void* fn, size_t bytes) -> int {
       if (bytes > cfg[k]) {
         VSSR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -971,10 +946,8 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if (memo) {
       if ((rc0 = want(4, (const void*)message_fwd_memo<true>, sm_fwd0))) return rc0;
       if ((rc0 = want(5, (const void*)message_fwd_memo<false>, sm_fwd))) return rc0;
-      if (!constrained) {
-        if ((rc0 = want(6, (const void*)message_bwd_memo<true>, sm_bwdm0))) return rc0;
-        if ((rc0 = want(7, (const void*)message_bwd_memo<false>, sm_bwdm))) return rc0;
-      }
+      if ((rc0 = want(6, (const void*)message_bwd_memo<true>, sm_bwdm0))) return rc0;
+      if ((rc0 = want(7, (const void*)message_bwd_memo<false>, sm_bwdm))) return rc0;
       if ((rc0 = want(8, (const void*)message_bwd_memo_state, sm_state))) return rc0;
       if (pair_fwd0 && (rc0 = want(9, (const void*)message_fwd_memo_group<true, G_FWD0, T_FWD0>, sp_fwd0))) return rc0;
       if (pair_fwd && (rc0 = want(10, (const void*)message_fwd_memo_group<false, G_FWD, T_FWD>, sp_fwd))) return rc0;
@@ -984,7 +957,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
 
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(A, 4), 128, 0, st>>>(
       pos, atom_ptr, cell, n_struct, A, rowptr, col, shift, (long long)e_cap, cutoff, memo ? fc : FilterCacheView{},
-      w.nvalid, w.erec, w.nmemo, w.mrec, w.evex, w.grad0, kb_on ? w.crec : nullptr));
+      w.nvalid, w.erec, w.nmemo, w.mrec, w.evex, w.grad0));
   if (staged)
     VSSR_PROF(VSSR_K_GEOM, st, row_order_kernel<<<n_struct, 128, (size_t)2 * nmax * sizeof(int32_t), st>>>(
         atom_ptr, w.nvalid, w.nmemo, w.order_d, w.order_m, memo ? fc.n0 : 0, fc.nmemo0, w.canonical));
@@ -1002,7 +975,8 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     g = GemmArgs{w.act, F, MA_F, wl + L_W2T, F3, W_STRIDE, wl + L_B2, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.phi[l], F3, (long long)A * F3, A, F3, F};
     if ((rc = run_gemm<128, 0, 1>(g, wl + L_W2T, F3, wl + L_W2, M, st))) return rc;
-    // F3
+    // F3: memo pass (group kernels for canonical structures, one-structure kernels for the rest), then the direct pass
+    // over 1..W sender windows (accumulating in window order)
     if (staged) {
       if (l == 0) {
         if (pair_fwd0)
@@ -1012,15 +986,10 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<true><<<memo_grid, MEMO_THREADS_FWD, sm_fwd0, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l],
               pair_fwd0 ? w.canonical : nullptr, n_struct, G_FWD0, ga_fwd0));
-        if (kb_on) {
-          if ((rc = kb_launch_fwd<1, true, KB_T>(kb_smem(kb_fwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
-                                                 w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
-          if ((rc = kb_launch_fwd<2, true, KB_T>(kb_smem(kb_fwd_per(2), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
-                                                 w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
-        } else
-        VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
-            w.cat[l], w.vmid[l], memo ? 1 : 0));
+        for (int win = 0; win < windows_of(cap_fwd0); ++win)
+          VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
+              weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
+              w.cat[l], w.vmid[l], memo ? 1 : 0, cap_fwd0, win));
       } else {
         if (pair_fwd)
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo_group<false, G_FWD, T_FWD><<<dim3(n_struct / G_FWD, F / MSG_FC, M), T_FWD, sp_fwd, st>>>(
@@ -1029,17 +998,10 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<false><<<memo_grid, MEMO_THREADS_FWD, sm_fwd, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l],
               pair_fwd ? w.canonical : nullptr, n_struct, G_FWD, ga_fwd));
-        if (kb_on) {
-          if ((rc = kb_launch_fwd<1, false, KB_T>(kb_smem(kb_fwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
-                                                  w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
-          if ((rc = kb_launch_fwd<2, false, KB_T>(kb_smem(kb_fwd_per(2), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
-                                                  w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
-          if ((rc = kb_launch_fwd<0, false, KB_T>(kb_smem(kb_fwd_per(0), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr,
-                                                  w.order_d, w.nvalid, w.crec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l], memo ? 1 : 0))) return rc;
-        } else
-        VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
-            w.cat[l], w.vmid[l], memo ? 1 : 0));
+        for (int win = 0; win < windows_of(cap_fwd); ++win)
+          VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
+              weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
+              w.cat[l], w.vmid[l], memo ? 1 : 0, cap_fwd, win));
       }
     } else {
       if (l == 0)
@@ -1111,22 +1073,16 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if ((rc = run_gemm<128, 0, 3>(g, wl + L_UV, F, wl + L_UVT, M, st))) return rc;
     // B3
     if (staged) {
-      // accum bit 0: dphi/dv_in were started by a memo pass; bit 1: so was gradp
+      // accum bit 0: dphi/dv_in were started by a memo pass; bit 1: so was gradp (later sender windows set both)
       if (l == 0) {
         if (memo && !constrained)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<true><<<memo_grid, MEMO_THREADS_BWD, sm_bwdm0, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp));
-        if (kb_on) {
-          const int acc = (memo && !constrained) ? 1 : 0;   // the full-gradient memo pass started state and gradp
-          const uint8_t* fz = constrained ? fc.frozen : nullptr;
-          if ((rc = kb_launch_bwd<1, true, KB_T>(kb_smem(kb_bwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
-                                                 w.nvalid, w.crec, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp, acc, acc, fz, fc.n0))) return rc;
-          if ((rc = kb_launch_bwd<2, true, KB_T>(kb_smem(kb_bwd_per(2), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
-                                                 w.nvalid, w.crec, w.phi[l], nullptr, w.ds, dv_cur, nullptr, nullptr, w.gradp, acc, 1, fz, fc.n0))) return rc;
-        } else
-        VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
-            dv_cur, nullptr, nullptr, w.gradp, (memo && !constrained) ? 3 : 0, constrained ? fc.frozen : nullptr, fc.n0));
+        for (int win = 0; win < windows_of(cap_bwd0); ++win)
+          VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<true><<<v2_grid, MSG_THREADS, smem_bwd0, st>>>(
+              weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], nullptr, w.ds,
+              dv_cur, nullptr, nullptr, w.gradp, (memo && !constrained) ? 3 : 0, constrained ? fc.frozen : nullptr, fc.n0,
+              cap_bwd0, win));
       } else {
         if (pair_state)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo_state_group<G_STATE, T_STATE><<<dim3(n_struct / G_STATE, F / MSG_FC, M), T_STATE, sp_state, st>>>(
@@ -1138,20 +1094,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
         else if (memo)
           VSSR_PROF(VSSR_K_MSG_BWD_MEMO, st, message_bwd_memo<false><<<memo_grid, MEMO_THREADS_BWD, sm_bwdm, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp));
-        if (kb_on) {
-          const int acc = memo ? 1 : 0;                        // a memo pass started the state outputs
-          const int gacc = (memo && !constrained) ? 1 : 0;     // ... and gradp only in full-gradient mode
-          const uint8_t* fz = constrained ? fc.frozen : nullptr;
-          if ((rc = kb_launch_bwd<1, false, KB_T>(kb_smem(kb_bwd_per(1), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
-                                                  w.nvalid, w.crec, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp, acc, gacc, fz, fc.n0))) return rc;
-          if ((rc = kb_launch_bwd<2, false, KB_T>(kb_smem(kb_bwd_per(2), KB_T), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
-                                                  w.nvalid, w.crec, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp, acc, 1, fz, fc.n0))) return rc;
-          if ((rc = kb_launch_bwd<0, false, KB_T0>(kb_smem(kb_bwd_per(0), KB_T0), v2_grid, st, weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d,
-                                                   w.nvalid, w.crec, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt, w.gradp, acc, 1, fz, fc.n0))) return rc;
-        } else
-        VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
-            weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
-            dv_cur, w.dphi, dv_nxt, w.gradp, constrained ? 1 : (memo ? 3 : 0), constrained ? fc.frozen : nullptr, fc.n0));
+        for (int win = 0; win < windows_of(cap_bwd); ++win)
+          VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_v2<false><<<v2_grid, MSG_THREADS, smem_bwd, st>>>(
+              weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds,
+              dv_cur, w.dphi, dv_nxt, w.gradp, constrained ? 1 : (memo ? 3 : 0), constrained ? fc.frozen : nullptr, fc.n0,
+              cap_bwd, win));
       }
       VSSR_PROF(VSSR_K_ELEMWISE, st, grad_accum_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.gradp, 3 * A, grad));
     } else {
@@ -1276,7 +1223,7 @@ extern "C" int vssr_painn_filter_cache_build(const float* weights, int32_t n_mod
   if (rc) return rc;
   VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(n0, 4), 128, 0, st>>>(
       pos0, atom_ptr, cell, 1, n0, c.rowptr, col, shift, (long long)e_cap0, cutoff, FilterCacheView{}, c.nvalid, erec, nmemo, mrec,
-      evex, grad0, nullptr));
+      evex, grad0));
   VSSR_PROF(VSSR_K_GEOM, st, cache_slot_kernel<<<1, 32, 0, st>>>(erec, c.rowptr, c.nvalid, fixed0, n0, c.key, c.slot, c.d, c.counter));
   VSSR_PROF(VSSR_K_GEOM, st, cache_fill_kernel<<<dim3((unsigned)e_cap0, n_models * NCONV), 128, 0, st>>>(
       weights, erec, c.slot, (int)e_cap0, c.wc, c.qc));
@@ -1285,7 +1232,7 @@ extern "C" int vssr_painn_filter_cache_build(const float* weights, int32_t n_mod
     const FilterCacheView self = cache_view(cache, n_models, n0, e_cap0);
     VSSR_PROF(VSSR_K_GEOM, st, edge_geometry_kernel<<<ceil_div(n0, 4), 128, 0, st>>>(
         pos0, atom_ptr, cell, 1, n0, c.rowptr, col, shift, (long long)e_cap0, cutoff, self, deg, erec, c.nmemo0, c.mrec0,
-        evex, grad0, nullptr));
+        evex, grad0));
     VSSR_PROF(VSSR_K_GEOM, st, row_order_kernel<<<1, 128, (size_t)2 * n0 * sizeof(int32_t), st>>>(
         atom_ptr, c.nmemo0, c.nmemo0, c.order0, nmemo, 0, nullptr, nullptr));
   }

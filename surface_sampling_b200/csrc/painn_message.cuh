@@ -76,6 +76,32 @@ __device__ __forceinline__ void wait_record() {
   __syncwarp();
 }
 
+// Sender windows.  A CTA of the direct pass stages the rows of at most `cap` atoms; a structure with n > cap atoms is
+// covered by W = ceil(n / cap) launches ("windows" of ceil(n / W) consecutive atoms): launch `win` handles, for every
+// receiver, exactly the edges whose SENDER lies in its window and accumulates onto the earlier launches.  Direct
+// records of a row are sorted by sender (CSR order survives the compaction), so a window is a contiguous slice of the
+// row, found by binary search.  W depends on the structure's own atom count only, never on the rest of the batch, and
+// windows are applied in ascending order: results stay bitwise batch-invariant.  n <= cap is the old single launch.
+struct SenderWindow { int lo, hi; bool live; };
+__device__ __forceinline__ SenderWindow sender_window(int n, int cap, int win) {
+  const int W = (n + cap - 1) / cap;
+  const int wsz = W > 0 ? (n + W - 1) / W : 0;
+  SenderWindow w;
+  w.live = win < W;
+  w.lo = win * wsz;
+  w.hi = min(n, w.lo + wsz);
+  return w;
+}
+// index of the first direct record of a row whose local sender index is >= L (warp-uniform)
+__device__ __forceinline__ int first_sender_at_least(const float* __restrict__ rec0, int ne, int a0, int L) {
+  int lo = 0, hi = ne;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__float_as_int(__ldg(rec0 + (long long)mid * REC + REC_EJ)) - a0 < L) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // Rows (receivers) are handed to warps dynamically, most expensive first (row_order_kernel sorts each
 // structure's rows by edge count): longest-processing-time-first scheduling.  A row is always computed
 // whole by one warp, so the result does not depend on which warp takes it.
@@ -262,9 +288,10 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
   cat += (mA + a0) * 2 * F;
   v_mid += (mA + a0) * 3 * F;
   if (!FIRST) v_in += (mA + a0) * 3 * F + h * MSG_FC;
-  float* ring = smem + (size_t)n * PER + warp * (MEMO_STAGES * MEMO_STAGE_FLOATS);
-  stage_rows(smem, PER, 0, phi, F3, F, 3, n, tid, MEMO_THREADS_FWD);
-  if (!FIRST) stage_rows(smem, PER, 3 * MSG_FC, v_in, 3 * F, F, 3, n, tid, MEMO_THREADS_FWD);
+  const int ns = min(n, fc.n0);   // memoised edges join framework atoms: only their rows are ever gathered
+  float* ring = smem + (size_t)ns * PER + warp * (MEMO_STAGES * MEMO_STAGE_FLOATS);
+  stage_rows(smem, PER, 0, phi, F3, F, 3, ns, tid, MEMO_THREADS_FWD);
+  if (!FIRST) stage_rows(smem, PER, 3 * MSG_FC, v_in, 3 * F, F, 3, ns, tid, MEMO_THREADS_FWD);
   const int f0 = h * MSG_FC + 2 * lane;
   const float* __restrict__ wbase = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC;
   stage_wait();
@@ -282,10 +309,15 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_fwd_memo(
     const float2 s0 = ld2(s_in + (long long)il * F + f0);
     *reinterpret_cast<float2*>(cat + (long long)il * 2 * F + f0) = __fadd2_rn(s0, ds);
     if (!FIRST) {
-      const float* si = smem + il * PER + 2 * lane;
-      dvx = __fadd2_rn(dvx, ld2(si + 3 * MSG_FC));
-      dvy = __fadd2_rn(dvy, ld2(si + 4 * MSG_FC));
-      dvz = __fadd2_rn(dvz, ld2(si + 5 * MSG_FC));
+      if (il < ns) {
+        const float* si = smem + il * PER + 2 * lane;
+        dvx = __fadd2_rn(dvx, ld2(si + 3 * MSG_FC));
+        dvy = __fadd2_rn(dvy, ld2(si + 4 * MSG_FC));
+        dvz = __fadd2_rn(dvz, ld2(si + 5 * MSG_FC));
+      } else {   // adsorbate row (not staged)
+        const float* vg = v_in + (long long)il * 3 * F + 2 * lane;
+        dvx = __fadd2_rn(dvx, ldg2(vg)); dvy = __fadd2_rn(dvy, ldg2(vg + F)); dvz = __fadd2_rn(dvz, ldg2(vg + 2 * F));
+      }
     }
     float* vo = v_mid + (long long)il * 3 * F + f0;
     *reinterpret_cast<float2*>(vo) = dvx;
@@ -302,7 +334,7 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order, const int32_t* __restrict__ nvalid,
     const float* __restrict__ erec,
     const float* __restrict__ phi, const float* __restrict__ s_in, const float* __restrict__ v_in,
-    float* __restrict__ cat, float* __restrict__ v_mid, int accum) {
+    float* __restrict__ cat, float* __restrict__ v_mid, int accum, int cap_atoms, int win) {
   extern __shared__ __align__(16) float smem_all[];
   __shared__ int row_ctr;
   if (threadIdx.x == 0) row_ctr = 0;
@@ -315,14 +347,19 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
   const int h = blockIdx.y, m = blockIdx.z;
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
   const long long mA = (long long)m * n_atoms;
+  const SenderWindow wn = sender_window(n, cap_atoms, win);
+  if (!wn.live) return;                          // this structure needs fewer windows than the largest of the batch
+  const bool whole = wn.lo == 0 && wn.hi == n;   // single window: the row's whole list
+  if (win > 0) accum = 1;
   phi += (mA + a0) * F3 + h * MSG_FC;
   s_in += (mA + a0) * F;
   cat += (mA + a0) * 2 * F;
   v_mid += (mA + a0) * 3 * F;
   if (!FIRST) v_in += (mA + a0) * 3 * F + h * MSG_FC;
 
-  stage_rows(smem, PER, 0, phi, F3, F, 3, n, tid, MSG_THREADS);
-  if (!FIRST) stage_rows(smem, PER, 3 * MSG_FC, v_in, 3 * F, F, 3, n, tid, MSG_THREADS);
+  stage_rows(smem, PER, 0, phi + (long long)wn.lo * F3, F3, F, 3, wn.hi - wn.lo, tid, MSG_THREADS);
+  if (!FIRST) stage_rows(smem, PER, 3 * MSG_FC, v_in + (long long)wn.lo * 3 * F, 3 * F, F, 3, wn.hi - wn.lo, tid, MSG_THREADS);
+  const int sbase = a0 + wn.lo;                  // global index of the first staged atom
 
   const int f0 = h * MSG_FC + 2 * lane;  // first feature of this lane's pair
   const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
@@ -341,8 +378,13 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
     const int il = __ldg(order + a0 + t);
     const int i = a0 + il;
     const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
-    const int ne = __ldg(nvalid + i);
-    if (accum && ne == 0) continue;   // nothing to add to the memo pass' result
+    int ne = __ldg(nvalid + i);
+    if (!whole) {                     // the slice of this row whose senders lie in the window
+      const int e_lo = first_sender_at_least(rec0, ne, a0, wn.lo), e_hi = first_sender_at_least(rec0, ne, a0, wn.hi);
+      rec0 += (long long)e_lo * REC;
+      ne = e_hi - e_lo;
+    }
+    if (accum && ne == 0) continue;   // nothing to add to the memo pass' / earlier windows' result
     float2 ds = dup2(0.f), dvx = dup2(0.f), dvy = dup2(0.f), dvz = dup2(0.f);
     // two edges per iteration: their filter evaluations (2 x 60 independent FFMA2 on the same weight registers)
     // and gathers interleave, which hides the shared-memory latencies that 8 warps per SM cannot
@@ -374,8 +416,8 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
         w2b = __ffma2_rn(wd2[2 * q + 1], b1r, w2b);
       }
       const int ja = __float_as_int(reca[REC_EJ]), jb = __float_as_int(recb[REC_EJ]);
-      fwd_edge<FIRST>(ga, smem + (ja - a0) * PER + 2 * lane, w0a, w1a, w2a, ds, dvx, dvy, dvz);
-      if (e + 1 < ne) fwd_edge<FIRST>(gb, smem + (jb - a0) * PER + 2 * lane, w0b, w1b, w2b, ds, dvx, dvy, dvz);
+      fwd_edge<FIRST>(ga, smem + (ja - sbase) * PER + 2 * lane, w0a, w1a, w2a, ds, dvx, dvy, dvz);
+      if (e + 1 < ne) fwd_edge<FIRST>(gb, smem + (jb - sbase) * PER + 2 * lane, w0b, w1b, w2b, ds, dvx, dvy, dvz);
       __syncwarp();   // both stages are free again
       prefetch_record(ring + (e % MSG_STAGES_FWD) * REC, rec0 + (long long)(e + MSG_STAGES_FWD) * REC, lane, N16,
                       e + MSG_STAGES_FWD < ne);
@@ -392,10 +434,15 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
     } else {
       *reinterpret_cast<float2*>(so) = __fadd2_rn(ld2(s_in + (long long)il * F + f0), ds);
       if (!FIRST) {
-        const float* si = smem + il * PER + 2 * lane;
-        dvx = __fadd2_rn(dvx, ld2(si + 3 * MSG_FC));
-        dvy = __fadd2_rn(dvy, ld2(si + 4 * MSG_FC));
-        dvz = __fadd2_rn(dvz, ld2(si + 5 * MSG_FC));
+        if (il >= wn.lo && il < wn.hi) {
+          const float* si = smem + (il - wn.lo) * PER + 2 * lane;
+          dvx = __fadd2_rn(dvx, ld2(si + 3 * MSG_FC));
+          dvy = __fadd2_rn(dvy, ld2(si + 4 * MSG_FC));
+          dvz = __fadd2_rn(dvz, ld2(si + 5 * MSG_FC));
+        } else {   // own row outside the staged window
+          const float* vg = v_in + (long long)il * 3 * F + 2 * lane;
+          dvx = __fadd2_rn(dvx, ldg2(vg)); dvy = __fadd2_rn(dvy, ldg2(vg + F)); dvz = __fadd2_rn(dvz, ldg2(vg + 2 * F));
+        }
       }
       *reinterpret_cast<float2*>(vo) = dvx;
       *reinterpret_cast<float2*>(vo + F) = dvy;
@@ -430,6 +477,24 @@ __device__ __forceinline__ void bwd_load_own(const float* __restrict__ si, BwdOw
   o.gvix = ld2(si + O::O_DV); o.gviy = ld2(si + O::O_DV + MSG_FC); o.gviz = ld2(si + O::O_DV + 2 * MSG_FC);
   o.vix = o.viy = o.viz = dup2(0.f);
   if (!FIRST) { o.vix = ld2(si + O::O_V); o.viy = ld2(si + O::O_V + MSG_FC); o.viz = ld2(si + O::O_V + 2 * MSG_FC); }
+}
+
+// the same values straight from global memory (own row outside the staged rows); pointers are the kernel's
+// structure- and half-offset bases (phi: stride F3, ds: F, dv / v_in: 3F per atom)
+template <bool FIRST>
+__device__ __forceinline__ void bwd_load_own_global(const float* __restrict__ phi, const float* __restrict__ v_in,
+                                                    const float* __restrict__ ds, const float* __restrict__ dv, int il, int lane,
+                                                    BwdOwn& o) {
+  const float* p = phi + (long long)il * F3 + 2 * lane;
+  o.pi0 = ldg2(p); o.pi1 = ldg2(p + F); o.pi2 = ldg2(p + 2 * F);
+  o.gsi = ldg2(ds + (long long)il * F + 2 * lane);
+  const float* g = dv + (long long)il * 3 * F + 2 * lane;
+  o.gvix = ldg2(g); o.gviy = ldg2(g + F); o.gviz = ldg2(g + 2 * F);
+  o.vix = o.viy = o.viz = dup2(0.f);
+  if (!FIRST) {
+    const float* v = v_in + (long long)il * 3 * F + 2 * lane;
+    o.vix = ldg2(v); o.viy = ldg2(v + F); o.viz = ldg2(v + 2 * F);
+  }
 }
 
 // shared per-edge backward math given the filter rows w_k and their d-derivative q_k
@@ -540,8 +605,9 @@ __global__ void __launch_bounds__(MEMO_THREADS_BWD, 1) message_bwd_memo(
     dphi += (mA + a0) * F3;
     dv_in += (mA + a0) * 3 * F;
   }
-  bwd_stage<FIRST>(smem, phi, v_in, ds, dv, n, tid, MEMO_THREADS_BWD);
-  float* ring = smem + (size_t)n * PER + warp * (MEMO6_STAGES * MEMO6_STAGE_FLOATS);
+  const int ns = min(n, fc.n0);   // memoised edges join framework atoms: only their rows are ever gathered
+  bwd_stage<FIRST>(smem, phi, v_in, ds, dv, ns, tid, MEMO_THREADS_BWD);
+  float* ring = smem + (size_t)ns * PER + warp * (MEMO6_STAGES * MEMO6_STAGE_FLOATS);
   const int f0 = h * MSG_FC + 2 * lane;
   const long long ml = (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC;
   const float* __restrict__ wbase = fc.wc + ml;
@@ -554,7 +620,8 @@ __global__ void __launch_bounds__(MEMO_THREADS_BWD, 1) message_bwd_memo(
     const float4* mr = reinterpret_cast<const float4*>(mrec + (long long)__ldg(rowptr + i) * MREC);
     const int ne = __ldg(nmemo + i);
     BwdOwn o;
-    bwd_load_own<FIRST>(smem + il * PER + 2 * lane, o);
+    if (il < ns) bwd_load_own<FIRST>(smem + il * PER + 2 * lane, o);
+    else bwd_load_own_global<FIRST>(phi, v_in, ds, dv, il, lane, o);
     BwdAcc a;
     a.dp0 = a.dp1 = a.dp2n = a.dvx = a.dvy = a.dvz = a.gnx = a.gny = a.gnz = dup2(0.f);
     memo_walk_ring6<!FIRST>(mr, ne, lane, wbase, qbase, ring, [&](const float4 g, int j, float inv_d, const float* r) {
@@ -594,9 +661,10 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_bwd_memo_state(
   dv += (mA + a0) * 3 * F + h * MSG_FC;
   dphi += (mA + a0) * F3 + f0;
   dv_in += (mA + a0) * 3 * F + f0;
-  float* ring = smem + (size_t)n * PER + warp * (MEMO_STAGES * MEMO_STAGE_FLOATS);
-  stage_rows(smem, PER, 0, ds, F, F, 1, n, tid, MEMO_THREADS_FWD);
-  stage_rows(smem, PER, MSG_FC, dv, 3 * F, F, 3, n, tid, MEMO_THREADS_FWD);
+  const int ns = min(n, fc.n0);
+  float* ring = smem + (size_t)ns * PER + warp * (MEMO_STAGES * MEMO_STAGE_FLOATS);
+  stage_rows(smem, PER, 0, ds, F, F, 1, ns, tid, MEMO_THREADS_FWD);
+  stage_rows(smem, PER, MSG_FC, dv, 3 * F, F, 3, ns, tid, MEMO_THREADS_FWD);
   const float* __restrict__ wbase = fc.wc + (long long)(m * NCONV + layer) * fc.nslots_cap * F3 + h * MSG_FC;
   stage_wait();
   __syncthreads();
@@ -622,15 +690,22 @@ __global__ void __launch_bounds__(MEMO_THREADS_FWD, 1) message_bwd_memo_state(
       const float2 tv = __fmul2_rn(pi0, w0);
       dvx = __ffma2_rn(tv, gvjx, dvx); dvy = __ffma2_rn(tv, gvjy, dvy); dvz = __ffma2_rn(tv, gvjz, dvz);
     });
-    const float* si = smem + il * PER + 2 * lane;
+    float2 ox, oy, oz;      // own dv row
+    if (il < ns) {
+      const float* si = smem + il * PER + 2 * lane;
+      ox = ld2(si + MSG_FC); oy = ld2(si + 2 * MSG_FC); oz = ld2(si + 3 * MSG_FC);
+    } else {
+      const float* dg = dv + (long long)il * 3 * F + 2 * lane;
+      ox = ldg2(dg); oy = ldg2(dg + F); oz = ldg2(dg + 2 * F);
+    }
     float* dpo = dphi + (long long)il * F3;
     float* dvo = dv_in + (long long)il * 3 * F;
     *reinterpret_cast<float2*>(dpo) = dp0;
     *reinterpret_cast<float2*>(dpo + F) = dp1;
     *reinterpret_cast<float2*>(dpo + 2 * F) = neg2(dp2n);
-    *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ld2(si + MSG_FC), dvx);
-    *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ld2(si + 2 * MSG_FC), dvy);
-    *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ld2(si + 3 * MSG_FC), dvz);
+    *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ox, dvx);
+    *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(oy, dvy);
+    *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(oz, dvz);
   }
 }
 
@@ -642,7 +717,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     const float* __restrict__ erec,
     const float* __restrict__ phi, const float* __restrict__ v_in, const float* __restrict__ ds,
     const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in, float* __restrict__ gradp,
-    int accum, const uint8_t* __restrict__ frozen, int n0) {
+    int accum, const uint8_t* __restrict__ frozen, int n0, int cap_atoms, int win) {
   extern __shared__ __align__(16) float smem_all[];
   __shared__ int row_ctr;
   if (threadIdx.x == 0) row_ctr = 0;
@@ -655,6 +730,10 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
   const int h = blockIdx.y, m = blockIdx.z;
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
   const long long mA = (long long)m * n_atoms;
+  const SenderWindow wn = sender_window(n, cap_atoms, win);
+  if (!wn.live) return;
+  const bool whole = wn.lo == 0 && wn.hi == n;
+  if (win > 0) accum = 3;                        // earlier windows started both the state outputs and gradp
   phi += (mA + a0) * F3 + h * MSG_FC;
   ds += (mA + a0) * F + h * MSG_FC;
   dv += (mA + a0) * 3 * F + h * MSG_FC;
@@ -663,7 +742,9 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     dphi += (mA + a0) * F3;
     dv_in += (mA + a0) * 3 * F;
   }
-  bwd_stage<FIRST>(smem, phi, v_in, ds, dv, n, tid, MSG_THREADS);
+  bwd_stage<FIRST>(smem, phi + (long long)wn.lo * F3, FIRST ? v_in : v_in + (long long)wn.lo * 3 * F, ds + (long long)wn.lo * F,
+                   dv + (long long)wn.lo * 3 * F, wn.hi - wn.lo, tid, MSG_THREADS);
+  const int sbase = a0 + wn.lo;
 
   const int f0 = h * MSG_FC + 2 * lane;
   const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
@@ -682,8 +763,14 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     const int il = __ldg(order + a0 + t);
     const int i = a0 + il;
     const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
-    const int ne = __ldg(nvalid + i);
-    if ((accum & 1) && ne == 0) {   // state already written by the memo pass; gradp may still need its zero
+    int ne = __ldg(nvalid + i);
+    if (!whole) {
+      const int e_lo = first_sender_at_least(rec0, ne, a0, wn.lo), e_hi = first_sender_at_least(rec0, ne, a0, wn.hi);
+      rec0 += (long long)e_lo * REC;
+      ne = e_hi - e_lo;
+    }
+    const bool own_staged = il >= wn.lo && il < wn.hi;
+    if ((accum & 1) && ne == 0) {   // state already written by the memo pass / earlier windows; gradp may still need its zero
       if (!(accum & 2) && lane == 0) {
         float* gp = gradp + (((long long)m * 2 + h) * n_atoms + i) * 3;
         gp[0] = 0.f; gp[1] = 0.f; gp[2] = 0.f;
@@ -700,8 +787,10 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
       if (FIRST) continue;
       using O = BwdOffsets<FIRST>;
       constexpr int N16L = (REC_RE + 44) / 4;   // geometry + rbf rows only
-      const float* si = smem + il * PER + 2 * lane;
-      const float2 pi0 = ld2(si), vix = ld2(si + O::O_V), viy = ld2(si + O::O_V + MSG_FC), viz = ld2(si + O::O_V + 2 * MSG_FC);
+      BwdOwn ow;
+      if (own_staged) bwd_load_own<FIRST>(smem + (il - wn.lo) * PER + 2 * lane, ow);
+      else bwd_load_own_global<FIRST>(phi, v_in, ds, dv, il, lane, ow);
+      const float2 pi0 = ow.pi0, vix = ow.vix, viy = ow.viy, viz = ow.viz;
       float2 dp0 = dup2(0.f), dp1 = dup2(0.f), dp2n = dup2(0.f), dvx = dup2(0.f), dvy = dup2(0.f), dvz = dup2(0.f);
       __syncwarp();
 #pragma unroll
@@ -724,7 +813,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
           w0 = __ffma2_rn(wd0[2 * q + 1], rb, w0); w1 = __ffma2_rn(wd1[2 * q + 1], rb, w1);
           w2 = __ffma2_rn(wd2[2 * q + 1], rb, w2);
         }
-        const float* sj = smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane;
+        const float* sj = smem + (__float_as_int(rec[REC_EJ]) - sbase) * PER + 2 * lane;
         const float2 gsj = ld2(sj + O::O_DS);
         const float2 gvjx = ld2(sj + O::O_DV), gvjy = ld2(sj + O::O_DV + MSG_FC), gvjz = ld2(sj + O::O_DV + 2 * MSG_FC);
         // same operation order as bwd_edge
@@ -749,14 +838,15 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
         *reinterpret_cast<float2*>(dpo) = dp0;
         *reinterpret_cast<float2*>(dpo + F) = dp1;
         *reinterpret_cast<float2*>(dpo + 2 * F) = neg2(dp2n);
-        *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ld2(si + O::O_DV), dvx);
-        *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ld2(si + O::O_DV + MSG_FC), dvy);
-        *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ld2(si + O::O_DV + 2 * MSG_FC), dvz);
+        *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ow.gvix, dvx);
+        *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ow.gviy, dvy);
+        *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ow.gviz, dvz);
       }
       continue;
     }
     BwdOwn o;
-    bwd_load_own<FIRST>(smem + il * PER + 2 * lane, o);
+    if (own_staged) bwd_load_own<FIRST>(smem + (il - wn.lo) * PER + 2 * lane, o);
+    else bwd_load_own_global<FIRST>(phi, v_in, ds, dv, il, lane, o);
     BwdAcc a;
     a.dp0 = a.dp1 = a.dp2n = a.dvx = a.dvy = a.dvz = a.gnx = a.gny = a.gnz = dup2(0.f);
     __syncwarp();
@@ -787,7 +877,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
         q0 = __ffma2_rn(wd0[2 * q + 1], db, q0); q1 = __ffma2_rn(wd1[2 * q + 1], db, q1);
         q2 = __ffma2_rn(wd2[2 * q + 1], db, q2);
       }
-      bwd_edge<FIRST>(g, rec[7], smem + (__float_as_int(rec[REC_EJ]) - a0) * PER + 2 * lane, o, w0, w1, w2, q0, q1, q2, a);
+      bwd_edge<FIRST>(g, rec[7], smem + (__float_as_int(rec[REC_EJ]) - sbase) * PER + 2 * lane, o, w0, w1, w2, q0, q1, q2, a);
     }
     bwd_store<FIRST>(o, a, il, i, f0, lane, m, h, n_atoms, dphi, dv_in, gradp, accum);
   }
@@ -973,240 +1063,6 @@ __global__ void __launch_bounds__(T, 1) message_bwd_memo_state_group(
       *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ox, dvx[s]);
       *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(oy, dvy[s]);
       *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(oz, dvz[s]);
-    }
-  }
-}
-
-// ============================================================================================
-// k-block kernels for the direct edges.  The filter has three 128-wide blocks w0|w1|w2 that feed different
-// outputs (x0 = phi0.w0 -> dv via v_j ; x1 = phi1.w1 -> ds ; x2 = phi2.w2 -> dv via u), so the direct pass can be
-// split into one kernel per block: a lane then keeps 20 weight pairs instead of 60 (the w and dw/dd of a block
-// share them), stages 1-7 rows per atom instead of 6-10, and needs ~100 registers instead of 244 -- 16 warps
-// per SM instead of 8, which is what the FMA pipe needed (it was 35-47 % busy).  The price is that the compact
-// 256-byte records are read three times.  Launch order per layer: forward 1, 2, 0 ; backward 1, 2, 0 ; block 0
-// does not exist at the first layer (v = 0).  Sums into one output from different blocks happen in that fixed
-// order, through memory.
-// ============================================================================================
-constexpr int KB_STAGES = 4;
-__host__ __device__ constexpr int kb_ring_floats(int threads) { return threads / 32 * KB_STAGES * CREC; }
-__host__ __device__ constexpr int kb_fwd_per(int kb) { return kb == 0 ? 4 * MSG_FC : MSG_FC; }
-__host__ __device__ constexpr int kb_bwd_per(int kb) { return kb == 0 ? 7 * MSG_FC : (kb == 1 ? 2 * MSG_FC : 4 * MSG_FC); }
-
-// ring walk over the compact records of one row: body(rec) per edge, N16 = 16-byte pieces to fetch
-template <int N16, typename Body>
-__device__ __forceinline__ void kb_walk(const float* __restrict__ rec0, int ne, int lane, float* __restrict__ ring, Body body) {
-  __syncwarp();
-#pragma unroll
-  for (int s = 0; s < KB_STAGES - 1; ++s) prefetch_record(ring + s * CREC, rec0 + (long long)s * CREC, lane, N16, s < ne);
-  for (int e = 0; e < ne; ++e) {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(KB_STAGES - 2));
-    __syncwarp();
-    const int nx = e + KB_STAGES - 1;
-    prefetch_record(ring + (nx % KB_STAGES) * CREC, rec0 + (long long)nx * CREC, lane, N16, nx < ne);
-    body(ring + (e % KB_STAGES) * CREC);
-  }
-}
-
-// w = bd*env + sum_n wd[n]*r[n]  (and q with the derivative row) from a compact record
-template <bool WITH_Q>
-__device__ __forceinline__ void kb_filter(const float* __restrict__ rec, const float2* __restrict__ wd, float2 bd, float2& w, float2& q) {
-  w = __fmul2_rn(bd, dup2(rec[CREC_RE + 20]));
-  if (WITH_Q) q = __fmul2_rn(bd, dup2(rec[CREC_RE + 21]));
-#pragma unroll
-  for (int n4 = 0; n4 < NRBF / 4; ++n4) {
-    const float4 r = *reinterpret_cast<const float4*>(rec + CREC_RE + 4 * n4);
-    w = __ffma2_rn(wd[4 * n4], dup2(r.x), w); w = __ffma2_rn(wd[4 * n4 + 1], dup2(r.y), w);
-    w = __ffma2_rn(wd[4 * n4 + 2], dup2(r.z), w); w = __ffma2_rn(wd[4 * n4 + 3], dup2(r.w), w);
-    if (WITH_Q) {
-      const float4 d = *reinterpret_cast<const float4*>(rec + CREC_DRE + 4 * n4);
-      q = __ffma2_rn(wd[4 * n4], dup2(d.x), q); q = __ffma2_rn(wd[4 * n4 + 1], dup2(d.y), q);
-      q = __ffma2_rn(wd[4 * n4 + 2], dup2(d.z), q); q = __ffma2_rn(wd[4 * n4 + 3], dup2(d.w), q);
-    }
-  }
-}
-
-template <int KB, bool FIRST, int T>
-__global__ void __launch_bounds__(T, (T <= 256 ? 2 : 1)) msg_fwd_kb(
-    const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order, const int32_t* __restrict__ nvalid,
-    const float* __restrict__ crec, const float* __restrict__ phi, const float* __restrict__ s_in,
-    const float* __restrict__ v_in, float* __restrict__ cat, float* __restrict__ v_mid, int accum) {
-  extern __shared__ __align__(16) float smem_all[];
-  __shared__ int row_ctr;
-  if (threadIdx.x == 0) row_ctr = 0;
-  constexpr int PER = kb_fwd_per(KB);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* ring = smem_all + warp * KB_STAGES * CREC;
-  float* smem = smem_all + kb_ring_floats(T);
-  const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
-  const int h = blockIdx.y, m = blockIdx.z;
-  const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
-  const long long mA = (long long)m * n_atoms;
-  stage_rows(smem, PER, 0, phi + (mA + a0) * F3 + KB * F + h * MSG_FC, F3, F, 1, n, tid, T);
-  if (KB == 0) stage_rows(smem, PER, MSG_FC, v_in + (mA + a0) * 3 * F + h * MSG_FC, 3 * F, F, 3, n, tid, T);
-  const int f0 = h * MSG_FC + 2 * lane;
-  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
-  float2 wd[NRBF];
-#pragma unroll
-  for (int q = 0; q < NRBF; ++q) wd[q] = ld2(wl + L_WDT + q * F3 + KB * F + f0);
-  const float2 bd = ld2(wl + L_BD + KB * F + f0);
-  stage_wait();
-  __syncthreads();
-  for (int t = ch + n_chunks * next_row(&row_ctr, lane); t < n; t = ch + n_chunks * next_row(&row_ctr, lane)) {
-    const int il = __ldg(order + a0 + t);
-    const long long i = mA + a0 + il;
-    const int ne = __ldg(nvalid + a0 + il);
-    if (ne == 0 && (accum || KB == 0)) continue;     // block 0 always adds onto block 2's result
-    float2 acc0 = dup2(0.f), acc1 = dup2(0.f), acc2 = dup2(0.f);   // ds (block 1) or dv (blocks 2, 0)
-    kb_walk<(CREC_RE + 24) / 4>(crec + (long long)__ldg(rowptr + a0 + il) * CREC, ne, lane, ring, [&](const float* rec) {
-      float2 w, unused;
-      kb_filter<false>(rec, wd, bd, w, unused);
-      const float* sj = smem + (__float_as_int(rec[4]) - a0) * PER + 2 * lane;
-      const float2 x = __fmul2_rn(ld2(sj), w);
-      if (KB == 1) {
-        acc0 = __fadd2_rn(acc0, x);
-      } else if (KB == 2) {
-        acc0 = __ffma2_rn(x, dup2(rec[0]), acc0); acc1 = __ffma2_rn(x, dup2(rec[1]), acc1); acc2 = __ffma2_rn(x, dup2(rec[2]), acc2);
-      } else {
-        acc0 = __ffma2_rn(x, ld2(sj + MSG_FC), acc0); acc1 = __ffma2_rn(x, ld2(sj + 2 * MSG_FC), acc1);
-        acc2 = __ffma2_rn(x, ld2(sj + 3 * MSG_FC), acc2);
-      }
-    });
-    if (KB == 1) {
-      float* so = cat + i * 2 * F + f0;
-      *reinterpret_cast<float2*>(so) = __fadd2_rn(accum ? ld2(so) : ld2(s_in + i * F + f0), acc0);
-    } else {
-      float* vo = v_mid + i * 3 * F + f0;
-      float2 bx, by, bz;
-      if (accum || KB == 0) { bx = ld2(vo); by = ld2(vo + F); bz = ld2(vo + 2 * F); }
-      else if (FIRST) { bx = by = bz = dup2(0.f); }
-      else { const float* vi = v_in + i * 3 * F + f0; bx = ld2(vi); by = ld2(vi + F); bz = ld2(vi + 2 * F); }
-      *reinterpret_cast<float2*>(vo) = __fadd2_rn(bx, acc0);
-      *reinterpret_cast<float2*>(vo + F) = __fadd2_rn(by, acc1);
-      *reinterpret_cast<float2*>(vo + 2 * F) = __fadd2_rn(bz, acc2);
-    }
-  }
-}
-
-// accum bit 0: the state outputs (dphi block, dv_in) were started by a memo pass; gaccum: gradp was started
-// (by a memo pass or by an earlier block's kernel of this layer)
-template <int KB, bool FIRST, int T>
-__global__ void __launch_bounds__(T, (T <= 256 ? 2 : 1)) msg_bwd_kb(
-    const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ atom_ptr, int n_chunks,
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order, const int32_t* __restrict__ nvalid,
-    const float* __restrict__ crec, const float* __restrict__ phi, const float* __restrict__ v_in,
-    const float* __restrict__ ds, const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in,
-    float* __restrict__ gradp, int accum, int gaccum, const uint8_t* __restrict__ frozen, int n0) {
-  extern __shared__ __align__(16) float smem_all[];
-  __shared__ int row_ctr;
-  if (threadIdx.x == 0) row_ctr = 0;
-  constexpr int PER = kb_bwd_per(KB);
-  constexpr int O_G = KB == 0 ? 4 * MSG_FC : MSG_FC;   // offset of the gradient rows (ds or dv) inside an atom's block
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* ring = smem_all + warp * KB_STAGES * CREC;
-  float* smem = smem_all + kb_ring_floats(T);
-  const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
-  const int h = blockIdx.y, m = blockIdx.z;
-  const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
-  const long long mA = (long long)m * n_atoms;
-  stage_rows(smem, PER, 0, phi + (mA + a0) * F3 + KB * F + h * MSG_FC, F3, F, 1, n, tid, T);
-  if (KB == 0) stage_rows(smem, PER, MSG_FC, v_in + (mA + a0) * 3 * F + h * MSG_FC, 3 * F, F, 3, n, tid, T);
-  if (KB == 1) stage_rows(smem, PER, O_G, ds + (mA + a0) * F + h * MSG_FC, F, F, 1, n, tid, T);
-  else stage_rows(smem, PER, O_G, dv + (mA + a0) * 3 * F + h * MSG_FC, 3 * F, F, 3, n, tid, T);
-  const int f0 = h * MSG_FC + 2 * lane;
-  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
-  float2 wd[NRBF];
-#pragma unroll
-  for (int q = 0; q < NRBF; ++q) wd[q] = ld2(wl + L_WDT + q * F3 + KB * F + f0);
-  const float2 bd = ld2(wl + L_BD + KB * F + f0);
-  stage_wait();
-  __syncthreads();
-  for (int t = ch + n_chunks * next_row(&row_ctr, lane); t < n; t = ch + n_chunks * next_row(&row_ctr, lane)) {
-    const int il = __ldg(order + a0 + t);
-    const long long i = mA + a0 + il;
-    const int ne = __ldg(nvalid + a0 + il);
-    const bool light = frozen && il < n0 && frozen[il];   // constrained mode: no dE/dx wanted for this receiver
-    float* gp = gradp + (((long long)m * 2 + h) * n_atoms + a0 + il) * 3;
-    const float* si = smem + il * PER + 2 * lane;
-    float2 dp = dup2(0.f), dvx = dup2(0.f), dvy = dup2(0.f), dvz = dup2(0.f), gnx = dup2(0.f), gny = dup2(0.f), gnz = dup2(0.f);
-    if (ne > 0 && !(light && FIRST)) {
-      const float2 pi = ld2(si);
-      float2 o1 = dup2(0.f), o2 = dup2(0.f), o3 = dup2(0.f), o4 = dup2(0.f), o5 = dup2(0.f), o6 = dup2(0.f);
-      if (KB == 1) { o1 = ld2(si + O_G); }                                                             // gs_i
-      if (KB == 2) { o1 = ld2(si + O_G); o2 = ld2(si + O_G + MSG_FC); o3 = ld2(si + O_G + 2 * MSG_FC); }   // gv_i
-      if (KB == 0) {
-        o1 = ld2(si + O_G); o2 = ld2(si + O_G + MSG_FC); o3 = ld2(si + O_G + 2 * MSG_FC);               // gv_i
-        o4 = ld2(si + MSG_FC); o5 = ld2(si + 2 * MSG_FC); o6 = ld2(si + 3 * MSG_FC);                    // v_i
-      }
-      auto edge = [&](const float* rec, auto with_q) {
-        constexpr bool Q = decltype(with_q)::value;
-        float2 w, q = dup2(0.f);
-        kb_filter<Q>(rec, wd, bd, w, q);
-        const float* sj = smem + (__float_as_int(rec[4]) - a0) * PER + 2 * lane;
-        const float2 pj = ld2(sj);
-        const float2 ux = dup2(rec[0]), uy = dup2(rec[1]), uz = dup2(rec[2]);
-        if (KB == 1) {
-          const float2 gsj = ld2(sj + O_G);
-          dp = __ffma2_rn(gsj, w, dp);
-          if (Q) {
-            const float2 dd = __fmul2_rn(__ffma2_rn(o1, pj, __fmul2_rn(gsj, pi)), q);
-            gnx = __ffma2_rn(dd, ux, gnx); gny = __ffma2_rn(dd, uy, gny); gnz = __ffma2_rn(dd, uz, gnz);
-          }
-        } else if (KB == 2) {
-          const float2 gvjx = ld2(sj + O_G), gvjy = ld2(sj + O_G + MSG_FC), gvjz = ld2(sj + O_G + 2 * MSG_FC);
-          const float2 nB2 = __ffma2_rn(gvjz, uz, __ffma2_rn(gvjy, uy, __fmul2_rn(gvjx, ux)));
-          dp = __ffma2_rn(nB2, w, dp);                                   // stored negated (dphi2 = -sum)
-          if (Q) {
-            const float2 dxA2 = __ffma2_rn(o3, uz, __ffma2_rn(o2, uy, __fmul2_rn(o1, ux)));
-            const float2 dd = __fmul2_rn(__ffma2_rn(dxA2, pj, neg2(__fmul2_rn(nB2, pi))), q);
-            const float2 ta = __fmul2_rn(pj, w), tbn = neg2(__fmul2_rn(pi, w));
-            const float2 ex = __ffma2_rn(o1, ta, __fmul2_rn(gvjx, tbn));
-            const float2 ey = __ffma2_rn(o2, ta, __fmul2_rn(gvjy, tbn));
-            const float2 ez = __ffma2_rn(o3, ta, __fmul2_rn(gvjz, tbn));
-            const float2 proj = __ffma2_rn(ez, uz, __ffma2_rn(ey, uy, __fmul2_rn(ex, ux)));
-            const float2 invd = dup2(rec[7]);
-            const float2 c = __ffma2_rn(neg2(proj), invd, dd);
-            gnx = __ffma2_rn(c, ux, __ffma2_rn(ex, invd, gnx));
-            gny = __ffma2_rn(c, uy, __ffma2_rn(ey, invd, gny));
-            gnz = __ffma2_rn(c, uz, __ffma2_rn(ez, invd, gnz));
-          }
-        } else {
-          const float2 gvjx = ld2(sj + O_G), gvjy = ld2(sj + O_G + MSG_FC), gvjz = ld2(sj + O_G + 2 * MSG_FC);
-          const float2 dxB0 = __ffma2_rn(gvjz, o6, __ffma2_rn(gvjy, o5, __fmul2_rn(gvjx, o4)));
-          dp = __ffma2_rn(dxB0, w, dp);
-          const float2 tv = __fmul2_rn(pi, w);
-          dvx = __ffma2_rn(tv, gvjx, dvx); dvy = __ffma2_rn(tv, gvjy, dvy); dvz = __ffma2_rn(tv, gvjz, dvz);
-          if (Q) {
-            const float2 vjx = ld2(sj + MSG_FC), vjy = ld2(sj + 2 * MSG_FC), vjz = ld2(sj + 3 * MSG_FC);
-            const float2 dxA0 = __ffma2_rn(o3, vjz, __ffma2_rn(o2, vjy, __fmul2_rn(o1, vjx)));
-            const float2 dd = __fmul2_rn(__ffma2_rn(dxA0, pj, __fmul2_rn(dxB0, pi)), q);
-            gnx = __ffma2_rn(dd, ux, gnx); gny = __ffma2_rn(dd, uy, gny); gnz = __ffma2_rn(dd, uz, gnz);
-          }
-        }
-      };
-      const float* rec0 = crec + (long long)__ldg(rowptr + a0 + il) * CREC;
-      if (light) kb_walk<(CREC_RE + 24) / 4>(rec0, ne, lane, ring, [&](const float* rec) { edge(rec, std::false_type{}); });
-      else kb_walk<(CREC_DRE + 20) / 4>(rec0, ne, lane, ring, [&](const float* rec) { edge(rec, std::true_type{}); });
-    }
-    if (!FIRST && !(accum && ne == 0)) {
-      float* dpo = dphi + i * F3 + KB * F + f0;
-      const float2 val = KB == 2 ? neg2(dp) : dp;
-      *reinterpret_cast<float2*>(dpo) = accum ? __fadd2_rn(ld2(dpo), val) : val;
-      if (KB == 0) {
-        float* dvo = dv_in + i * 3 * F + f0;
-        const float2 bx = accum ? ld2(dvo) : ld2(si + O_G), by = accum ? ld2(dvo + F) : ld2(si + O_G + MSG_FC),
-                     bz = accum ? ld2(dvo + 2 * F) : ld2(si + O_G + 2 * MSG_FC);
-        *reinterpret_cast<float2*>(dvo) = __fadd2_rn(bx, dvx);
-        *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(by, dvy);
-        *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(bz, dvz);
-      }
-    }
-    if (!(gaccum && (ne == 0 || light))) {
-      const float gx = warp_sum(gnx.x + gnx.y), gy = warp_sum(gny.x + gny.y), gz = warp_sum(gnz.x + gnz.y);
-      if (lane == 0) {
-        if (gaccum) { gp[0] -= gx; gp[1] -= gy; gp[2] -= gz; }
-        else { gp[0] = -gx; gp[1] = -gy; gp[2] = -gz; }
-      }
     }
   }
 }

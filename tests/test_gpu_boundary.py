@@ -225,7 +225,8 @@ def test_nff_pourbaix_calculator_on_gpu(structures, sto_weights):
         assert abs(r["surface_energy"] - ref) < 1e-5 * len(numbers), (phi, pH, r["surface_energy"], ref)
         assert abs(calc.get_property("surface_energy", atoms=atoms) - r["surface_energy"]) == 0.0       # cached
         # the batched driver's scalar is the same function of (energy, symbols)
-        assert abs(calc.surface_energy_fn()(float(r["energy"][0]), symbols) - r["surface_energy"]) < 1e-9
+        # (the calculator's results are fp32 like NFF's -- E_slab + correction stays a float32 array -- the driver's fp64)
+        assert abs(calc.surface_energy_fn()(float(r["energy"][0]), symbols) - float(r["surface_energy"][0])) < 1e-4
 
 
 def test_embedding_values_vs_oracle(structures, potentials, sto_weights):

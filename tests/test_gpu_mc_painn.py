@@ -161,10 +161,12 @@ def test_late_mc_batch_vs_fp64_oracle(structures):
         p, z = arrs[k]
         o = ens64.calculate(p, z, s["cell"], PBC3)
         fscale = np.abs(o["grads_per_model"]).max()
-        overlap = fscale > 50      # trial placements on neighbouring sites overlap: fp32 resolution, not 1e-5, bounds them
+        # trial placements on neighbouring sites overlap (|dE/dx| of 1e2..1e3 eV/A): there fp32 resolution bounds the result,
+        # not 1e-4 -- one fp32 ulp of the largest force is already 1e-5 eV/A and a force row sums ~1e2 such terms
+        overlap = fscale > 50
         etol = E_TOL_PER_ATOM * len(z) + (2e-7 * np.abs(o["energies_per_model"]).max() if overlap else 0.0)
         assert abs(e[k] - o["energy"][0]) <= etol, (k, n_ads[k], e[k], o["energy"][0])
-        assert (np.abs(f[k] - o["forces"]) <= 1e-4 + (2e-6 * fscale if overlap else 0.0)).all(), (k, np.abs(f[k] - o["forces"]).max(), fscale)
+        assert (np.abs(f[k] - o["forces"]) <= 1e-4 + (1e-5 * fscale if overlap else 0.0)).all(), (k, np.abs(f[k] - o["forces"]).max(), fscale)
         worst_e = max(worst_e, abs(e[k] - o["energy"][0]) / len(z))
         if fscale < 50:
             worst_f = max(worst_f, np.abs(f[k] - o["forces"]).max())

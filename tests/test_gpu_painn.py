@@ -241,21 +241,49 @@ def test_frozen_pair_filter_memo(structures, potentials, sto_weights):
     assert torch.equal(r2["forces"], r0["forces"]) or (r2["forces"] - r0["forces"]).abs().max().item() < 2e-5
 
 
-def test_large_structure_global_gather_path(structures):
-    """Structures beyond the shared-memory staging budget (> 84 atoms) take the global-gather message kernels;
-    same tolerances vs the oracle, also inside a batch with a small structure."""
+def _stacked(base, n_ads):
+    """base slab + n_ads adsorbates on 4x4 grids, 1.9 A apart, stacked in layers above the surface (no overlaps)."""
+    ztop = base["positions"][:, 2].max()
+    grid = np.array([[0.5 + 1.9 * (a % 4) + 0.9 * ((a // 16) % 2), 0.5 + 1.9 * ((a // 4) % 4) + 0.9 * ((a // 16) % 2),
+                      ztop + 1.5 + 1.9 * (a // 16)] for a in range(n_ads)])
+    return {"positions": np.vstack([base["positions"], grid]), "cell": base["cell"],
+            "numbers": np.concatenate([base["numbers"], np.array(([8, 38, 22, 8] * ((n_ads + 3) // 4))[:n_ads])])}
+
+
+def test_large_structures_sender_windows(structures):
+    """Structures beyond one CTA's staging area (> 86 atoms in the backward) are covered by several sender-window
+    launches of the direct message kernels: same tolerances vs the oracle, with and without the frozen-framework memo,
+    and -- because the window count depends on a structure's own size only -- the same BITS alone and inside a batch."""
     from surface_sampling_b200 import engine
     states = [init_random_weights(s) for s in (0, 1, 2)]
-    eng = engine.PainnEngine(states, None)
     ens = EnsembleOracle(states, None, dtype=torch.float64)
     base = structures["SrTiO3_001_2x2"]
-    ztop = base["positions"][:, 2].max()
-    grid = np.array([[0.5 + 1.9 * (a % 4) + 0.9 * (a // 16), 0.5 + 1.9 * ((a // 4) % 4) + 0.9 * (a // 16),
-                      ztop + 1.5 + 1.9 * (a // 16)] for a in range(32)])
-    big = {"positions": np.vstack([base["positions"], grid]), "cell": base["cell"],
-           "numbers": np.concatenate([base["numbers"], np.array([8, 38, 22, 8] * 8)])}
-    assert len(big["numbers"]) == 92
-    _compare(eng, ens, [big, base])
+    fixed0 = orelax.fixed_mask_from_surface_depth(base["positions"], base["cell"], 1)
+    big, mid, huge = _stacked(base, 72), _stacked(base, 32), _stacked(base, 150)
+    assert (len(big["numbers"]), len(mid["numbers"]), len(huge["numbers"])) == (132, 92, 210)
+    plain = engine.PainnEngine(states, None)
+    _compare(plain, ens, [big, base, mid])
+    _compare(plain, ens, [huge])
+    memo = engine.PainnEngine(states, None)
+    memo.set_framework(base["positions"], base["cell"], PBC3, fixed0, constrained_forces=True)
+    _compare(memo, ens, [mid, big, base, big])
+    batch = [big, base, mid, huge]
+    for eng in (plain, memo):
+        r_all = eng.energy_forces(_batch(batch))
+        b = _batch(batch)
+        for k, s in enumerate(batch):
+            solo = eng.energy_forces(_batch([s]))
+            lo, hi = b.atom_ptr_host[k], b.atom_ptr_host[k + 1]
+            assert torch.equal(solo["forces"], r_all["forces"][lo:hi]) and solo["energy"][0] == r_all["energy"][k], k
+    # fused relaxation on the windowed path: constrained (framework registered) and plain agree, frozen atoms stay put
+    fx = [np.concatenate([fixed0, np.zeros(len(s["numbers"]) - 60, bool)]) for s in (big, mid)]
+    b0, b1 = _batch([big, mid], fx), _batch([big, mid], fx)
+    o0 = plain.relax(b0, relax_steps=6, check=True)["out"].cpu().numpy()
+    o1 = memo.relax(b1, relax_steps=6, check=True)["out"].cpu().numpy()
+    assert np.array_equal(o0[:, 4:], o1[:, 4:]) and np.abs(o0[:, 0] - o1[:, 0]).max() < 2e-4
+    assert (b0.pos - b1.pos).abs().max().item() < 2e-5
+    frozen = torch.from_numpy(np.concatenate(fx)).cuda()
+    assert torch.equal(b1.pos[frozen], _batch([big, mid], fx).pos[frozen])
 
 
 def test_relax_retries_on_edge_capacity_overflow(structures, potentials, sto_weights):
