@@ -259,8 +259,9 @@ def test_large_structures_sender_windows(structures):
     ens = EnsembleOracle(states, None, dtype=torch.float64)
     base = structures["SrTiO3_001_2x2"]
     fixed0 = orelax.fixed_mask_from_surface_depth(base["positions"], base["cell"], 1)
-    big, mid, huge = _stacked(base, 72), _stacked(base, 32), _stacked(base, 150)
-    assert (len(big["numbers"]), len(mid["numbers"]), len(huge["numbers"])) == (132, 92, 210)
+    # 7 adsorbate layers fill the vacuum; `huge` sits on the thicker 2x2x4 slab -> 3 sender windows in the backward
+    big, mid, huge = _stacked(base, 72), _stacked(base, 32), _stacked(structures["SrTiO3_001_2x2x4"], 112)
+    assert (len(big["numbers"]), len(mid["numbers"]), len(huge["numbers"])) == (132, 92, 192)
     plain = engine.PainnEngine(states, None)
     _compare(plain, ens, [big, base, mid])
     _compare(plain, ens, [huge])

@@ -77,6 +77,39 @@ def test_sharded_statistics_gather_gloo_world2(tmp_path):
     assert np.array_equal(got[0], ref["energy_hist"]) and np.array_equal(got[2], ref["adsorption_count_hist"])
 
 
+def _grid_driver(rank, world):
+    """Toy slab, Pourbaix grand potential per (pH, U) unit exactly as bench.py wires BASELINE config 5."""
+    import bench
+    mine, seeds, cpp = bench.grid_units("sto_pourbaix", 2 * len(bench.PH_VALUES) * len(bench.U_VALUES) // world, rank, world)
+    n_total = len(bench.PH_VALUES) * len(bench.U_VALUES) * cpp
+    base, _ = _driver([0])
+    drv = mc.MultiChainMC([NUMBERS[q] for q in ["Sr", "Ti", "O", "O"]], base.chains[0]._pos0, np.ones(4, bool),
+                          base.chains[0].ads_coords, ["Sr", "O", "HO"], base.relax_fn,
+                          bench.surface_energy_fns("sto_pourbaix", None, mine), seeds)
+    return drv, n_total
+
+
+@pytest.mark.timeout(180)
+def test_pourbaix_grid_shards_over_ranks_gloo_world2(tmp_path):
+    """BASELINE config 5: 8 pH x 7 U grid points x chains as independent (pH, U, chain) units, round-robin over ranks
+    (parallel.shard_grid); every unit carries its own grand-potential scalar; only per-sweep scalars are gathered.
+    Two gloo ranks reproduce the single-process run unit by unit."""
+    script = ROOT / "tests" / "_gloo_worker.py"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29733", PYTHONPATH=str(ROOT))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", str(tmp_path), "grid"], env=env) for r in range(2)]
+    assert all(p.wait(timeout=160) == 0 for p in procs)
+    got = np.load(tmp_path / "gathered.npy")
+    drv, n_total = _grid_driver(0, 1)
+    assert n_total == 112 and len(drv.chains) == 112
+    ref = drv.run(total_sweeps=2, sweep_size=3, start_temp=0.257, perform_annealing=False)
+    assert np.array_equal(got[0], ref["energy_hist"]) and np.array_equal(got[2], ref["adsorption_count_hist"])
+    # different grid points really see different grand potentials for the same structure
+    import bench
+    fns = bench.surface_energy_fns("sto_pourbaix", None, [(0.0, -1.0, 0), (14.0, 2.0, 0)])
+    sym = ["Sr", "Ti", "O", "O", "O", "H"]
+    assert abs(fns[0](-10.0, sym) - fns[1](-10.0, sym)) > 0.1
+
+
 def test_pipelined_groups_make_the_same_decisions():
     """MultiChainMC.pipeline (host logic of one chain group overlapped with the relaxation of the other,
     asynchronous relax handles) leaves every chain's accept/reject sequence and occupancy unchanged."""
