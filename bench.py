@@ -349,7 +349,8 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
 
     if w["models"]:
         states = [loaders.init_random_weights(s) for s in range(w["models"])]     # random-init per BASELINE.json; untimed
-        eng = engine.PainnEngine(states, pots["offset_data"] if name == "sto_painn" else None)
+        # edge capacity: a half-covered slab reaches ~130 neighbours per atom inside the 6 A skin list
+        eng = engine.PainnEngine(states, pots["offset_data"] if name == "sto_painn" else None, edges_per_atom=192)
         to_species = lambda zz: zz
         if not os.environ.get("VSSR_NO_FILTER_MEMO"):
             # radial-filter memo for the frozen bulk (one-time, untimed); the relaxation holds those atoms with
@@ -362,10 +363,10 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
         if name == "gan_tersoff":
             tmap = {31: 0, 7: 1}
             eng = engine.ClassicalEngine(engine.POT_TERSOFF, engine.tersoff_param_table(pots["GaN.tersoff"], ["Ga", "N"]), 2,
-                                         n_max=64, max_nbr=24)
+                                         n_max=64, max_nbr=32)
         else:
             tmap = {14: 0}
-            eng = engine.ClassicalEngine(engine.POT_SW, engine.sw_param_table(), 1, n_max=128, max_nbr=32)
+            eng = engine.ClassicalEngine(engine.POT_SW, engine.sw_param_table(), 1, n_max=160, max_nbr=40)
         lut = np.zeros(120, np.int32)
         for zz_, t_ in tmap.items():
             lut[zz_] = t_
@@ -406,9 +407,13 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
         return Pending(r["out"])
 
     def check_statuses():
-        if statuses and int(torch.stack(statuses).max().item()) != 0:
-            raise RuntimeError("a relaxation reported a device-side overflow (edge capacity / neighbour slots): the run is invalid")
+        bits = 0
+        for st_ in statuses:
+            bits |= int(st_.item())
         statuses.clear()
+        if bits:
+            what = [n_ for b_, n_ in ((1, "edge capacity (edges_per_atom)"), (2, "neighbour slots (max_nbr)"), (4, "atoms per structure (n_max)")) if bits & b_]
+            raise RuntimeError(f"{name}: a relaxation reported a device-side overflow of {', '.join(what)}: the run is invalid")
 
     drv = build_driver(name, relax_fn, seeds, units)
     if w["canonical"]:
@@ -706,7 +711,11 @@ def main():
         # the other BASELINE configs, short runs (their own value / e2e / roofline / cpu_baseline)
         out["workloads"] = []
         for other in ("gan_tersoff", "si_sw", "sto_pourbaix"):
-            o = run_workload(other, args, ctx, min(args.steps, 10), 3, WORKLOADS[other]["burn_in"], headline=False)
+            try:
+                o = run_workload(other, args, ctx, min(args.steps, 10), 3, WORKLOADS[other]["burn_in"], headline=False)
+            except Exception as exc:      # a side workload must not cost the headline line
+                out["workloads"].append({"config": {"workload": WORKLOADS[other]["desc"]}, "error": f"{type(exc).__name__}: {exc}"})
+                continue
             out["workloads"].append({k: o[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "dtype", "config",
                                                        "e2e", "gpu_launches", "roofline", "kernel_breakdown_ms", "reference_published_single_chain") if k in o}
                                     | ({"cpu_baseline": o["cpu_baseline"]} if "cpu_baseline" in o else {}))

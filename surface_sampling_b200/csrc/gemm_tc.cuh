@@ -371,18 +371,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-
-template <int BN, int EPI, int CL>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmBh,
                                                                     const __grid_constant__ CUtensorMap tmBl,
@@ -398,14 +387,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
 
   const GemmArgs& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // CL == 2: the two CTAs of a cluster work on the same (model, n-tile) and neighbouring m-tiles; each loads
-  // HALF of the B (weight) chunk and multicasts it into both CTAs' shared memory, so the L2->SM operand
-  // stream per CTA drops from 48 to 32 KB per chunk.  MMAs stay cta_group::1; a stage is released to the
-  // producers of BOTH CTAs (multicast tcgen05.commit), because either producer writes into both.
-  uint32_t crank = 0;
-  if (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-  const int wid = CL == 2 ? blockIdx.x / 2 : blockIdx.x;         // work-stream id (cluster or CTA)
-  const int nw = CL == 2 ? gridDim.x / 2 : gridDim.x;
+  // (a 2-CTA-cluster variant that multicast the weight tile was measured slower and removed: profiles/r2_notes.md section 4)
+  const int wid = blockIdx.x, nw = gridDim.x;                    // persistent CTAs stride over the work items
   if (tid == 0) TC_STAMP(0);
   if (warp == TM_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(4 * BN));
@@ -417,7 +400,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)) : "memory");
     for (int s = 0; s < TM_STAGES; ++s) {
       mbar_init(&full_bar[s], 1 + TM_SPLIT_WARPS);
-      mbar_init(&empty_bar[s], CL);
+      mbar_init(&empty_bar[s], 1);
       mbar_init(&araw_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
@@ -427,16 +410,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
   }
   fence_before();
   __syncthreads();
-  if (CL == 2) {   // the peer must see initialised barriers before its multicast can signal them
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
   fence_after();
   const uint32_t tmem0 = tmem_base_s;
   if (tid == 0) TC_STAMP(1);
 
-  // work items: (model, m-group, n-tile), a m-group = CL neighbouring m-tiles (one per CTA of the cluster)
-  const int m_tiles = ((g.M + BM - 1) / BM + CL - 1) / CL, n_tiles = g.N / BN;
+  // work items: (model, m-tile, n-tile)
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN;
   const int total = m_tiles * n_tiles * p.n_models;
   const int nchunks = g.K / BK;
   constexpr uint32_t idesc = make_idesc(BM, BN);
@@ -448,7 +427,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
       for (int t = wid; t < total; t += nw) {
         const int model = t / (m_tiles * n_tiles);
         const int rem = t % (m_tiles * n_tiles);
-        const int m0 = ((rem / n_tiles) * CL + (int)crank) * BM, n0 = (rem % n_tiles) * BN;
+        const int m0 = (rem / n_tiles) * BM, n0 = (rem % n_tiles) * BN;
         for (int c = 0; c < nchunks; ++c, ++gchunk) {
           const int s = gchunk % TM_STAGES;
           mbar_wait(&empty_bar[s], ((gchunk / TM_STAGES) & 1) ^ 1);
@@ -456,14 +435,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
           mbar_expect_tx(&araw_bar[s], A_BYTES);
           tma_load_3d(st, &tmA, &araw_bar[s], c * BK, m0, model);
           mbar_expect_tx(&full_bar[s], 2 * B_BYTES);   // bytes that will land in THIS CTA's stage
-          if (CL == 1) {
-            tma_load_3d(st + 2 * A_BYTES, &tmBh, &full_bar[s], c * BK, n0, model);
-            tma_load_3d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full_bar[s], c * BK, n0, model);
-          } else {   // my half of the rows, into both CTAs (same offsets, same barrier offset)
-            const int half = (int)crank * (BN / 2);
-            tma_load_3d_mc(st + 2 * A_BYTES + half * BK * 4, &tmBh, &full_bar[s], c * BK, n0 + half, model, (uint16_t)3);
-            tma_load_3d_mc(st + 2 * A_BYTES + B_BYTES + half * BK * 4, &tmBl, &full_bar[s], c * BK, n0 + half, model, (uint16_t)3);
-          }
+          tma_load_3d(st + 2 * A_BYTES, &tmBh, &full_bar[s], c * BK, n0, model);
+          tma_load_3d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full_bar[s], c * BK, n0, model);
         }
       }
     }
@@ -524,8 +497,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
               mma_tf32(d_corr, dAh + adv, dBl + adv, idesc, 1u);
             }
           }
-          if (CL == 1) mma_commit(&empty_bar[s]);
-          else mma_commit_mc(&empty_bar[s], (uint16_t)3);
+          mma_commit(&empty_bar[s]);
         }
         mma_commit(&tfull_bar[acc]);
         TC_STAMP(3);
@@ -548,7 +520,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
       const int acc = it & 1;
       const int model = t / (m_tiles * n_tiles);
       const int rem = t % (m_tiles * n_tiles);
-      const int m0 = ((rem / n_tiles) * CL + (int)crank) * BM, n0 = (rem % n_tiles) * BN;
+      const int m0 = (rem / n_tiles) * BM, n0 = (rem % n_tiles) * BN;
       const uint32_t d_main = tmem0 + acc * 2 * BN + ((uint32_t)(quarter * 32) << 16);
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       if (it == 0 && quarter == 0 && lane == 0) TC_STAMP(4);
@@ -629,10 +601,6 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
   }
   fence_before();
   __syncthreads();
-  if (CL == 2) {   // the peer may still multicast into this CTA's stages / signal its barriers
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
   if (tid == 0) TC_STAMP(6);
   if (warp == TM_MMA_WARP) {
     fence_after();
@@ -710,124 +678,53 @@ inline const CUtensorMap* get_tmap(const float* ptr, long long d0, long long d1,
   return m;
 }
 
-template <int BN, int EPI, int CL>
-int launch_gemm_tma_cl(const GemmArgs& g, const float* Bhi, const float* Blo, long long sBw, int n_models, int mode, cudaStream_t st, bool* done) {
+template <int BN, int EPI>
+int launch_gemm_tma(const GemmArgs& g, const float* Bhi, const float* Blo, long long sBw, int n_models, cudaStream_t st, bool* done) {
   *done = false;
   tmap_cache_trim();
   const CUtensorMap* mA = get_tmap(g.A, g.K, g.M, n_models, g.lda, g.sA, tc::BM);
-  const CUtensorMap* mBh = get_tmap(Bhi, g.K, g.N, n_models, g.K, sBw, BN / CL);
-  const CUtensorMap* mBl = get_tmap(Blo, g.K, g.N, n_models, g.K, sBw, BN / CL);
+  const CUtensorMap* mBh = get_tmap(Bhi, g.K, g.N, n_models, g.K, sBw, BN);
+  const CUtensorMap* mBl = get_tmap(Blo, g.K, g.N, n_models, g.K, sBw, BN);
   const CUtensorMap* mC = get_tmap(g.C, g.N, g.M, n_models, g.ldc, g.sC, 32);
   const CUtensorMap* mC2 = EPI == 4 ? get_tmap(g.C2, g.N, g.M, n_models, g.ldc, g.sC, 32) : mC;
   const CUtensorMap* mAux = EPI == 2 ? get_tmap(g.aux, g.N, g.M, n_models, g.ldaux, g.sAux, 32) : mC;
   if (!mA || !mBh || !mBl || !mC || !mC2 || !mAux) return 0;
-  static int dbg_on = -1, dbg_left = 3, dbg_skip = -1;
-  static unsigned long long* dbg = nullptr;
-  if (dbg_skip < 0) { const char* e = getenv("VSSR_TC_DEBUG_SKIP"); dbg_skip = e ? atoi(e) : 0; }
-  if (dbg_on < 0) { const char* e = getenv("VSSR_TC_DEBUG"); dbg_on = e ? atoi(e) : 0; if (dbg_on) cudaMalloc(&dbg, 148 * 16 * 8); }
-  if (dbg_on && dbg_skip > 0) --dbg_skip;
-  tc::TcArgs p{g, Bhi, Blo, sBw, n_models, mode, (dbg_on && dbg_left > 0 && dbg_skip == 0) ? dbg : nullptr};
-  const int total = ceil_div(ceil_div(g.M, tc::BM), CL) * (g.N / BN) * n_models;   // work items (m-groups of CL tiles)
+  tc::TcArgs p{g, Bhi, Blo, sBw, n_models, 0, nullptr};
+  const int total = ceil_div(g.M, tc::BM) * (g.N / BN) * n_models;   // work items
   constexpr size_t smem = tc::tma_smem_bytes<BN>();
-  static int max_streams = -1;   // CTAs (CL == 1) or clusters (CL == 2) that can be resident at once
-  if (max_streams < 0) {
-    VSSR_CUDA(cudaFuncSetAttribute(tc::gemm_tc_tma_kernel<BN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_streams = 148;
-    if (CL == 2) {
-      cudaLaunchConfig_t q{};
-      q.gridDim = dim3(148); q.blockDim = dim3(tc::TM_THREADS); q.dynamicSmemBytes = smem;
-      cudaLaunchAttribute qa{};
-      qa.id = cudaLaunchAttributeClusterDimension; qa.val.clusterDim.x = 2; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
-      q.attrs = &qa; q.numAttrs = 1;
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, tc::gemm_tc_tma_kernel<BN, EPI, CL>, &q) != cudaSuccess || nc <= 0) { max_streams = 0; cudaGetLastError(); }
-      else max_streams = nc < 74 ? nc : 74;
-    }
+  static bool configured[64] = {};   // the attribute is per device
+  int dev = 0;
+  VSSR_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    VSSR_CUDA(cudaFuncSetAttribute(tc::gemm_tc_tma_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev & 63] = true;
   }
-  if (max_streams <= 0) return 0;   // clusters not available: caller falls back
-  const int streams = total < max_streams ? total : max_streams;
-  const int grid = streams * CL;
-  if (CL == 1) {
-    VSSR_PROF(VSSR_K_GEMM, st, (tc::gemm_tc_tma_kernel<BN, EPI, CL><<<grid, tc::TM_THREADS, smem, st>>>(p, *mA, *mBh, *mBl, *mC, *mC2, *mAux)));
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::TM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at{};
-    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-    cfg.attrs = &at; cfg.numAttrs = 1;
-    VSSR_PROF(VSSR_K_GEMM, st, (cudaLaunchKernelEx(&cfg, tc::gemm_tc_tma_kernel<BN, EPI, CL>, p, *mA, *mBh, *mBl, *mC, *mC2, *mAux)));
-  }
-  if (p.dbg) {
-    --dbg_left;
-    unsigned long long h[148 * 16];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    unsigned long long t0 = ~0ull, t6 = 0;
-    for (int b = 0; b < grid; ++b) { if (h[b * 16] < t0) t0 = h[b * 16]; if (h[b * 16 + 6] > t6) t6 = h[b * 16 + 6]; }
-    for (int b : {0, grid - 1})
-      printf("[tma] CL=%d BN=%d E=%d M=%d N=%d K=%d items=%d grid=%d span=%.1fus | cta%d: start=%.1f init=%.1f first_full=%.1f last_commit=%.1f first_tfull=%.1f last_epi=%.1f end=%.1f\n",
-             CL, BN, EPI, g.M, g.N, g.K, total, grid, (t6 - t0) * 1e-3, b, (h[b*16]-t0)*1e-3, (h[b*16+1]-h[b*16])*1e-3, (h[b*16+2]-h[b*16])*1e-3,
-             (h[b*16+3]-h[b*16])*1e-3, (h[b*16+4]-h[b*16])*1e-3, (h[b*16+5]-h[b*16])*1e-3, (h[b*16+6]-h[b*16])*1e-3);
-  }
+  const int grid = total < 148 ? total : 148;   // one persistent CTA per SM
+  VSSR_PROF(VSSR_K_GEMM, st, (tc::gemm_tc_tma_kernel<BN, EPI><<<grid, tc::TM_THREADS, smem, st>>>(p, *mA, *mBh, *mBl, *mC, *mC2, *mAux)));
   *done = true;
   return 0;
 }
 
-template <int BN, int EPI>
-int launch_gemm_tma(const GemmArgs& g, const float* Bhi, const float* Blo, long long sBw, int n_models, int mode, cudaStream_t st, bool* done) {
-  // The 2-CTA multicast variant is OFF by default: measured on B200 it is slower (U/V GEMM 28.4 -> 32.8 us, the
-  // swish-epilogue GEMMs 6 -> 28 us) -- L2 already de-duplicates the two CTAs' requests for the same weight
-  // tile, and the cluster coupling adds stalls (profiles/r2_notes.md section 4).  VSSR_GEMM_CLUSTER=1 enables it.
-  static int cluster = -1;
-  if (cluster < 0) { const char* e = getenv("VSSR_GEMM_CLUSTER"); cluster = e ? atoi(e) : 0; }
-  if (cluster) {
-    const int rc = launch_gemm_tma_cl<BN, EPI, 2>(g, Bhi, Blo, sBw, n_models, mode, st, done);
-    if (rc || *done) return rc;
-  }
-  return launch_gemm_tma_cl<BN, EPI, 1>(g, Bhi, Blo, sBw, n_models, mode, st, done);
-}
-
+// AMODE 0: operands as stored -> TMA kernel.  AMODE 2 (A transformed on load: dswish(h5)*w6 of the readout backward):
+// the cp.async-fed tcgen05 kernel.
 template <int BN, int AMODE, int EPI>
 int launch_gemm_tc(const GemmArgs& g, const float* Bhi, const float* Blo, long long sBw, int n_models, cudaStream_t st) {
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("VSSR_TC_MODE"); mode = e ? atoi(e) : 0; }
-  static int use_tma = -1;
-  if (use_tma < 0) { const char* e = getenv("VSSR_GEMM_TMA"); use_tma = e ? atoi(e) : 1; }
-  if (AMODE == 0 && use_tma) {
+  if (AMODE == 0) {
     bool done = false;
-    const int rc = launch_gemm_tma<BN, EPI>(g, Bhi, Blo, sBw, n_models, mode, st, &done);
+    const int rc = launch_gemm_tma<BN, EPI>(g, Bhi, Blo, sBw, n_models, st, &done);
     if (rc || done) return rc;
   }
-  static int dbg_on = -1;
-  static unsigned long long* dbg = nullptr;
-  static int dbg_left = 12, dbg_skip = -1;
-  if (dbg_skip < 0) { const char* e = getenv("VSSR_TC_DEBUG_SKIP"); dbg_skip = e ? atoi(e) : 0; }
-  if (dbg_on && dbg_skip > 0) --dbg_skip;
-  if (dbg_on < 0) { const char* e = getenv("VSSR_TC_DEBUG"); dbg_on = e ? atoi(e) : 0; if (dbg_on) cudaMalloc(&dbg, 148 * 16 * 8); }
-  tc::TcArgs p{g, Bhi, Blo, sBw, n_models, mode, (dbg_on && dbg_left > 0 && dbg_skip == 0) ? dbg : nullptr};
+  tc::TcArgs p{g, Bhi, Blo, sBw, n_models, 0, nullptr};
   const int total = ceil_div(g.M, tc::BM) * (g.N / BN) * n_models;
-  {
-    static bool configured = false;
-    constexpr size_t smem = tc::ws_smem_bytes<BN>();
-    if (!configured) {
-      VSSR_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws_kernel<BN, AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
-    const int grid = total < 148 ? total : 148;
-    VSSR_PROF(VSSR_K_GEMM, st, (tc::gemm_tc_ws_kernel<BN, AMODE, EPI><<<grid, tc::WS_THREADS, smem, st>>>(p)));
-    if (p.dbg) {
-      --dbg_left;
-      unsigned long long h[148 * 16];
-      cudaStreamSynchronize(st);
-      cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-      unsigned long long t0 = ~0ull, t6 = 0;
-      for (int b = 0; b < grid; ++b) { if (h[b * 16] < t0) t0 = h[b * 16]; if (h[b * 16 + 6] > t6) t6 = h[b * 16 + 6]; }
-      const int b = grid - 1;
-      printf("[tc] BN=%d A=%d E=%d M=%d N=%d K=%d tiles=%d grid=%d span=%.1fus | cta%d: init=%.1f first_full=%.1f last_commit=%.1f first_tfull=%.1f last_epi=%.1f end=%.1f | prod use1: wait=%.2f issuedB=%.2f Adone=%.2f arrived=%.2f ; use2: wait=%.2f issuedB=%.2f Adone=%.2f arrived=%.2f\n", BN, AMODE, EPI, g.M, g.N, g.K, total, grid, (t6 - t0) * 1e-3, b,
-             (h[b*16+1]-h[b*16])*1e-3, (h[b*16+2]-h[b*16])*1e-3, (h[b*16+3]-h[b*16])*1e-3, (h[b*16+4]-h[b*16])*1e-3, (h[b*16+5]-h[b*16])*1e-3, (h[b*16+6]-h[b*16])*1e-3,
-             (h[b*16+8]-h[b*16])*1e-3, (h[b*16+9]-h[b*16])*1e-3, (h[b*16+10]-h[b*16])*1e-3, (h[b*16+11]-h[b*16])*1e-3, (h[b*16+12]-h[b*16])*1e-3, (h[b*16+13]-h[b*16])*1e-3, (h[b*16+14]-h[b*16])*1e-3, (h[b*16+15]-h[b*16])*1e-3);
-    }
-    return 0;
+  constexpr size_t smem = tc::ws_smem_bytes<BN>();
+  static bool configured[64] = {};
+  int dev = 0;
+  VSSR_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    VSSR_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws_kernel<BN, AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev & 63] = true;
   }
+  const int grid = total < 148 ? total : 148;
+  VSSR_PROF(VSSR_K_GEMM, st, (tc::gemm_tc_ws_kernel<BN, AMODE, EPI><<<grid, tc::WS_THREADS, smem, st>>>(p)));
   return 0;
 }

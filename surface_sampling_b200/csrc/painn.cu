@@ -60,167 +60,21 @@ struct GemmArgs {
   float* C2;   // EPI 4 only: second output swish(C) with C's leading dimension and model stride
 };
 
-template <int BN, int AMODE, int EPI>
-__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
-  constexpr int BM = 128, BK = 16, TN = BN / 16, NB4 = (BK * BN / 4) / 256;  // float4 B loads per thread
-  __shared__ __align__(16) float As[2][BK][BM + 4];
-  __shared__ __align__(16) float Bs[2][BK][BN];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int model = blockIdx.z;
-  const float* __restrict__ A = g.A + (long long)model * g.sA;
-  const float* __restrict__ B = g.B + (long long)model * g.sB;
-  float* __restrict__ C = g.C + (long long)model * g.sC;
-  const float* __restrict__ avec = AMODE == 2 ? g.avec + (long long)model * g.sAvec : nullptr;
-
-  const int a_row = tid >> 2, a_k = (tid & 3) * 4;  // rows a_row, a_row+64 ; k offset a_k
-  float4 ra[2], rb[NB4 > 0 ? NB4 : 1];
-
-  auto load_tiles = [&](int k0) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int r = m0 + a_row + 64 * h;
-      if (r < g.M) {
-        ra[h] = *reinterpret_cast<const float4*>(A + (long long)r * g.lda + k0 + a_k);
-        if (AMODE == 1) {
-          ra[h].x = swishf_(ra[h].x); ra[h].y = swishf_(ra[h].y); ra[h].z = swishf_(ra[h].z); ra[h].w = swishf_(ra[h].w);
-        } else if (AMODE == 2) {
-          const float4 av = *reinterpret_cast<const float4*>(avec + k0 + a_k);
-          ra[h].x = dswishf_(ra[h].x) * av.x; ra[h].y = dswishf_(ra[h].y) * av.y;
-          ra[h].z = dswishf_(ra[h].z) * av.z; ra[h].w = dswishf_(ra[h].w) * av.w;
-        }
-      } else {
-        ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < NB4; ++q) {
-      const int idx = tid + q * 256;
-      const int r = idx / (BN / 4), c4 = idx % (BN / 4);
-      rb[q] = *reinterpret_cast<const float4*>(B + (long long)(k0 + r) * g.ldb + n0 + c4 * 4);
-    }
-  };
-  auto store_tiles = [&](int buf) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int r = a_row + 64 * h;
-      As[buf][a_k + 0][r] = ra[h].x; As[buf][a_k + 1][r] = ra[h].y;
-      As[buf][a_k + 2][r] = ra[h].z; As[buf][a_k + 3][r] = ra[h].w;
-    }
-#pragma unroll
-    for (int q = 0; q < NB4; ++q) {
-      const int idx = tid + q * 256;
-      const int r = idx / (BN / 4), c4 = idx % (BN / 4);
-      *reinterpret_cast<float4*>(&Bs[buf][r][c4 * 4]) = rb[q];
-    }
-  };
-
-  // accumulators as adjacent-column pairs: packed fp32x2 FMAs (SASS FFMA2) double the FMA issue rate on sm_100
-  float2 acc[8][TN / 2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
-
-  load_tiles(0);
-  store_tiles(0);
-  __syncthreads();
-  const int nk = g.K / BK;
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float a[8];
-      float2 b[TN / 2];
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      b[0] = make_float2(b0.x, b0.y); b[1] = make_float2(b0.z, b0.w);
-      if (TN == 8) {
-        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][(BN / 2) + tx * 4]);
-        b[TN / 2 - 2] = make_float2(b1.x, b1.y); b[TN / 2 - 1] = make_float2(b1.z, b1.w);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 aa = make_float2(a[i], a[i]);
-#pragma unroll
-        for (int j = 0; j < TN / 2; ++j) acc[i][j] = __ffma2_rn(aa, b[j], acc[i][j]);
-      }
-    }
-    if (kt + 1 < nk) {
-      store_tiles(buf ^ 1);
-      __syncthreads();
-    }
-  }
-
-  // epilogue
-  const float* __restrict__ bias = (EPI == 1 || EPI == 4) ? g.bias + (long long)model * g.sBias : nullptr;
-  const float* __restrict__ aux = EPI == 2 ? g.aux + (long long)model * g.sAux : nullptr;
-  float* __restrict__ C2 = EPI == 4 ? g.C2 + (long long)model * g.sC : nullptr;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    if (r >= g.M) continue;
-#pragma unroll
-    for (int h = 0; h < TN / 4; ++h) {
-      const int c = n0 + (h == 0 ? tx * 4 : (BN / 2) + tx * 4);
-      float4 v = make_float4(acc[i][h * 2].x, acc[i][h * 2].y, acc[i][h * 2 + 1].x, acc[i][h * 2 + 1].y);
-      if (EPI == 1 || EPI == 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(bias + c);
-        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-      } else if (EPI == 2) {
-        const float4 x = *reinterpret_cast<const float4*>(aux + (long long)r * g.ldaux + c);
-        v.x *= dswishf_(x.x); v.y *= dswishf_(x.y); v.z *= dswishf_(x.z); v.w *= dswishf_(x.w);
-      } else if (EPI == 3) {
-        const float4 o = *reinterpret_cast<const float4*>(C + (long long)r * g.ldc + c);
-        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-      }
-      *reinterpret_cast<float4*>(C + (long long)r * g.ldc + c) = v;
-      if (EPI == 4)
-        *reinterpret_cast<float4*>(C2 + (long long)r * g.ldc + c) = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
-    }
-  }
-}
-
-template <int BN, int AMODE, int EPI>
-int launch_gemm(const GemmArgs& g, int n_models, cudaStream_t st) {
-  dim3 grid(ceil_div(g.M, 128), g.N / BN, n_models);
-  VSSR_PROF(VSSR_K_GEMM, st, gemm_kernel<BN, AMODE, EPI><<<grid, 256, 0, st>>>(g));
-  return 0;
-}
-
 #include "gemm_tc.cuh"
 
-// GEMM dispatcher.  Bkn = [K][N] copy of the weight (FMA path), Bnk = its K-major [N][K] copy, both
-// inside the exact-fp32 block of the packed weights; the TF32 hi/lo parts of Bnk live one and two
-// W_TOTAL further (see painn_layout.h).  VSSR_GEMM=fma forces the CUDA-core path.
-inline bool use_tensor_cores() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VSSR_GEMM");
-    v = (e && e[0] == 'f') ? 0 : 1;
-  }
-  return v == 1;
-}
-
+// GEMM dispatcher: every node MLP runs on the tcgen05 kernels (csrc/gemm_tc.cuh), 3xTF32.  Bnk = the K-major [N][K]
+// copy of the weight inside the exact-fp32 block of the packed weights; its TF32 hi / lo parts live one and two W_TOTAL
+// further (painn_layout.h).
 template <int BN, int AMODE, int EPI>
-int run_gemm(GemmArgs g, const float* Bkn, int ldb_kn, const float* Bnk, int n_models, cudaStream_t st) {
-  g.B = Bkn; g.ldb = ldb_kn; g.sB = W_STRIDE;
-  if (use_tensor_cores()) {
-    // wave quantisation: a 128-column GEMM on ~8000 rows is 195 tiles = 1.3 waves of the 148 persistent CTAs, i.e.
-    // two rounds; with 64-column tiles it is 390 half-size tiles = three half rounds
-    if (BN == 128 && AMODE == 0 && g.N == 128) {
-      static int narrow = -1;
-      if (narrow < 0) { const char* e = getenv("VSSR_GEMM_NARROW"); narrow = e ? atoi(e) : 1; }
-      const long long tiles = (long long)ceil_div(g.M, 128) * n_models;
-      if (narrow && tiles < 2 * 148)
-        return launch_gemm_tc<64, AMODE, EPI>(g, Bnk + W_TOTAL, Bnk + 2 * W_TOTAL, W_STRIDE, n_models, st);
-    }
-    return launch_gemm_tc<BN, AMODE, EPI>(g, Bnk + W_TOTAL, Bnk + 2 * W_TOTAL, W_STRIDE, n_models, st);
+int run_gemm(GemmArgs g, const float* Bnk, int n_models, cudaStream_t st) {
+  // wave quantisation: a 128-column GEMM on ~8000 rows is 195 tiles = 1.3 waves of the 148 persistent CTAs, i.e.
+  // two rounds; with 64-column tiles it is 390 half-size tiles = three half rounds
+  if (BN == 128 && AMODE == 0 && g.N == 128) {
+    const long long tiles = (long long)ceil_div(g.M, 128) * n_models;
+    if (tiles < 2 * 148)
+      return launch_gemm_tc<64, AMODE, EPI>(g, Bnk + W_TOTAL, Bnk + 2 * W_TOTAL, W_STRIDE, n_models, st);
   }
-  return launch_gemm<BN, AMODE, EPI>(g, n_models, st);
+  return launch_gemm_tc<BN, AMODE, EPI>(g, Bnk + W_TOTAL, Bnk + 2 * W_TOTAL, W_STRIDE, n_models, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -970,11 +824,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     // F1
     g = GemmArgs{w.s[l], F, MA_F, wl + L_W1T, F, W_STRIDE, wl + L_B1, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.h1[l], F, MA_F, A, F, F, w.act};
-    if ((rc = run_gemm<128, 0, 4>(g, wl + L_W1T, F, wl + L_W1, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 4>(g, wl + L_W1, M, st))) return rc;
     // F2
     g = GemmArgs{w.act, F, MA_F, wl + L_W2T, F3, W_STRIDE, wl + L_B2, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.phi[l], F3, (long long)A * F3, A, F3, F};
-    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W2T, F3, wl + L_W2, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W2, M, st))) return rc;
     // F3: memo pass (group kernels for canonical structures, one-structure kernels for the rest), then the direct pass
     // over 1..W sender windows (accumulating in window order)
     if (staged) {
@@ -1014,17 +868,17 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     // F4
     g = GemmArgs{w.vmid[l], F, (long long)A * 3 * F, wl + L_UVT, 2 * F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  w.UV[l], 2 * F, (long long)A * 6 * F, 3 * A, 2 * F, F};
-    if ((rc = run_gemm<128, 0, 0>(g, wl + L_UVT, 2 * F, wl + L_UV, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 0>(g, wl + L_UV, M, st))) return rc;
     // F5
     VSSR_PROF(VSSR_K_ELEMWISE, st, nrm_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], A, w.cat[l]));
     // F6
     g = GemmArgs{w.cat[l], 2 * F, (long long)A * 2 * F, wl + L_W3T, F, W_STRIDE, wl + L_B3, W_STRIDE, nullptr, 0, 0,
                  nullptr, 0, w.h3[l], F, MA_F, A, F, 2 * F, w.act};
-    if ((rc = run_gemm<128, 0, 4>(g, wl + L_W3T, F, wl + L_W3, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 4>(g, wl + L_W3, M, st))) return rc;
     // F7
     g = GemmArgs{w.act, F, MA_F, wl + L_W4T, F3, W_STRIDE, wl + L_B4, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                  w.a[l], F3, (long long)A * F3, A, F3, F};
-    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W4T, F3, wl + L_W4, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 1>(g, wl + L_W4, M, st))) return rc;
     // F8
     VSSR_PROF(VSSR_K_ELEMWISE, st, update_fwd_kernel<<<ew_grid, 256, 0, st>>>(w.UV[l], w.a[l], w.cat[l], w.vmid[l], A,
                                                                            w.s[l + 1], w.v[l + 1]));
@@ -1033,7 +887,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   {
     GemmArgs g{w.s[NCONV], F, MA_F, weights + R_W5T, FH, W_STRIDE, weights + R_B5, W_STRIDE, nullptr, 0, 0, nullptr, 0,
                w.h5, FH, (long long)A * FH, A, FH, F};
-    if ((rc = run_gemm<64, 0, 1>(g, weights + R_W5T, FH, weights + R_W5, M, st))) return rc;
+    if ((rc = run_gemm<64, 0, 1>(g, weights + R_W5, M, st))) return rc;
     VSSR_PROF(VSSR_K_READOUT, st, readout_energy_kernel<<<dim3(ceil_div(A, 4), M), 128, 0, st>>>(weights, w.h5, w.evex, A, w.e_atom));
     VSSR_PROF(VSSR_K_READOUT, st, energy_reduce_kernel<<<dim3(ceil_div(n_struct, 4), M), 128, 0, st>>>(w.e_atom, atom_ptr, n_struct, A, energy));
   }
@@ -1047,7 +901,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     // ds = (dswish(h5) * w6) . W5      [A,64]x[64,128]
     GemmArgs g{w.h5, FH, (long long)A * FH, weights + R_W5, F, W_STRIDE, nullptr, 0, nullptr, 0, 0, weights + R_W6,
                W_STRIDE, w.ds, F, MA_F, A, F, FH};
-    if ((rc = run_gemm<128, 2, 0>(g, weights + R_W5, F, weights + R_W5T, M, st))) return rc;
+    if ((rc = run_gemm<128, 2, 0>(g, weights + R_W5T, M, st))) return rc;
   }
   VSSR_CUDA(cudaMemsetAsync(w.dvA, 0, (size_t)M * A * 3 * F * sizeof(float), st));
   float* dv_cur = w.dvA;
@@ -1060,17 +914,17 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     // B7: dh3 = (da . W4) * dswish(h3)
     g = GemmArgs{w.da, F3, (long long)A * F3, wl + L_W4, F, W_STRIDE, nullptr, 0, w.h3[l], F, MA_F, nullptr, 0,
                  w.dh3, F, MA_F, A, F, F3};
-    if ((rc = run_gemm<128, 0, 2>(g, wl + L_W4, F, wl + L_W4T, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 2>(g, wl + L_W4T, M, st))) return rc;
     // B6: dcat = dh3 . W3
     g = GemmArgs{w.dh3, F, MA_F, wl + L_W3, 2 * F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  w.dcat, 2 * F, (long long)A * 2 * F, A, 2 * F, F};
-    if ((rc = run_gemm<128, 0, 0>(g, wl + L_W3, 2 * F, wl + L_W3T, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 0>(g, wl + L_W3T, M, st))) return rc;
     // B5
     VSSR_PROF(VSSR_K_ELEMWISE, st, nrm_bwd_kernel<<<ew_grid, 256, 0, st>>>(w.dcat, w.cat[l], w.UV[l], A, w.ds, w.dUV));
     // B4: dv += dUV . [U;V]      [3A,256]x[256,128]
     g = GemmArgs{w.dUV, 2 * F, (long long)A * 6 * F, wl + L_UV, F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                  dv_cur, F, (long long)A * 3 * F, 3 * A, F, 2 * F};
-    if ((rc = run_gemm<128, 0, 3>(g, wl + L_UV, F, wl + L_UVT, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 3>(g, wl + L_UVT, M, st))) return rc;
     // B3
     if (staged) {
       // accum bit 0: dphi/dv_in were started by a memo pass; bit 1: so was gradp (later sender windows set both)
@@ -1115,11 +969,11 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
       // B2: dh1 = (dphi . W2) * dswish(h1)
       g = GemmArgs{w.dphi, F3, (long long)A * F3, wl + L_W2, F, W_STRIDE, nullptr, 0, w.h1[l], F, MA_F, nullptr, 0,
                    w.dh1, F, MA_F, A, F, F3};
-    if ((rc = run_gemm<128, 0, 2>(g, wl + L_W2, F, wl + L_W2T, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 2>(g, wl + L_W2T, M, st))) return rc;
       // B1: ds += dh1 . W1
       g = GemmArgs{w.dh1, F, MA_F, wl + L_W1, F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
                    w.ds, F, MA_F, A, F, F};
-    if ((rc = run_gemm<128, 0, 3>(g, wl + L_W1, F, wl + L_W1T, M, st))) return rc;
+    if ((rc = run_gemm<128, 0, 3>(g, wl + L_W1T, M, st))) return rc;
       float* t = dv_cur; dv_cur = dv_nxt; dv_nxt = t;
     }
   }

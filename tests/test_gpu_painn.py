@@ -41,7 +41,7 @@ def _compare(eng, ens, structs):
         # 1e-4 eV/A absolute; fp32 cannot hold that on the >1e3 eV/A forces of overlapping trial
         # placements, so allow 2 ulp-ish relative slack there
         ftol = F_TOL + (2e-6 * fscale if fscale > 50 else 0.0)     # scale of the structure's largest force
-        assert (np.abs(f[k] - o["forces"]) <= ftol).all(), (k, np.abs(f[k] - o["forces"]).max())
+        assert (np.abs(f[k] - o["forces"]) <= ftol).all(), (k, np.abs(f[k] - o["forces"]).max(), fscale, np.abs(o["forces"]).max())
         assert (np.abs(fs[k] - o["forces_std"]) <= ftol).all()
     return e, f
 
