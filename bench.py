@@ -300,17 +300,30 @@ def workload_config(name, args, chains, world, extra=None):
     return cfg
 
 
+# adsorbates per chain after the default burn-in, measured by the B200 arm on this workload (profiles/round2_bench*.json:
+# config.coverage): the reference arm starts its chain at the same coverage so both arms relax structures of the same size
+REFERENCE_COVERAGE = {"sto_painn": 32, "sto_pourbaix": 12}
+
+
+def reference_occupancy(name):
+    k = REFERENCE_COVERAGE.get(name, 0)
+    w = WORKLOADS[name]
+    sites = np.random.RandomState(0).choice(w["n_sites"], size=k, replace=False)
+    return [(int(s_), w["adsorbates"][i % len(w["adsorbates"])]) for i, s_ in enumerate(sites)]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     name = args.workload
     threads = os.cpu_count() or 1
+    occ = reference_occupancy(name)
     for _ in range(min(args.warmup, 1)):
-        oracle_proposals(name, 1, threads)
+        oracle_proposals(name, 1, threads, burn_occ=occ)
     n, dt, evals = 0, 0.0, 0
     for s in range(args.steps):
-        a, b, c = oracle_proposals(name, 1, threads, seed0=s)
+        a, b, c = oracle_proposals(name, 1, threads, seed0=s, burn_occ=occ)
         n, dt, evals = n + a, dt + b, evals + c
     val = n / dt
     print(json.dumps({
@@ -320,8 +333,9 @@ def run_reference(args):
         "dtype": "f32" if WORKLOADS[name]["models"] else "f64", "data": "synthetic",
         "config": workload_config(name, args, 1, 1),
         "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} single-chain relaxed proposals (1 per step, from the pristine slab), oracle port of the "
-                                   "reference path (torch-CPU physics + numpy FIRE); the reference stack itself is not installable here"},
+                         "sample": f"{n} single-chain relaxed proposals (1 per step) from a slab carrying {len(occ)} adsorbates -- the "
+                                   "coverage the B200 arm reaches after its burn-in -- oracle port of the reference path (torch-CPU "
+                                   "physics + numpy FIRE); the reference stack itself is not installable here"},
         "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "painn_atom_model_evals_per_sec": evals / dt if evals else None,
     }))
@@ -529,6 +543,22 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
         extra["painn_atom_model_evals_per_sec"] = atoms_total * (steps_relax + 1) * w["models"] * world / (dev_ms * 1e-3)
     else:
         roof = classical_roofline(breakdown, a_prof, steps_relax + 1, peaks)
+        # saturation point (SURVEY.md 8d caveat): 256 chains = 256 CTAs occupy a fraction of the 148 SMs x 2-4 resident
+        # CTAs; the same kernel on 65,536 chains (the staged batch replicated) shows what the GPU sustains
+        reps = 65536 // C
+        pl, nl, fl = staged_host[0]
+        big = engine.Batch.from_arrays(pl * reps, [to_species(zz) for zz in nl] * reps, [cell] * (C * reps), [pbc] * (C * reps), fl * reps)
+        pos0 = big.pos.clone()
+        relax_batch(big, None)               # warm-up (the relaxation works in place)
+        big.pos.copy_(pos0)
+        torch.cuda.synchronize()
+        ev0.record()
+        st_big = relax_batch(big, None)["status"]
+        ev1.record()
+        torch.cuda.synchronize()
+        extra["saturation"] = {"chains_per_gpu": C * reps, "value": C * reps / (ev0.elapsed_time(ev1) * 1e-3), "unit": "proposals/s",
+                               "ms": ev0.elapsed_time(ev1), "status_bits": int(st_big.item()),
+                               "note": "device-resident, one relax call, the burnt-in batch replicated; per-GPU figure"}
     cfg_extra = {"coverage": {**coverage, "mean_adsorbates_after_timed_region": n_ads_end},
                  "timed_region_s": {"device": round(dev_ms * 1e-3, 3), "e2e": round(e2e_ms * 1e-3, 3)}}
     if grid is not None:
@@ -717,7 +747,7 @@ def main():
                 out["workloads"].append({"config": {"workload": WORKLOADS[other]["desc"]}, "error": f"{type(exc).__name__}: {exc}"})
                 continue
             out["workloads"].append({k: o[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "dtype", "config",
-                                                       "e2e", "gpu_launches", "roofline", "kernel_breakdown_ms", "reference_published_single_chain") if k in o}
+                                                       "e2e", "gpu_launches", "roofline", "kernel_breakdown_ms", "reference_published_single_chain", "saturation") if k in o}
                                     | ({"cpu_baseline": o["cpu_baseline"]} if "cpu_baseline" in o else {}))
     if rank == 0:
         print(json.dumps(out))
