@@ -33,6 +33,7 @@ if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1":
         os.environ[_k] = str(os.cpu_count() or 1)
 
 import argparse
+import contextlib
 import json
 import subprocess
 import threading
@@ -287,7 +288,8 @@ def workload_config(name, args, chains, world, extra=None):
            "l2": "per-evaluation working set (activations ~48 KB/atom/model, >1 GB) exceeds the 126 MB L2; no explicit flush"
                  if WORKLOADS[name]["models"] else "whole relaxation is shared-memory resident; L2 is not on the path",
            "parallelism": f"chains sharded, {world} rank(s), no data-path collective",
-           "e2e_driver": f"MultiChainMC.pipeline, {max(1, args.groups)} chain group(s) per GPU; value = one batch of all chains per step"}
+           "e2e_driver": "MultiChainMC.pipeline; PaiNN: 1 chain group per GPU (default stream); classical potentials: "
+                         f"{args.groups or 4} interleaved chain groups on separate CUDA streams; value = one batch of all chains per step"}
     if WORKLOADS[name]["models"]:
         cfg["engine_options"] = {
             "filter_memo": not os.environ.get("VSSR_NO_FILTER_MEMO"),
@@ -412,13 +414,28 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
             Pending.pool[self.key].append(self.host)
             return out
 
+    # e2e driver: chain groups of MultiChainMC.pipeline.  The classical kernels are one latency-bound CTA per chain and
+    # leave most of the GPU idle at 256 chains, so their groups run on separate CUDA streams: the relaxations of the
+    # groups overlap each other AND the host-side proposal / Metropolis work (the engine holds no shared workspace).
+    # The PaiNN engine fills the GPU with one batch and owns one workspace: one group, default stream.
+    n_groups = max(1, args.groups) if (args.groups or w["models"]) else 4
+    side_streams = [torch.cuda.Stream() for _ in range(n_groups)] if (n_groups > 1 and not w["models"]) else []
+    calls = [0]
+
     def relax_fn(pos_l, num_l, fix_l):
-        b = engine.Batch.from_arrays(pos_l, [to_species(zz) for zz in num_l], [cell] * len(pos_l), [pbc] * len(pos_l), fix_l)
-        r = relax_batch(b, np.concatenate(num_l))
-        statuses.append(r["status"])              # checked once after the timed regions (no sync here)
-        io["h2d"] += b.h2d_bytes() + 8 * b.n_struct
-        io["d2h"] += r["out"].numel() * 8
-        return Pending(r["out"])
+        stream = side_streams[calls[0] % n_groups] if side_streams else None
+        calls[0] += 1
+        with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+            b = engine.Batch.from_arrays(pos_l, [to_species(zz) for zz in num_l], [cell] * len(pos_l), [pbc] * len(pos_l), fix_l)
+            r = relax_batch(b, np.concatenate(num_l))
+            statuses.append(r["status"])              # checked once after the timed regions (no sync here)
+            io["h2d"] += b.h2d_bytes() + 8 * b.n_struct
+            io["d2h"] += r["out"].numel() * 8
+            return Pending(r["out"])
+
+    def join_side_streams():
+        for s_ in side_streams:
+            torch.cuda.current_stream().wait_stream(s_)
 
     def check_statuses():
         bits = 0
@@ -440,7 +457,7 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------ burn-in (untimed) + e2e: public API, host buffers
-    pipe = drv.pipeline(n_groups=max(1, args.groups))
+    pipe = drv.pipeline(n_groups=n_groups)
     t_burn = time.perf_counter()
     for k in range(burn_in):
         pipe.advance()
@@ -465,6 +482,8 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
     ev0.record()
     for _ in range(steps):
         pipe.advance()
+    pipe.drain()                # (in-flight iterations of the pipelined groups belong to the timed steps)
+    join_side_streams()
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
@@ -708,9 +727,10 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--chains-per-gpu", type=int, default=0)
     ap.add_argument("--burn-in", type=int, default=-1, help="untimed MC steps before the timed region (default: per workload)")
-    ap.add_argument("--groups", type=int, default=1,
-                    help="interleaved chain groups of the e2e driver (MultiChainMC.pipeline); 1 = plain lock step, which is "
-                         "fastest here: the host part of a step is ~3 ms and half-size batches cost the GPU more than that")
+    ap.add_argument("--groups", type=int, default=0,
+                    help="interleaved chain groups of the e2e driver (MultiChainMC.pipeline); default: 1 for PaiNN (the host part "
+                         "of a step is ~3 ms and half-size batches cost the GPU more than that), 4 on separate streams for the "
+                         "classical potentials")
     ap.add_argument("--cpu-baseline-proposals", type=int, default=0)
     ap.add_argument("--torch-gpu-proposals", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -765,7 +765,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const bool memo = staged && fc.n0 > 0 && sm_bwdm <= kSmemCap && sm_fwd <= kSmemCap;
   const bool constrained = memo && want_constrained;   // no dE/dx wanted on frozen atoms
   constexpr int n_chunks = 2;   // CTAs per (structure, feature half, model) in the direct pass
-  const dim3 v2_grid(n_struct * n_chunks, F / MSG_FC, M);
+  const dim3 v2_grid((F / MSG_FC) * M, n_struct * n_chunks);   // (half, model) fastest: see message_fwd_v2
   const dim3 memo_grid(n_struct, F / MSG_FC, M);
   // group kernels: G canonical structures per CTA (as many as fit in shared memory), no ring
   constexpr int G_FWD0 = 4, T_FWD0 = 512, G_FWD = 2, T_FWD = 832, G_STATE = 2, T_STATE = 512;

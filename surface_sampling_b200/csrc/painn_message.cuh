@@ -92,14 +92,18 @@ __device__ __forceinline__ SenderWindow sender_window(int n, int cap, int win) {
   w.hi = min(n, w.lo + wsz);
   return w;
 }
-// index of the first direct record of a row whose local sender index is >= L (warp-uniform)
-__device__ __forceinline__ int first_sender_at_least(const float* __restrict__ rec0, int ne, int a0, int L) {
-  int lo = 0, hi = ne;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__float_as_int(__ldg(rec0 + (long long)mid * REC + REC_EJ)) - a0 < L) lo = mid + 1; else hi = mid;
+// [e_lo, e_hi) = the direct records of a row whose local sender index lies in [lo, hi).  Records are sorted by sender,
+// so the bounds are counts: every lane reads the sender of one record (32 independent loads in flight, one memory
+// latency per 32 edges instead of a chain of dependent probes) and the warp counts by ballot.  Warp-uniform result.
+__device__ __forceinline__ void window_slice(const float* __restrict__ rec0, int ne, int a0, int lo, int hi, int lane,
+                                             int& e_lo, int& e_hi) {
+  e_lo = 0; e_hi = 0;
+  for (int base = 0; base < ne; base += 32) {
+    const int e = base + lane;
+    const int jl = e < ne ? __float_as_int(__ldg(rec0 + (long long)e * REC + REC_EJ)) - a0 : 0x7fffffff;
+    e_lo += __popc(__ballot_sync(0xffffffffu, jl < lo));
+    e_hi += __popc(__ballot_sync(0xffffffffu, jl < hi));
   }
-  return lo;
 }
 
 // Rows (receivers) are handed to warps dynamically, most expensive first (row_order_kernel sorts each
@@ -343,8 +347,10 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* ring = smem_all + warp * MSG_STAGES_FWD * REC;
   float* smem = smem_all + MSG_WARPS * MSG_STAGES_FWD * REC;
-  const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
-  const int h = blockIdx.y, m = blockIdx.z;
+  // grid = (halves x models, structures x chunks): the CTAs that stream the SAME edge records are neighbours in launch
+  // order and run together, so the records are read from DRAM once and served to the other five from L2
+  const int b = blockIdx.y / n_chunks, ch = blockIdx.y % n_chunks;
+  const int h = blockIdx.x % (F / MSG_FC), m = blockIdx.x / (F / MSG_FC);
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
   const long long mA = (long long)m * n_atoms;
   const SenderWindow wn = sender_window(n, cap_atoms, win);
@@ -380,7 +386,8 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
     const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
     int ne = __ldg(nvalid + i);
     if (!whole) {                     // the slice of this row whose senders lie in the window
-      const int e_lo = first_sender_at_least(rec0, ne, a0, wn.lo), e_hi = first_sender_at_least(rec0, ne, a0, wn.hi);
+      int e_lo, e_hi;
+      window_slice(rec0, ne, a0, wn.lo, wn.hi, lane, e_lo, e_hi);
       rec0 += (long long)e_lo * REC;
       ne = e_hi - e_lo;
     }
@@ -726,8 +733,10 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* ring = smem_all + warp * MSG_STAGES * REC;
   float* smem = smem_all + MSG_WARPS * MSG_STAGES * REC;
-  const int b = blockIdx.x / n_chunks, ch = blockIdx.x % n_chunks;
-  const int h = blockIdx.y, m = blockIdx.z;
+  // grid = (halves x models, structures x chunks): the CTAs that stream the SAME edge records are neighbours in launch
+  // order and run together, so the records are read from DRAM once and served to the other five from L2
+  const int b = blockIdx.y / n_chunks, ch = blockIdx.y % n_chunks;
+  const int h = blockIdx.x % (F / MSG_FC), m = blockIdx.x / (F / MSG_FC);
   const int a0 = __ldg(atom_ptr + b), n = __ldg(atom_ptr + b + 1) - a0;
   const long long mA = (long long)m * n_atoms;
   const SenderWindow wn = sender_window(n, cap_atoms, win);
@@ -765,7 +774,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
     int ne = __ldg(nvalid + i);
     if (!whole) {
-      const int e_lo = first_sender_at_least(rec0, ne, a0, wn.lo), e_hi = first_sender_at_least(rec0, ne, a0, wn.hi);
+      int e_lo, e_hi;
+      window_slice(rec0, ne, a0, wn.lo, wn.hi, lane, e_lo, e_hi);
       rec0 += (long long)e_lo * REC;
       ne = e_hi - e_lo;
     }

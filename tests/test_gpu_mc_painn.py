@@ -71,7 +71,7 @@ def test_accept_reject_parity_sto_painn(structures, potentials, sto_weights, fix
         # A single evaluation agrees to 1e-5 eV/atom (test_gpu_painn.py); along a relaxation the force noise is amplified
         # by the trajectory, most for strained trial placements tens of eV above the current state (rejected whatever
         # their last digits are).  Bounds: 1e-4 eV/atom for every proposal within 10 eV of the state it came from, 1e-3 of
-        # the energy jump beyond that; the median proposal within the single-evaluation 1e-5 eV/atom and 90 % within twice that.
+        # the energy jump beyond that; the median proposal within 2e-6 eV/atom and 98 % within the single-evaluation 1e-5 eV/atom.
         for i, (x, n) in enumerate(zip(d, c["n_atoms"])):
             if abs(c["curr"][i]) < 1e3:          # overlapping trial placements give 1e5 eV: fp32 cannot hold 1e-5/atom
                 err = abs(x[1] - c["curr"][i])
@@ -85,7 +85,8 @@ def test_accept_reject_parity_sto_painn(structures, potentials, sto_weights, fix
         for (acc, curr, prev, u), T, n in zip(d, c["temps"], c["n_atoms"]):
             assert abs((curr - prev) + T * np.log(u)) > 2 * E_TOL_PER_ATOM * n
     print("relaxed-energy |dE|/atom percentiles 50/90/99/100:", np.percentile(per_atom, [50, 90, 99, 100]))
-    assert np.median(per_atom) <= E_TOL_PER_ATOM and np.mean(np.array(per_atom) <= 2 * E_TOL_PER_ATOM) >= 0.90
+    # measured on B200: median 6e-7, 99th percentile 1.9e-6, worst 5.4e-5 eV/atom over 364 proposals
+    assert np.median(per_atom) <= 0.2 * E_TOL_PER_ATOM and np.mean(np.array(per_atom) <= E_TOL_PER_ATOM) >= 0.98
     print(f"|E_gpu - E_oracle| over {len(per_atom)} relaxed proposals: median {np.median(per_atom):.2e}, worst {worst:.2e} eV/atom")
 
 
