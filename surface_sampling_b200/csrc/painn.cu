@@ -742,7 +742,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const int nmax = max_atoms_per_struct;
   const FilterCacheView fc = cache_view(filter_cache, n_models, fc_n0, fc_e_cap0);
   const bool staged = nmax > 0;
-  const size_t kSmemCap = 226 * 1024;   // 227 KB per SM minus the kernels' few bytes of static shared memory
+  const size_t kSmemCap = 223 * 1024;   // 227 KB per SM minus the kernels' static shared memory (row table: 3 KB)
   // direct pass: staged rows of one window + the per-warp record rings.  The first-layer forward runs two CTAs per SM.
   constexpr int B_FWD0 = MsgFwdLayout<true>::PER * 4, B_FWD = MsgFwdLayout<false>::PER * 4;
   constexpr int B_BWD0 = MsgBwdLayout<true>::PER * 4, B_BWD = MsgBwdLayout<false>::PER * 4;

@@ -82,6 +82,24 @@ __device__ __forceinline__ void wait_record() {
 // records of a row are sorted by sender (CSR order survives the compaction), so a window is a contiguous slice of the
 // row, found by binary search.  W depends on the structure's own atom count only, never on the rest of the batch, and
 // windows are applied in ascending order: results stay bitwise batch-invariant.  n <= cap is the old single launch.
+// Row table of a direct-pass CTA: (local atom, first record, record count) of the structure's rows in LPT order, read
+// once by all threads while the rows are being staged -- a warp that grabs a row then starts its record ring at once
+// instead of walking three dependent global loads (order -> rowptr -> nvalid) with 8 warps per SM to hide them.
+constexpr int MSG_MAXROWS = 256;   // larger structures read the tail of the table from global memory
+struct RowTable { int il[MSG_MAXROWS], e0[MSG_MAXROWS], ne[MSG_MAXROWS]; };
+__device__ __forceinline__ void row_table_fill(RowTable& rt, const int32_t* __restrict__ order, const int32_t* __restrict__ rowptr,
+                                               const int32_t* __restrict__ nvalid, int a0, int n, int tid, int nthreads) {
+  for (int t = tid; t < n && t < MSG_MAXROWS; t += nthreads) {
+    const int il = __ldg(order + a0 + t);
+    rt.il[t] = il; rt.e0[t] = __ldg(rowptr + a0 + il); rt.ne[t] = __ldg(nvalid + a0 + il);
+  }
+}
+__device__ __forceinline__ void row_table_get(const RowTable& rt, const int32_t* __restrict__ order, const int32_t* __restrict__ rowptr,
+                                              const int32_t* __restrict__ nvalid, int a0, int t, int& il, int& e0, int& ne) {
+  if (t < MSG_MAXROWS) { il = rt.il[t]; e0 = rt.e0[t]; ne = rt.ne[t]; }
+  else { il = __ldg(order + a0 + t); e0 = __ldg(rowptr + a0 + il); ne = __ldg(nvalid + a0 + il); }
+}
+
 struct SenderWindow { int lo, hi; bool live; };
 __device__ __forceinline__ SenderWindow sender_window(int n, int cap, int win) {
   const int W = (n + cap - 1) / cap;
@@ -366,6 +384,8 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
   stage_rows(smem, PER, 0, phi + (long long)wn.lo * F3, F3, F, 3, wn.hi - wn.lo, tid, MSG_THREADS);
   if (!FIRST) stage_rows(smem, PER, 3 * MSG_FC, v_in + (long long)wn.lo * 3 * F, 3 * F, F, 3, wn.hi - wn.lo, tid, MSG_THREADS);
   const int sbase = a0 + wn.lo;                  // global index of the first staged atom
+  __shared__ RowTable rt;
+  row_table_fill(rt, order, rowptr, nvalid, a0, n, tid, MSG_THREADS);
 
   const int f0 = h * MSG_FC + 2 * lane;  // first feature of this lane's pair
   const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
@@ -381,10 +401,9 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
   __syncthreads();
 
   for (int t = ch + n_chunks * next_row(&row_ctr, lane); t < n; t = ch + n_chunks * next_row(&row_ctr, lane)) {
-    const int il = __ldg(order + a0 + t);
-    const int i = a0 + il;
-    const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
-    int ne = __ldg(nvalid + i);
+    int il, e0, ne;
+    row_table_get(rt, order, rowptr, nvalid, a0, t, il, e0, ne);
+    const float* rec0 = erec + (long long)e0 * REC;
     if (!whole) {                     // the slice of this row whose senders lie in the window
       int e_lo, e_hi;
       window_slice(rec0, ne, a0, wn.lo, wn.hi, lane, e_lo, e_hi);
@@ -754,6 +773,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
   bwd_stage<FIRST>(smem, phi + (long long)wn.lo * F3, FIRST ? v_in : v_in + (long long)wn.lo * 3 * F, ds + (long long)wn.lo * F,
                    dv + (long long)wn.lo * 3 * F, wn.hi - wn.lo, tid, MSG_THREADS);
   const int sbase = a0 + wn.lo;
+  __shared__ RowTable rt;
+  row_table_fill(rt, order, rowptr, nvalid, a0, n, tid, MSG_THREADS);
 
   const int f0 = h * MSG_FC + 2 * lane;
   const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
@@ -769,10 +790,10 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
   __syncthreads();
 
   for (int t = ch + n_chunks * next_row(&row_ctr, lane); t < n; t = ch + n_chunks * next_row(&row_ctr, lane)) {
-    const int il = __ldg(order + a0 + t);
+    int il, e0, ne;
+    row_table_get(rt, order, rowptr, nvalid, a0, t, il, e0, ne);
     const int i = a0 + il;
-    const float* rec0 = erec + (long long)__ldg(rowptr + i) * REC;
-    int ne = __ldg(nvalid + i);
+    const float* rec0 = erec + (long long)e0 * REC;
     if (!whole) {
       int e_lo, e_hi;
       window_slice(rec0, ne, a0, wn.lo, wn.hi, lane, e_lo, e_hi);
