@@ -304,7 +304,7 @@ def workload_config(name, args, chains, world, extra=None):
 
 # adsorbates per chain after the default burn-in, measured by the B200 arm on this workload (profiles/round2_bench*.json:
 # config.coverage): the reference arm starts its chain at the same coverage so both arms relax structures of the same size
-REFERENCE_COVERAGE = {"sto_painn": 32, "sto_pourbaix": 12}
+REFERENCE_COVERAGE = {"sto_painn": 32, "sto_pourbaix": 0}
 
 
 def reference_occupancy(name):

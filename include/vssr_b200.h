@@ -80,9 +80,9 @@ int vssr_painn_energy_grad(const float* weights, int32_t n_models,
                            const float* pos /*[A,3]*/, const int32_t* z /*[A]*/,
                            const int32_t* atom_ptr, const float* cell, int32_t n_struct,
                            int32_t n_atoms,
-                           int32_t max_atoms_per_struct /* host-known max of atom_ptr[b+1]-atom_ptr[b];
-                              selects the shared-memory staged message kernels (<= 90 atoms); 0 = unknown
-                              -> global-gather kernels */,
+                           int32_t max_atoms_per_struct /* host-known max of atom_ptr[b+1]-atom_ptr[b] (> 0): sizes the
+                              shared-memory staging of the message kernels; structures beyond one staging area are
+                              covered by several sender-window launches */,
                            const int32_t* rowptr, const int32_t* col,
                            const int8_t* shift, int64_t e_cap, float cutoff,
                            const void* filter_cache /* from vssr_painn_filter_cache_build, or NULL */,

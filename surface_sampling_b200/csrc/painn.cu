@@ -257,82 +257,6 @@ __global__ void embed_kernel(const float* __restrict__ weights, const int32_t* _
   reinterpret_cast<float4*>(s0 + (long long)m * n_atoms * F)[idx] = emb[zz * (F / 4) + f4];
 }
 
-// ------------------------------------------------------------------------------------------
-// F3: message passing, forward.  grid (ceil(A/APB), M), 128 threads (thread = feature f).
-// ------------------------------------------------------------------------------------------
-constexpr int MSG_APB = 4;
-
-template <bool FIRST>
-__global__ void __launch_bounds__(128) message_fwd_kernel(
-    const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ nvalid, const float* __restrict__ erec, const float* __restrict__ phi,
-    const float* __restrict__ s_in, const float* __restrict__ v_in, float* __restrict__ cat,
-    float* __restrict__ v_mid) {
-  const int m = blockIdx.y, f = threadIdx.x;
-  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
-  float wd0[NRBF], wd1[NRBF], wd2[NRBF];
-#pragma unroll
-  for (int n = 0; n < NRBF; ++n) {
-    wd0[n] = __ldg(wl + L_WDT + n * F3 + f);
-    wd1[n] = __ldg(wl + L_WDT + n * F3 + F + f);
-    wd2[n] = __ldg(wl + L_WDT + n * F3 + 2 * F + f);
-  }
-  const float bd0 = __ldg(wl + L_BD + f), bd1 = __ldg(wl + L_BD + F + f), bd2 = __ldg(wl + L_BD + 2 * F + f);
-  const long long mA = (long long)m * n_atoms;
-  phi += mA * F3; s_in += mA * F; cat += mA * 2 * F; v_mid += mA * 3 * F;
-  if (!FIRST) v_in += mA * 3 * F;
-
-  const int i_end = min(n_atoms, (int)(blockIdx.x + 1) * MSG_APB);
-  for (int i = blockIdx.x * MSG_APB; i < i_end; ++i) {
-    const long long e0 = __ldg(rowptr + i), e1 = e0 + __ldg(nvalid + i);
-    float ds = 0.f, dvx = 0.f, dvy = 0.f, dvz = 0.f;
-    for (long long e = e0; e < e1; ++e) {
-      const float* rec = erec + e * REC;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(rec));
-      const int j = __float_as_int(__ldg(rec + REC_EJ));
-      const float p0 = __ldg(phi + (long long)j * F3 + f);
-      const float p1 = __ldg(phi + (long long)j * F3 + F + f);
-      const float p2 = __ldg(phi + (long long)j * F3 + 2 * F + f);
-      float vjx = 0.f, vjy = 0.f, vjz = 0.f;
-      if (!FIRST) {
-        vjx = __ldg(v_in + (long long)j * 3 * F + f);
-        vjy = __ldg(v_in + (long long)j * 3 * F + F + f);
-        vjz = __ldg(v_in + (long long)j * 3 * F + 2 * F + f);
-      }
-      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
-      float rr[NRBF];
-#pragma unroll
-      for (int q = 0; q < NRBF / 2; ++q) {
-        const float4 t = __ldg(r4 + q);   // (r,r,r',r') duplicated pairs
-        rr[2 * q] = t.x; rr[2 * q + 1] = t.z;
-      }
-      const float env = __ldg(r4 + 10).x;
-      float w0 = bd0 * env, w1 = bd1 * env, w2 = bd2 * env;
-#pragma unroll
-      for (int n = 0; n < NRBF; ++n) {
-        w0 = fmaf(wd0[n], rr[n], w0);
-        w1 = fmaf(wd1[n], rr[n], w1);
-        w2 = fmaf(wd2[n], rr[n], w2);
-      }
-      const float x0 = p0 * w0, x1 = p1 * w1, x2 = p2 * w2;
-      ds += x1;
-      dvx += x2 * g.x; dvy += x2 * g.y; dvz += x2 * g.z;
-      if (!FIRST) { dvx = fmaf(x0, vjx, dvx); dvy = fmaf(x0, vjy, dvy); dvz = fmaf(x0, vjz, dvz); }
-    }
-    const float s0 = __ldg(s_in + (long long)i * F + f);
-    cat[(long long)i * 2 * F + f] = s0 + ds;
-    float vx = dvx, vy = dvy, vz = dvz;
-    if (!FIRST) {
-      vx += __ldg(v_in + (long long)i * 3 * F + f);
-      vy += __ldg(v_in + (long long)i * 3 * F + F + f);
-      vz += __ldg(v_in + (long long)i * 3 * F + 2 * F + f);
-    }
-    v_mid[(long long)i * 3 * F + f] = vx;
-    v_mid[(long long)i * 3 * F + F + f] = vy;
-    v_mid[(long long)i * 3 * F + 2 * F + f] = vz;
-  }
-}
-
 // F5: cat[a][128+f] = sqrt(sum_c (Vv[c][f]^2 + 1e-15))
 __global__ void nrm_kernel(const float* __restrict__ UV, int n_atoms, float* __restrict__ cat) {
   const int m = blockIdx.y;
@@ -446,129 +370,6 @@ __global__ void nrm_bwd_kernel(const float* __restrict__ dcat, const float* __re
   du[F + f] += t * uv[F + f];
   du[3 * F + f] += t * uv[3 * F + f];
   du[5 * F + f] += t * uv[5 * F + f];
-}
-
-// ------------------------------------------------------------------------------------------
-// B3: message passing, backward (gather over receiver row; edge A = i<-j, edge B = j<-i).
-// Outputs: dphi[i] (skipped for the first layer), dv_in[i] = dv_mid[i] + sender terms (skipped
-// for the first layer), grad[m][i] += position gradient.
-// ------------------------------------------------------------------------------------------
-template <bool FIRST>
-__global__ void __launch_bounds__(128) message_bwd_kernel(
-    const float* __restrict__ weights, int layer, int n_atoms, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ nvalid, const float* __restrict__ erec, const float* __restrict__ phi,
-    const float* __restrict__ v_in,
-    const float* __restrict__ ds, const float* __restrict__ dv, float* __restrict__ dphi, float* __restrict__ dv_in,
-    float* __restrict__ grad) {
-  __shared__ float red[4][3];
-  const int m = blockIdx.y, f = threadIdx.x, lane = f & 31, wid = f >> 5;
-  const float* __restrict__ wl = weights + (long long)m * W_STRIDE + W_LAYER0 + (long long)layer * L_SIZE;
-  float wd0[NRBF], wd1[NRBF], wd2[NRBF];
-#pragma unroll
-  for (int n = 0; n < NRBF; ++n) {
-    wd0[n] = __ldg(wl + L_WDT + n * F3 + f);
-    wd1[n] = __ldg(wl + L_WDT + n * F3 + F + f);
-    wd2[n] = __ldg(wl + L_WDT + n * F3 + 2 * F + f);
-  }
-  const float bd0 = __ldg(wl + L_BD + f), bd1 = __ldg(wl + L_BD + F + f), bd2 = __ldg(wl + L_BD + 2 * F + f);
-  const long long mA = (long long)m * n_atoms;
-  phi += mA * F3; ds += mA * F; dv += mA * 3 * F; grad += mA * 3;
-  if (!FIRST) { v_in += mA * 3 * F; dphi += mA * F3; dv_in += mA * 3 * F; }
-
-  const int i_end = min(n_atoms, (int)(blockIdx.x + 1) * MSG_APB);
-  for (int i = blockIdx.x * MSG_APB; i < i_end; ++i) {
-    const long long e0 = __ldg(rowptr + i), e1 = e0 + __ldg(nvalid + i);
-    const float gsi = __ldg(ds + (long long)i * F + f);
-    const float gvix = __ldg(dv + (long long)i * 3 * F + f);
-    const float gviy = __ldg(dv + (long long)i * 3 * F + F + f);
-    const float gviz = __ldg(dv + (long long)i * 3 * F + 2 * F + f);
-    const float pi0 = __ldg(phi + (long long)i * F3 + f);
-    const float pi1 = __ldg(phi + (long long)i * F3 + F + f);
-    const float pi2 = __ldg(phi + (long long)i * F3 + 2 * F + f);
-    float vix = 0.f, viy = 0.f, viz = 0.f;
-    if (!FIRST) {
-      vix = __ldg(v_in + (long long)i * 3 * F + f);
-      viy = __ldg(v_in + (long long)i * 3 * F + F + f);
-      viz = __ldg(v_in + (long long)i * 3 * F + 2 * F + f);
-    }
-    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;        // dphi_i
-    float dvx = 0.f, dvy = 0.f, dvz = 0.f;        // sender-side dv_in
-    float gx = 0.f, gy = 0.f, gz = 0.f;           // per-feature partial of dE/dx_i
-    for (long long e = e0; e < e1; ++e) {
-      const float* rec = erec + e * REC;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(rec));
-      const int j = __float_as_int(__ldg(rec + REC_EJ));
-      const float pj0 = __ldg(phi + (long long)j * F3 + f);
-      const float pj1 = __ldg(phi + (long long)j * F3 + F + f);
-      const float pj2 = __ldg(phi + (long long)j * F3 + 2 * F + f);
-      const float gsj = __ldg(ds + (long long)j * F + f);
-      const float gvjx = __ldg(dv + (long long)j * 3 * F + f);
-      const float gvjy = __ldg(dv + (long long)j * 3 * F + F + f);
-      const float gvjz = __ldg(dv + (long long)j * 3 * F + 2 * F + f);
-      float vjx = 0.f, vjy = 0.f, vjz = 0.f;
-      if (!FIRST) {
-        vjx = __ldg(v_in + (long long)j * 3 * F + f);
-        vjy = __ldg(v_in + (long long)j * 3 * F + F + f);
-        vjz = __ldg(v_in + (long long)j * 3 * F + 2 * F + f);
-      }
-      const float4* r4 = reinterpret_cast<const float4*>(rec + REC_RE);
-      const float4* d4 = reinterpret_cast<const float4*>(rec + REC_DRE);
-      float rr[NRBF], dr[NRBF];
-#pragma unroll
-      for (int q = 0; q < NRBF / 2; ++q) {
-        const float4 t = __ldg(r4 + q);
-        const float4 u = __ldg(d4 + q);
-        rr[2 * q] = t.x; rr[2 * q + 1] = t.z;
-        dr[2 * q] = u.x; dr[2 * q + 1] = u.z;
-      }
-      const float4 ev = __ldg(r4 + 10);
-      const float env = ev.x, denv = ev.z;
-      float w0 = bd0 * env, w1 = bd1 * env, w2 = bd2 * env;
-      float q0 = bd0 * denv, q1 = bd1 * denv, q2 = bd2 * denv;
-#pragma unroll
-      for (int n = 0; n < NRBF; ++n) {
-        w0 = fmaf(wd0[n], rr[n], w0); w1 = fmaf(wd1[n], rr[n], w1); w2 = fmaf(wd2[n], rr[n], w2);
-        q0 = fmaf(wd0[n], dr[n], q0); q1 = fmaf(wd1[n], dr[n], q1); q2 = fmaf(wd2[n], dr[n], q2);
-      }
-      // edge A: i receives from j
-      const float dxA1 = gsi;
-      const float dxA2 = gvix * g.x + gviy * g.y + gviz * g.z;
-      const float dxA0 = FIRST ? 0.f : (gvix * vjx + gviy * vjy + gviz * vjz);
-      // edge B: j receives from i (unit negated)
-      const float dxB1 = gsj;
-      const float dxB2 = -(gvjx * g.x + gvjy * g.y + gvjz * g.z);
-      const float dxB0 = FIRST ? 0.f : (gvjx * vix + gvjy * viy + gvjz * viz);
-      if (!FIRST) {
-        dp0 = fmaf(dxB0, w0, dp0); dp1 = fmaf(dxB1, w1, dp1); dp2 = fmaf(dxB2, w2, dp2);
-        const float t = pi0 * w0;
-        dvx = fmaf(t, gvjx, dvx); dvy = fmaf(t, gvjy, dvy); dvz = fmaf(t, gvjz, dvz);
-      }
-      // d(filter) chain: dd = sum_k (dwA_k + dwB_k) q_k
-      const float dd = (dxA0 * pj0 + dxB0 * pi0) * q0 + (dxA1 * pj1 + dxB1 * pi1) * q1 + (dxA2 * pj2 + dxB2 * pi2) * q2;
-      // unit-vector chain: delta = duA - duB,  duA = gv_i * (phi_j2 w2), duB = gv_j * (phi_i2 w2)
-      const float ta = pj2 * w2, tb = pi2 * w2;
-      const float ex = gvix * ta - gvjx * tb, ey = gviy * ta - gvjy * tb, ez = gviz * ta - gvjz * tb;
-      const float proj = ex * g.x + ey * g.y + ez * g.z;
-      const float inv_d = 1.0f / g.w;
-      gx -= dd * g.x + (ex - proj * g.x) * inv_d;
-      gy -= dd * g.y + (ey - proj * g.y) * inv_d;
-      gz -= dd * g.z + (ez - proj * g.z) * inv_d;
-    }
-    if (!FIRST) {
-      dphi[(long long)i * F3 + f] = dp0;
-      dphi[(long long)i * F3 + F + f] = dp1;
-      dphi[(long long)i * F3 + 2 * F + f] = dp2;
-      dv_in[(long long)i * 3 * F + f] = gvix + dvx;
-      dv_in[(long long)i * 3 * F + F + f] = gviy + dvy;
-      dv_in[(long long)i * 3 * F + 2 * F + f] = gviz + dvz;
-    }
-    // fixed-order block reduction of the position gradient over the 128 features
-    gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
-    __syncthreads();
-    if (lane == 0) { red[wid][0] = gx; red[wid][1] = gy; red[wid][2] = gz; }
-    __syncthreads();
-    if (f < 3) grad[3 * i + f] += (red[0][f] + red[1][f]) + (red[2][f] + red[3][f]);
-  }
 }
 
 #include "painn_message.cuh"
@@ -734,14 +535,14 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const int M = n_models, A = n_atoms;
   const long long MA_F = (long long)A * F;  // per-model stride of [A,128]
   const dim3 ew_grid(ceil_div((long long)A * F, 256), M);
-  const dim3 msg_grid(ceil_div(A, MSG_APB), M);
 
   // message kernels: shared-memory staged FFMA2 kernels.  A CTA of the direct pass stages at most cap_* atoms; larger
   // structures are covered by several launches over "sender windows" (painn_message.cuh: sender_window), so there is
-  // no atom-count cliff any more.  The global-gather kernels only serve callers that do not know max_atoms_per_struct.
+  // no atom-count cliff (round 1's global-gather fallback kernels are gone).
   const int nmax = max_atoms_per_struct;
+  if (nmax <= 0) return VSSR_ERR_ARG;   // the caller knows its largest structure (sizes the staging areas)
   const FilterCacheView fc = cache_view(filter_cache, n_models, fc_n0, fc_e_cap0);
-  const bool staged = nmax > 0;
+  constexpr bool staged = true;
   const size_t kSmemCap = 223 * 1024;   // 227 KB per SM minus the kernels' static shared memory (row table: 3 KB)
   // direct pass: staged rows of one window + the per-warp record rings.  The first-layer forward runs two CTAs per SM.
   constexpr int B_FWD0 = MsgFwdLayout<true>::PER * 4, B_FWD = MsgFwdLayout<false>::PER * 4;
@@ -857,13 +658,6 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
               weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
               w.cat[l], w.vmid[l], memo ? 1 : 0, cap_fwd, win));
       }
-    } else {
-      if (l == 0)
-        VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<true><<<msg_grid, 128, 0, st>>>(
-            weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l]));
-      else
-        VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_kernel<false><<<msg_grid, 128, 0, st>>>(
-            weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l]));
     }
     // F4
     g = GemmArgs{w.vmid[l], F, (long long)A * 3 * F, wl + L_UVT, 2 * F, W_STRIDE, nullptr, 0, nullptr, 0, 0, nullptr, 0,
@@ -955,15 +749,6 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
               cap_bwd, win));
       }
       VSSR_PROF(VSSR_K_ELEMWISE, st, grad_accum_kernel<<<dim3(ceil_div(3 * A, 256), M), 256, 0, st>>>(w.gradp, 3 * A, grad));
-    } else {
-      if (l == 0)
-        VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<true><<<msg_grid, 128, 0, st>>>(
-            weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], nullptr, w.ds, dv_cur, nullptr,
-            nullptr, grad));
-      else
-        VSSR_PROF(VSSR_K_MSG_BWD, st, message_bwd_kernel<false><<<msg_grid, 128, 0, st>>>(
-            weights, l, A, rowptr, w.nvalid, w.erec, w.phi[l], w.v[l], w.ds, dv_cur, w.dphi, dv_nxt,
-            grad));
     }
     if (l > 0) {
       // B2: dh1 = (dphi . W2) * dswish(h1)

@@ -507,6 +507,8 @@ class MultiChainMC:
         from pathlib import Path
 
         from . import io
+        if self.cell is None:
+            raise ValueError("save_structures needs the cell: MultiChainMC(..., cell=..., pbc=...)")
         sel = [self.chains[k] for k in chains]
         arrs = [c.arrays() for c in sel]
         fix = [np.concatenate([self.fixed0, np.zeros(len(z) - len(self.fixed0), dtype=bool)]) for _, z in arrs]
