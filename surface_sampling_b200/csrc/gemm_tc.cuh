@@ -139,7 +139,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BN, int AMODE, int EPI>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc_ws_kernel(TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the shared array (an integer round trip would lose the shared address space: generic LD/ST)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   __shared__ __align__(8) uint64_t full_bar[WS_STAGES], empty_bar[WS_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -379,7 +380,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tc_tma_kernel(TcArgs p, co
                                                                     const __grid_constant__ CUtensorMap tmC2,
                                                                     const __grid_constant__ CUtensorMap tmAux) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the shared array (an integer round trip would lose the shared address space: generic LD/ST)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   __shared__ __align__(8) uint64_t full_bar[TM_STAGES], empty_bar[TM_STAGES], araw_bar[TM_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ __align__(8) uint64_t aux_bar[4];

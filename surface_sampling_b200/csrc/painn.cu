@@ -373,6 +373,7 @@ __global__ void nrm_bwd_kernel(const float* __restrict__ dcat, const float* __re
 }
 
 #include "painn_message.cuh"
+#include "painn_message_tc.cuh"
 
 // ---- filter memo construction (one-time per framework + weights) ----
 struct CacheBlob {
@@ -565,6 +566,14 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   // runs without the memo
   const bool memo = staged && fc.n0 > 0 && sm_bwdm <= kSmemCap && sm_fwd <= kSmemCap;
   const bool constrained = memo && want_constrained;   // no dE/dx wanted on frozen atoms
+  // VSSR_MSG_TC=1: direct FORWARD pass with the radial filter on the tensor core (painn_message_tc.cuh).  Experimental
+  // and OFF by default: parity-green but slower than message_fwd_v2 (profiles/round2_notes.md section 4)
+  static int tc_env = -1;
+  if (tc_env < 0) { const char* e = getenv("VSSR_MSG_TC"); tc_env = (e && atoi(e) > 0) ? 1 : 0; }
+  const size_t tc_rows_budget = 227 * 1024 - 6144 /* static shared memory of the kernel */ - 1024 - mtc::FIXED_BYTES;
+  const int cap_tc0 = (int)(tc_rows_budget / B_FWD0), cap_tc = (int)(tc_rows_budget / B_FWD);
+  const bool tc_fwd = tc_env != 0 && nmax <= 2 * mtc::MAXROWS;
+  const size_t smem_tc0 = mtc::fwd_smem_bytes(rows_of(cap_tc0), true), smem_tc = mtc::fwd_smem_bytes(rows_of(cap_tc), false);
   constexpr int n_chunks = 2;   // CTAs per (structure, feature half, model) in the direct pass
   const dim3 v2_grid((F / MSG_FC) * M, n_struct * n_chunks);   // (half, model) fastest: see message_fwd_v2
   const dim3 memo_grid(n_struct, F / MSG_FC, M);
@@ -582,7 +591,7 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
   const bool pair_state = group_on && constrained && n_struct >= G_STATE && ga_state > 0;
   if (staged) {
     // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: cache what was configured per device
-    static size_t cfg_dev[64][12] = {};
+    static size_t cfg_dev[64][16] = {};
     int dev = 0;
     VSSR_CUDA(cudaGetDevice(&dev));
     size_t* cfg = cfg_dev[dev & 63];
@@ -598,6 +607,10 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
     if ((rc0 = want(1, (const void*)message_fwd_v2<false>, smem_fwd))) return rc0;
     if ((rc0 = want(2, (const void*)message_bwd_v2<true>, smem_bwd0))) return rc0;
     if ((rc0 = want(3, (const void*)message_bwd_v2<false>, smem_bwd))) return rc0;
+    if (tc_fwd) {
+      if ((rc0 = want(12, (const void*)mtc::message_fwd_tc<true>, smem_tc0))) return rc0;
+      if ((rc0 = want(13, (const void*)mtc::message_fwd_tc<false>, smem_tc))) return rc0;
+    }
     if (memo) {
       if ((rc0 = want(4, (const void*)message_fwd_memo<true>, sm_fwd0))) return rc0;
       if ((rc0 = want(5, (const void*)message_fwd_memo<false>, sm_fwd))) return rc0;
@@ -641,6 +654,12 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<true><<<memo_grid, MEMO_THREADS_FWD, sm_fwd0, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], nullptr, w.cat[l], w.vmid[l],
               pair_fwd0 ? w.canonical : nullptr, n_struct, G_FWD0, ga_fwd0));
+        if (tc_fwd)
+          for (int win = 0; win < windows_of(cap_tc0); ++win)
+            VSSR_PROF(VSSR_K_MSG_FWD, st, mtc::message_fwd_tc<true><<<v2_grid, mtc::THREADS, smem_tc0, st>>>(
+                weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
+                w.cat[l], w.vmid[l], memo ? 1 : 0, cap_tc0, win));
+        else
         for (int win = 0; win < windows_of(cap_fwd0); ++win)
           VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<true><<<v2_grid, MSG_THREADS, smem_fwd0, st>>>(
               weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], nullptr,
@@ -653,6 +672,12 @@ extern "C" int vssr_painn_energy_grad(const float* weights, int32_t n_models, co
           VSSR_PROF(VSSR_K_MSG_FWD_MEMO, st, message_fwd_memo<false><<<memo_grid, MEMO_THREADS_FWD, sm_fwd, st>>>(
               l, A, atom_ptr, rowptr, w.order_m, w.nmemo, w.mrec, fc, w.phi[l], w.s[l], w.v[l], w.cat[l], w.vmid[l],
               pair_fwd ? w.canonical : nullptr, n_struct, G_FWD, ga_fwd));
+        if (tc_fwd)
+          for (int win = 0; win < windows_of(cap_tc); ++win)
+            VSSR_PROF(VSSR_K_MSG_FWD, st, mtc::message_fwd_tc<false><<<v2_grid, mtc::THREADS, smem_tc, st>>>(
+                weights, l, A, atom_ptr, n_chunks, rowptr, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],
+                w.cat[l], w.vmid[l], memo ? 1 : 0, cap_tc, win));
+        else
         for (int win = 0; win < windows_of(cap_fwd); ++win)
           VSSR_PROF(VSSR_K_MSG_FWD, st, message_fwd_v2<false><<<v2_grid, MSG_THREADS, smem_fwd, st>>>(
               weights, l, A, atom_ptr, n_chunks, rowptr, w.order_d, w.nvalid, w.erec, w.phi[l], w.s[l], w.v[l],

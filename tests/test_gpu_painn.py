@@ -305,3 +305,22 @@ def test_relax_retries_on_edge_capacity_overflow(structures, potentials, sto_wei
     r2 = eng.relax(b2, relax_steps=5, e_cap=1000, check=True)
     assert int(r2["status"].item()) == 0
     assert torch.equal(r2["out"], out0) and torch.equal(b2.pos, b0.pos)
+
+
+def test_tensor_core_filter_forward_opt_in():
+    """`VSSR_MSG_TC=1` routes the direct forward message pass through `mtc::message_fwd_tc` (radial filter as 3xTF32
+    `tcgen05.mma`, csrc/painn_message_tc.cuh).  It is off by default -- measured slower than the FFMA2 kernel,
+    profiles/round2_notes.md section 4 -- but it has to stay parity-green: the same oracle comparisons, in a fresh
+    process because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("VSSR_MSG_TC", "0") not in ("", "0"):
+        pytest.skip("already running with the tensor-core forward")
+    env = dict(os.environ, VSSR_MSG_TC="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_painn.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "random_weights or sender_windows or frozen_pair or batch_invariant"],
+                       env=env, cwd=os.path.dirname(here), capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
