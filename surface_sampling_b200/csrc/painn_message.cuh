@@ -37,6 +37,11 @@ __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+// *p += x without the load latency: one fire-and-forget reduction per address and launch -- a single IEEE addition onto
+// the stored value, i.e. the bits of load + add + store (launches are stream-ordered, so the result stays deterministic)
+__device__ __forceinline__ void red_add2(float* p, float2 x) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x.x), "f"(x.y) : "memory");
+}
 
 // smem floats per staged atom
 template <bool FIRST> struct MsgFwdLayout { static constexpr int PER = FIRST ? 3 * MSG_FC : 6 * MSG_FC; };
@@ -121,6 +126,46 @@ __device__ __forceinline__ void window_slice(const float* __restrict__ rec0, int
     const int jl = e < ne ? __float_as_int(__ldg(rec0 + (long long)e * REC + REC_EJ)) - a0 : 0x7fffffff;
     e_lo += __popc(__ballot_sync(0xffffffffu, jl < lo));
     e_hi += __popc(__ballot_sync(0xffffffffu, jl < hi));
+  }
+}
+
+// The same for every row a CTA owns (table slots t = ch, ch + n_chunks, ...), done once in the prologue while the sender
+// rows are being staged: four rows per warp and step, their sender loads all in flight before the first ballot, so the
+// CTA pays two or three memory latencies here instead of one per row inside the row loop.  The table then holds the
+// window's slice of each row; slots beyond the table (n > MSG_MAXROWS) are sliced in the row loop as before.
+__device__ __forceinline__ void row_table_slice(RowTable& rt, const float* __restrict__ erec, int a0, int n, int ch, int n_chunks,
+                                                int lo, int hi, int warp, int lane, int nwarps) {
+  const int nt = min(n, MSG_MAXROWS);
+  for (int k = 4 * warp; ch + n_chunks * k < nt; k += 4 * nwarps) {
+    int e0[4], ne[4], jl[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = ch + n_chunks * (k + u);
+      e0[u] = t < nt ? rt.e0[t] : 0;
+      ne[u] = t < nt ? rt.ne[t] : 0;
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        const int e = 32 * sg + lane;
+        jl[u][sg] = e < ne[u] ? __float_as_int(__ldg(erec + (long long)(e0[u] + e) * REC + REC_EJ)) - a0 : 0x7fffffff;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = ch + n_chunks * (k + u);
+      int e_lo = 0, e_hi = 0;
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        e_lo += __popc(__ballot_sync(0xffffffffu, jl[u][sg] < lo));
+        e_hi += __popc(__ballot_sync(0xffffffffu, jl[u][sg] < hi));
+      }
+      for (int base = 64; base < ne[u]; base += 32) {     // rows with more than 64 direct records (warp-uniform)
+        const int e = base + lane;
+        const int j = e < ne[u] ? __float_as_int(__ldg(erec + (long long)(e0[u] + e) * REC + REC_EJ)) - a0 : 0x7fffffff;
+        e_lo += __popc(__ballot_sync(0xffffffffu, j < lo));
+        e_hi += __popc(__ballot_sync(0xffffffffu, j < hi));
+      }
+      if (lane == 0 && t < nt) { rt.e0[t] = e0[u] + e_lo; rt.ne[t] = e_hi - e_lo; }
+    }
   }
 }
 
@@ -397,6 +442,10 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
     wd2[q] = ld2(wl + L_WDT + q * F3 + 2 * F + f0);
   }
   const float2 bd0 = ld2(wl + L_BD + f0), bd1 = ld2(wl + L_BD + F + f0), bd2 = ld2(wl + L_BD + 2 * F + f0);
+  if (!whole) {
+    __syncthreads();                  // row table complete
+    row_table_slice(rt, erec, a0, n, ch, n_chunks, wn.lo, wn.hi, warp, lane, MSG_THREADS / 32);
+  }
   stage_wait();
   __syncthreads();
 
@@ -404,7 +453,7 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
     int il, e0, ne;
     row_table_get(rt, order, rowptr, nvalid, a0, t, il, e0, ne);
     const float* rec0 = erec + (long long)e0 * REC;
-    if (!whole) {                     // the slice of this row whose senders lie in the window
+    if (!whole && t >= MSG_MAXROWS) { // the slice of this row whose senders lie in the window (table rows: done above)
       int e_lo, e_hi;
       window_slice(rec0, ne, a0, wn.lo, wn.hi, lane, e_lo, e_hi);
       rec0 += (long long)e_lo * REC;
@@ -453,10 +502,10 @@ __global__ void __launch_bounds__(MSG_THREADS, FIRST ? 2 : 1) message_fwd_v2(
     float* so = cat + (long long)il * 2 * F + f0;
     float* vo = v_mid + (long long)il * 3 * F + f0;
     if (accum) {
-      *reinterpret_cast<float2*>(so) = __fadd2_rn(ld2(so), ds);
-      *reinterpret_cast<float2*>(vo) = __fadd2_rn(ld2(vo), dvx);
-      *reinterpret_cast<float2*>(vo + F) = __fadd2_rn(ld2(vo + F), dvy);
-      *reinterpret_cast<float2*>(vo + 2 * F) = __fadd2_rn(ld2(vo + 2 * F), dvz);
+      red_add2(so, ds);
+      red_add2(vo, dvx);
+      red_add2(vo + F, dvy);
+      red_add2(vo + 2 * F, dvz);
     } else {
       *reinterpret_cast<float2*>(so) = __fadd2_rn(ld2(s_in + (long long)il * F + f0), ds);
       if (!FIRST) {
@@ -574,12 +623,12 @@ __device__ __forceinline__ void bwd_store(const BwdOwn& o, const BwdAcc& a, int 
     float* dpo = dphi + (long long)il * F3 + f0;
     float* dvo = dv_in + (long long)il * 3 * F + f0;
     if (accum & 1) {
-      *reinterpret_cast<float2*>(dpo) = __fadd2_rn(ld2(dpo), a.dp0);
-      *reinterpret_cast<float2*>(dpo + F) = __fadd2_rn(ld2(dpo + F), a.dp1);
-      *reinterpret_cast<float2*>(dpo + 2 * F) = __fadd2_rn(ld2(dpo + 2 * F), neg2(a.dp2n));
-      *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ld2(dvo), a.dvx);
-      *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ld2(dvo + F), a.dvy);
-      *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ld2(dvo + 2 * F), a.dvz);
+      red_add2(dpo, a.dp0);
+      red_add2(dpo + F, a.dp1);
+      red_add2(dpo + 2 * F, neg2(a.dp2n));
+      red_add2(dvo, a.dvx);
+      red_add2(dvo + F, a.dvy);
+      red_add2(dvo + 2 * F, a.dvz);
     } else {
       *reinterpret_cast<float2*>(dpo) = a.dp0;
       *reinterpret_cast<float2*>(dpo + F) = a.dp1;
@@ -592,7 +641,7 @@ __device__ __forceinline__ void bwd_store(const BwdOwn& o, const BwdAcc& a, int 
   const float gx = warp_sum(a.gnx.x + a.gnx.y), gy = warp_sum(a.gny.x + a.gny.y), gz = warp_sum(a.gnz.x + a.gnz.y);
   if (lane == 0) {
     float* gp = gradp + (((long long)m * 2 + h) * n_atoms + i) * 3;
-    if (accum & 2) { gp[0] -= gx; gp[1] -= gy; gp[2] -= gz; }
+    if (accum & 2) { atomicAdd(gp, -gx); atomicAdd(gp + 1, -gy); atomicAdd(gp + 2, -gz); }
     else { gp[0] = -gx; gp[1] = -gy; gp[2] = -gz; }
   }
 }
@@ -786,6 +835,10 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     wd2[q] = ld2(wl + L_WDT + q * F3 + 2 * F + f0);
   }
   const float2 bd0 = ld2(wl + L_BD + f0), bd1 = ld2(wl + L_BD + F + f0), bd2 = ld2(wl + L_BD + 2 * F + f0);
+  if (!whole) {
+    __syncthreads();                  // row table complete
+    row_table_slice(rt, erec, a0, n, ch, n_chunks, wn.lo, wn.hi, warp, lane, MSG_THREADS / 32);
+  }
   stage_wait();
   __syncthreads();
 
@@ -794,7 +847,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
     row_table_get(rt, order, rowptr, nvalid, a0, t, il, e0, ne);
     const int i = a0 + il;
     const float* rec0 = erec + (long long)e0 * REC;
-    if (!whole) {
+    if (!whole && t >= MSG_MAXROWS) {
       int e_lo, e_hi;
       window_slice(rec0, ne, a0, wn.lo, wn.hi, lane, e_lo, e_hi);
       rec0 += (long long)e_lo * REC;
@@ -859,12 +912,12 @@ __global__ void __launch_bounds__(MSG_THREADS, 1) message_bwd_v2(
       float* dpo = dphi + (long long)il * F3 + f0;
       float* dvo = dv_in + (long long)il * 3 * F + f0;
       if (accum & 1) {
-        *reinterpret_cast<float2*>(dpo) = __fadd2_rn(ld2(dpo), dp0);
-        *reinterpret_cast<float2*>(dpo + F) = __fadd2_rn(ld2(dpo + F), dp1);
-        *reinterpret_cast<float2*>(dpo + 2 * F) = __fadd2_rn(ld2(dpo + 2 * F), neg2(dp2n));
-        *reinterpret_cast<float2*>(dvo) = __fadd2_rn(ld2(dvo), dvx);
-        *reinterpret_cast<float2*>(dvo + F) = __fadd2_rn(ld2(dvo + F), dvy);
-        *reinterpret_cast<float2*>(dvo + 2 * F) = __fadd2_rn(ld2(dvo + 2 * F), dvz);
+        red_add2(dpo, dp0);
+        red_add2(dpo + F, dp1);
+        red_add2(dpo + 2 * F, neg2(dp2n));
+        red_add2(dvo, dvx);
+        red_add2(dvo + F, dvy);
+        red_add2(dvo + 2 * F, dvz);
       } else {
         *reinterpret_cast<float2*>(dpo) = dp0;
         *reinterpret_cast<float2*>(dpo + F) = dp1;
