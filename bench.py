@@ -514,14 +514,15 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
     for b, zh in staged[:warmup]:
         statuses.append(relax_batch(b, zh)["status"])
     barrier()
-    l0 = int(lib.vssr_launch_count())
+    l0, g0 = int(lib.vssr_launch_count()), int(lib.vssr_graph_launch_count())
     ev0.record()
     for b, zh in staged[warmup:]:
         statuses.append(relax_batch(b, zh)["status"])
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    launches = int(lib.vssr_launch_count()) - l0
+    launches = int(lib.vssr_launch_count()) - l0                 # kernels executed (graph replays count their nodes)
+    graph_launches = int(lib.vssr_graph_launch_count()) - g0      # of which arrived through cudaGraphLaunch calls
     clocks = sampler.stop()
     check_statuses()
 
@@ -590,7 +591,7 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
         "config": workload_config(name, args, C, world, cfg_extra),
         "e2e": {"value": e2e, "unit": "proposals/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
                 "ms_per_step": e2e_ms / steps},
-        "gpu_launches": launches, "gpu_launches_e2e": e2e_launches,
+        "gpu_launches": launches, "gpu_launches_e2e": e2e_launches, "graph_launches": graph_launches,
         "roofline": roof, "kernel_breakdown_ms": breakdown, "clocks": clocks, **extra,
     }
     if name in REFERENCE_PUBLISHED:

@@ -212,8 +212,11 @@ int vssr_classical_relax_host(int32_t kind, const double* params, int32_t ntypes
                               double fmax, double skin, double* out, double* forces,
                               int32_t* status);
 
-/* number of kernel launches this library has enqueued since load (bench.py: gpu_launches)     */
+/* number of kernels this library has enqueued since load (bench.py: gpu_launches); kernels replayed from the
+ * relaxation's CUDA graph count once per replay.  vssr_graph_launch_count: cudaGraphLaunch calls issued (the
+ * iterations 1 .. relax_steps-1 of vssr_painn_relax are one graph launch each; VSSR_NO_GRAPH=1 turns that off).  */
 int64_t vssr_launch_count(void);
+int64_t vssr_graph_launch_count(void);
 
 /* Optional per-kernel-class profile (bench.py roofline): when enabled, every launch is bracketed
  * by a cudaEvent pair on its own stream.  Classes: 0 nbr, 1 edge geometry, 2 GEMM, 3 message fwd,

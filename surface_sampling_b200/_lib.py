@@ -23,6 +23,7 @@ SIGNATURES = {
     "vssr_version": (c_int, []),
     "vssr_device_cc": (c_int, []),
     "vssr_launch_count": (c_i64, []),
+    "vssr_graph_launch_count": (c_i64, []),
     "vssr_kernel_class_count": (c_int, []),
     "vssr_profile_enable": (c_int, [c_int]),
     "vssr_profile_collect": (c_int, [c_void_p, c_void_p, c_int]),

@@ -2,10 +2,12 @@
 #include "common.cuh"
 
 long long g_vssr_launches = 0;
+long long g_vssr_graph_launches = 0;
 
 extern "C" int vssr_version(void) { return 100; }
 
 extern "C" int64_t vssr_launch_count(void) { return (int64_t)g_vssr_launches; }
+extern "C" int64_t vssr_graph_launch_count(void) { return (int64_t)g_vssr_graph_launches; }
 
 extern "C" int vssr_device_cc(void) {
   int dev = 0;
@@ -36,6 +38,7 @@ void vssr_prof_begin(int cls, cudaStream_t st) {
   g_cls[g_prof_n] = cls;
   cudaEventRecord(g_ev0[g_prof_n], st);
 }
+bool vssr_prof_active() { return g_prof_on; }
 void vssr_prof_end(int cls, cudaStream_t st) {
   (void)cls;
   if (!g_prof_on || g_prof_n >= kMaxPairs) return;

@@ -5,7 +5,8 @@
 
 #include "../../include/vssr_b200.h"
 
-extern long long g_vssr_launches;  // defined in api.cu
+extern long long g_vssr_launches;        // kernels launched (graph replays count their kernel nodes); defined in api.cu
+extern long long g_vssr_graph_launches;  // cudaGraphLaunch calls
 
 // Kernel classes for the optional per-class CUDA-event profile (bench.py roofline).
 enum VssrKernelClass {
@@ -14,6 +15,7 @@ enum VssrKernelClass {
 };
 void vssr_prof_begin(int cls, cudaStream_t st);  // no-ops unless vssr_profile_enable(1)
 void vssr_prof_end(int cls, cudaStream_t st);
+bool vssr_prof_active();
 
 #define VSSR_LAUNCH_CHECK()                                  \
   do {                                                       \

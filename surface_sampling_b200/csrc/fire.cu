@@ -4,6 +4,7 @@
 // optimize_slab (mcmc/dynamics.py:120-168), get_system_val (mcmc/uncertainty/prediction.py:181-223).
 // CPU restatement: oracle/relax.py, oracle/painn.py::EnsembleOracle.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -313,6 +314,48 @@ extern "C" int vssr_painn_relax_edge_stats(const void* relax_workspace, int32_t 
                                fc_e_cap0, out5, stream);
 }
 
+namespace {
+// Executable graphs of relaxations still in flight: destroyed once the event recorded after their last launch has
+// completed (polled at the next call; the oldest is waited for when 32 are pending).
+struct GraphPool {
+  struct Item { cudaGraphExec_t exec; cudaEvent_t done; };
+  cudaStream_t capture_stream = nullptr;
+  Item items[32];
+  int n = 0;
+  int reap(bool all) {
+    int kept = 0;
+    for (int k = 0; k < n; ++k) {
+      cudaError_t q = all ? cudaEventSynchronize(items[k].done) : cudaEventQuery(items[k].done);
+      if (q == cudaSuccess) {
+        cudaGraphExecDestroy(items[k].exec);
+        cudaEventDestroy(items[k].done);
+      } else if (q == cudaErrorNotReady) {
+        items[kept++] = items[k];
+      } else {
+        return (int)q;
+      }
+    }
+    n = kept;
+    return VSSR_OK;
+  }
+  int retire(cudaGraphExec_t exec, cudaStream_t st) {
+    if (n == 32) {
+      const int r = reap(true);
+      if (r) return r;
+    }
+    Item it{exec, nullptr};
+    VSSR_CUDA(cudaEventCreateWithFlags(&it.done, cudaEventDisableTiming));
+    VSSR_CUDA(cudaEventRecord(it.done, st));
+    items[n++] = it;
+    return VSSR_OK;
+  }
+};
+GraphPool& graph_pool() {
+  static thread_local GraphPool pool;
+  return pool;
+}
+}  // namespace
+
 extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* pos, const int32_t* z,
                                 const uint8_t* fixed, const int32_t* atom_ptr, const float* cell, const uint8_t* pbc,
                                 const double* offset_ev, int32_t n_struct, int32_t n_atoms,
@@ -335,23 +378,57 @@ extern "C" int vssr_painn_relax(const float* weights, int32_t n_models, double* 
                            w.shift, e_cap, status, stream)))
     return rc;
   if ((rc = vssr_fire_init(w.state, w.vel, n_struct, n_atoms, stream))) return rc;
-  for (int it = 0; it <= relax_steps; ++it) {
-    // the last evaluation is the one whose raw forces on ALL atoms feed the out-of-bounds test
-    // (mcmc/dynamics.py:155-159): it always computes the full gradient
-    const int32_t flags_it = it == relax_steps ? (fc_flags & ~VSSR_FC_CONSTRAINED_GRAD) : fc_flags;
-    if ((rc = vssr_painn_energy_grad(weights, n_models, w.pos32, z, atom_ptr, cell, n_struct, n_atoms,
-                                     max_atoms_per_struct, w.rowptr,
-                                     w.col, w.shift, e_cap, cutoff, filter_cache, fc_n0, fc_e_cap0, flags_it, w.painn, w.painn_bytes, w.energy,
-                                     w.grad, nullptr,
-                                     stream)))
-      return rc;
-    const bool last = it == relax_steps;
-    if ((rc = vssr_ensemble_stats(w.energy, w.grad, offset_ev, atom_ptr, n_models, n_struct, n_atoms, w.e_mean,
-                                  w.e_std, forces, last ? forces_std : nullptr, stream)))
-      return rc;
-    if ((rc = vssr_fire_step(pos, w.pos32, w.vel, forces, fixed, atom_ptr, n_struct, w.state, relax_steps, fmax,
-                             stream)))
-      return rc;
+  // one optimiser iteration: ensemble evaluation, statistics, FIRE step.  Iterations 0 .. relax_steps-1 are the SAME
+  // launches with the same arguments (the step counter lives in w.state); the last evaluation is the one whose raw
+  // forces on ALL atoms feed the out-of-bounds test (mcmc/dynamics.py:155-159): it always computes the full gradient
+  auto iteration = [&](bool last, void* s) -> int {
+    const int32_t flags_it = last ? (fc_flags & ~VSSR_FC_CONSTRAINED_GRAD) : fc_flags;
+    int r;
+    if ((r = vssr_painn_energy_grad(weights, n_models, w.pos32, z, atom_ptr, cell, n_struct, n_atoms,
+                                    max_atoms_per_struct, w.rowptr, w.col, w.shift, e_cap, cutoff, filter_cache, fc_n0,
+                                    fc_e_cap0, flags_it, w.painn, w.painn_bytes, w.energy, w.grad, nullptr, s)))
+      return r;
+    if ((r = vssr_ensemble_stats(w.energy, w.grad, offset_ev, atom_ptr, n_models, n_struct, n_atoms, w.e_mean,
+                                 w.e_std, forces, last ? forces_std : nullptr, s)))
+      return r;
+    return vssr_fire_step(pos, w.pos32, w.vel, forces, fixed, atom_ptr, n_struct, w.state, relax_steps, fmax, s);
+  };
+  // Iterations 1 .. relax_steps-1 are replayed from a CUDA graph captured once per call (~75 kernel nodes): the host
+  // issues relax_steps graph launches instead of ~1500 kernel launches and never fills the launch queue.  Iteration 0
+  // runs directly (it configures function attributes and tensor maps -- nothing of that happens inside the capture).
+  // Off while the per-class event profile is recording, and with VSSR_NO_GRAPH=1 (bench documentation switch).
+  static const bool no_graph = getenv("VSSR_NO_GRAPH") && atoi(getenv("VSSR_NO_GRAPH")) > 0;
+  if (relax_steps < 3 || no_graph || vssr_prof_active()) {
+    for (int it = 0; it <= relax_steps; ++it)
+      if ((rc = iteration(it == relax_steps, stream))) return rc;
+  } else {
+    if ((rc = iteration(false, stream))) return rc;
+    GraphPool& gp = graph_pool();
+    if ((rc = gp.reap(false))) return rc;
+    if (!gp.capture_stream) VSSR_CUDA(cudaStreamCreateWithFlags(&gp.capture_stream, cudaStreamNonBlocking));
+    const long long l0 = g_vssr_launches;
+    VSSR_CUDA(cudaStreamBeginCapture(gp.capture_stream, cudaStreamCaptureModeThreadLocal));
+    rc = iteration(false, gp.capture_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ec = cudaStreamEndCapture(gp.capture_stream, &graph);
+    const long long per_iteration = g_vssr_launches - l0;   // kernel nodes of one iteration
+    g_vssr_launches = l0;
+    if (rc || ec != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc ? rc : (int)ec;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return (int)ei;
+    for (int it = 1; it < relax_steps; ++it) {
+      const cudaError_t el = cudaGraphLaunch(exec, st);
+      if (el != cudaSuccess) { cudaGraphExecDestroy(exec); return (int)el; }
+      g_vssr_launches += per_iteration;
+      ++g_vssr_graph_launches;
+    }
+    if ((rc = gp.retire(exec, st))) return rc;
+    if ((rc = iteration(true, stream))) return rc;
   }
   VSSR_PROF(VSSR_K_FIRE, st, relax_finalize_kernel<<<ceil_div(n_struct, 128), 128, 0, st>>>(w.e_mean, w.e_std, w.state, forces, atom_ptr, n_struct, out));
   return VSSR_OK;

@@ -146,6 +146,40 @@ def test_relax_fire_vs_oracle(structures, potentials, sto_weights):
         assert abs(se_gpu - se_cpu) <= 2 * E_TOL_PER_ATOM * n
 
 
+def test_relax_graph_replay_is_bitwise_the_direct_loop(structures, potentials, sto_weights):
+    """vssr_painn_relax replays iterations 1..n-1 from a CUDA graph captured per call; with the per-class event profile
+    recording it issues the same kernels directly.  Same bits either way -- positions, energies, forces, flags -- with
+    and without the framework memo, and the launch counters tell the two paths apart."""
+    from surface_sampling_b200 import _lib, engine
+    lib = _lib.load()
+    od = potentials["offset_data"]
+    rng = np.random.default_rng(21)
+    base = structures["SrTiO3_001_2x2"]
+    fixed0 = orelax.fixed_mask_from_surface_depth(base["positions"], base["cell"], 1)
+    structs = [with_adsorbates(base, rng, k, [8, 38, 22]) for k in (2, 5, 9, 1)]
+    fixed = [np.concatenate([fixed0, np.zeros(len(s["numbers"]) - 60, bool)]) for s in structs]
+    for memo in (False, True):
+        eng = engine.PainnEngine(sto_weights, od)
+        if memo:
+            eng.set_framework(base["positions"], base["cell"], PBC3, fixed0, constrained_forces=True)
+        runs = []
+        for profiled in (False, True, False):
+            b = _batch(structs, fixed)
+            lib.vssr_profile_enable(1 if profiled else 0)
+            g0, l0 = int(lib.vssr_graph_launch_count()), int(lib.vssr_launch_count())
+            try:
+                r = eng.relax(b, relax_steps=8, fmax=0.01, check=True)
+                torch.cuda.synchronize()
+            finally:
+                lib.vssr_profile_enable(0)
+            runs.append((b.pos.clone(), r["out"].clone(), r["forces"].clone(), r["forces_std"].clone(),
+                         int(lib.vssr_graph_launch_count()) - g0, int(lib.vssr_launch_count()) - l0))
+        (p0, o0, f0, s0, g_graph, l_graph), (p1, o1, f1, s1, g_direct, l_direct), (p2, o2, _, _, _, _) = runs
+        assert g_graph == 7 and g_direct == 0 and l_graph == l_direct      # 7 replays; the same kernels executed
+        assert torch.equal(p0, p1) and torch.equal(o0, o1) and torch.equal(f0, f1) and torch.equal(s0, s1)
+        assert torch.equal(p0, p2) and torch.equal(o0, o2)
+
+
 def test_uncertainty_reductions(structures, potentials, sto_weights):
     from surface_sampling_b200 import engine
     eng = engine.PainnEngine(sto_weights, potentials["offset_data"])
