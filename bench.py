@@ -62,11 +62,16 @@ PH_VALUES = [0.0, 2.0, 4.0, 6.0, 8.0, 10.0, 12.0, 14.0]
 U_VALUES = [-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]
 # PourbaixAtom table: Sr / O / H rows are the literals of the reference's tests/pourbaix/test_pourbaix_atoms.py:44-86
 # (phi=1, pH=0 case); the Ti row is synthetic (TiO2: 4 e-, 4 H+), pymatgen being unavailable
+# The reference energies (atom_std_state_energy) are RE-CENTRED for the synthetic model: a random-init PaiNN has no
+# DFT-scale atomic energies, so with the literal values adding any atom costs +6 .. +28 eV and nothing is ever accepted
+# (the chains would stay pristine).  Shifted by +8.84262 / +20.75244 / +5.89452 / +4.94979 eV, adding one Sr / Ti / O / H
+# is grand-potential neutral at the grid centre (pH 7, U 0.5 V); the pH and U slopes (num_e, num_H, species_conc,
+# delta_G2_std) stay the reference's, so coverage and species vary over the grid as in a real Pourbaix run.
 POURBAIX_TABLE = {
-    "Sr": dict(species_conc=1e-6, num_e=2, num_H=0, atom_std_state_energy=-1.68949, delta_G2_std=-5.79807),
-    "Ti": dict(species_conc=1.0, num_e=4, num_H=4, atom_std_state_energy=-7.8955, delta_G2_std=-9.20),
-    "O": dict(species_conc=1.0, num_e=-2, num_H=-2, atom_std_state_energy=-5.26469, delta_G2_std=-2.45830),
-    "H": dict(species_conc=1.0, num_e=1, num_H=1, atom_std_state_energy=-4.0356, delta_G2_std=0.0),
+    "Sr": dict(species_conc=1e-6, num_e=2, num_H=0, atom_std_state_energy=-1.68949 + 8.84262, delta_G2_std=-5.79807),
+    "Ti": dict(species_conc=1.0, num_e=4, num_H=4, atom_std_state_energy=-7.8955 + 20.75244, delta_G2_std=-9.20),
+    "O": dict(species_conc=1.0, num_e=-2, num_H=-2, atom_std_state_energy=-5.26469 + 5.89452, delta_G2_std=-2.45830),
+    "H": dict(species_conc=1.0, num_e=1, num_H=1, atom_std_state_energy=-4.0356 + 4.94979, delta_G2_std=0.0),
 }
 
 # single-chain rates the reference's own notebooks print (other hardware, other optimiser settings)
@@ -91,10 +96,11 @@ WORKLOADS = {
                   desc="Si(111) 5x5 VSSR-MC, Stillinger-Weber (SW-1985 literature parameters, parity unpinned), semigrand "
                        "Si on 100 virtual sites, FIRE relax_steps=100 fmax=0.01, ids<=75 frozen (BASELINE.json configs[2])"),
     "sto_pourbaix": dict(slab="SrTiO3_001_2x2", n_sites=64, adsorbates=["Sr", "Ti", "O", "HO"], relax_steps=20,
-                         canonical=False, num_ads=0, height=1.5, chains=112, temp=0.257, burn_in=60, cpu_props=3, models=1,
+                         canonical=False, num_ads=0, height=1.5, chains=112, temp=0.257, burn_in=150, cpu_props=3, models=1,
                          desc="SrTiO3(001) 2x2 Pourbaix VSSR-MC (sample_pourbaix_surface.py): single PaiNN model (random-init, "
                               "seed 0) + NFFPourbaix grand potential, 8 pH x 7 U grid points x chains sharded as (pH,U,chain) "
-                              "units, semigrand Sr/Ti/O/HO on 64 sites, HO correction 0.23 eV, kT=0.0257, T=0.257, FIRE "
+                              "units, semigrand Sr/Ti/O/HO on 64 sites, HO correction 0.23 eV, kT=0.0257, T=0.257, reference energies "
+                              "re-centred for the random-init model (grand-potential neutral at pH 7, U 0.5 V), FIRE "
                               "relax_steps=20 (BASELINE.json configs[4])"),
 }
 
@@ -304,7 +310,7 @@ def workload_config(name, args, chains, world, extra=None):
 
 # adsorbates per chain after the default burn-in, measured by the B200 arm on this workload (profiles/round2_bench*.json:
 # config.coverage): the reference arm starts its chain at the same coverage so both arms relax structures of the same size
-REFERENCE_COVERAGE = {"sto_painn": 32, "sto_pourbaix": 0}
+REFERENCE_COVERAGE = {"sto_painn": 32, "sto_pourbaix": 28}
 
 
 def reference_occupancy(name):
@@ -562,7 +568,7 @@ def run_workload(name, args, ctx, steps, warmup, burn_in, headline):
         roof = painn_roofline(breakdown, edge_stats, a_prof, steps_relax + 1, w["models"], peaks)
         extra["painn_atom_model_evals_per_sec"] = atoms_total * (steps_relax + 1) * w["models"] * world / (dev_ms * 1e-3)
     else:
-        roof = classical_roofline(breakdown, a_prof, steps_relax + 1, peaks)
+        roof = classical_roofline(breakdown, a_prof, steps_relax + 1, peaks, name, proposals=C * len(fresh))
         # saturation point (SURVEY.md 8d caveat): 256 chains = 256 CTAs occupy a fraction of the 148 SMs x 2-4 resident
         # CTAs; the same kernel on 65,536 chains (the staged batch replicated) shows what the GPU sustains
         reps = 65536 // C
@@ -701,22 +707,35 @@ def painn_roofline(breakdown, edge_stats, a_prof, evals, M, peaks):
                     if not is_tensor else "3xTF32 on tcgen05: `frac` = algorithmic FLOPs / TF32 peak (x3 in issued tensor MACs)"}
 
 
-def classical_roofline(breakdown, a_prof, evals, peaks):
+def classical_roofline(breakdown, a_prof, evals, peaks, name=None, proposals=0):
     """Persistent one-CTA-per-chain kernel: the slab never leaves shared memory between FIRE steps, so HBM traffic is ~0
-    and the kernel is FP64-pipe / latency bound.  Reported: the algorithmic HBM figure of SURVEY.md 8d (53 B per
-    atom-evaluation if it streamed) and atom-evaluations/s."""
+    and the kernel is FP64-pipe / latency bound.  Reported against the FP64 pipe: executed FP64 flops per relaxed
+    proposal (ncu instruction counts on this bench's own launches, profiles/round2_classical_fp64.json) x the proposals
+    of the profiled launches / their time; the algorithmic HBM figure of SURVEY.md 8d (53 B per atom-evaluation if
+    the kernel streamed) is kept beside it."""
     hbm = peaks["hbm_gbs"] if peaks else 6650.0
     k = "classical_relax"
     if k not in breakdown or breakdown[k]["ms"] <= 0:
         return None
     t = breakdown[k]["ms"] * 1e-3
-    achieved = 53.0 * a_prof * evals / t / 1e9
-    return {"bound": "hbm", "kernel": k, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-            "atom_evals_per_sec": a_prof * evals / t,
-            "note": "upper bound on evaluations: converged chains stop early inside the kernel. The kernel keeps the whole relaxation "
-                    "in shared memory (0 B of HBM traffic between FIRE steps), so the HBM fraction only shows that it is not "
-                    "bandwidth-bound; it is FP64/SFU-latency bound with one 128-thread CTA per chain"}
+    streamed = 53.0 * a_prof * evals / t / 1e9
+    roof = {"bound": "fp64", "kernel": k, "achieved": None, "peak": FP64_PEAK, "unit": "TFLOP/s", "frac": None, "traffic": None,
+            "peak_source": "nominal B200 FP64 (148 SMs x 64 DFMA/clk x 2 x 1.965 GHz); MEASURED_PEAKS.json has no FP64 entry",
+            "atom_evals_per_sec_upper_bound": a_prof * evals / t,
+            "hbm_if_streamed": {"achieved_gbs": streamed, "peak_gbs": hbm, "frac": streamed / hbm,
+                                "note": "SURVEY.md 8d: 53 B per atom-evaluation; the kernel keeps the relaxation in shared "
+                                        "memory, so this only shows that it is not bandwidth-bound"},
+            "note": "one 128-thread CTA per chain, whole relaxation (<= 100 FIRE steps, converged chains stop early) inside "
+                    "the SM: bound by FP64 issue latency at 4 warps per CTA, not by the pipe's throughput"}
+    f = ROOT / "profiles" / "round2_classical_fp64.json"
+    if f.exists() and name:
+        d = json.loads(f.read_text()).get(name)
+        if d:
+            roof["achieved"] = d["fp64_flop_per_proposal"] * proposals / t / 1e12
+            roof["frac"] = roof["achieved"] / FP64_PEAK
+            roof["fp64_flop_per_proposal"] = d["fp64_flop_per_proposal"]
+            roof["flop_source"] = "profiles/round2_classical_fp64.json: " + d["source"]
+    return roof
 
 
 def main():

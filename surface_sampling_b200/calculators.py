@@ -304,8 +304,25 @@ class NFFPourbaix(EnsembleNFF):
         temperature and corrections, at the given (phi, pH) grid point (default: the calculator's own)."""
         phi = self.phi if phi is None else phi
         pH = self.pH if pH is None else pH
-        table, temp, corr = self.pourbaix_atoms, self.temp, self.adsorbate_corrections
-        return lambda e, symbols: pourbaix_potential_from(e, symbols, table, phi, pH, temp, corr)
+        table, temp, corr = self.pourbaix_atoms, self.temp, self.adsorbate_corrections or {}
+        # pourbaix_potential_from with the per-species addends of this grid point formed once: the per-atom loop below
+        # adds, atom by atom and in the same order, exactly the floats that function would recompute for every atom
+        term = {sym: a.delta_G2_std + (-a.num_e * phi - np.log(10) * a.num_H * temp * pH + temp * np.log(a.species_conc))
+                for sym, a in table.items()}
+        std = {sym: a.atom_std_state_energy for sym, a in table.items()}
+
+        def fn(e, symbols):
+            cnt = Counter(symbols)
+            sum_std = 0
+            for sym, c in cnt.items():
+                sum_std += c * std[sym]
+            dg1 = sum_std - (e + adsorbate_correction(dict(cnt), corr))
+            dg2 = 0
+            for sym in symbols:
+                dg2 += term[sym]
+            return -(dg1 + dg2)
+
+        return fn
 
     def set(self, **kwargs) -> dict:
         changed = EnsembleNFF.set(self, **kwargs)
