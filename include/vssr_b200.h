@@ -187,7 +187,9 @@ int vssr_painn_relax_edge_stats(const void* relax_workspace, int32_t n_models, i
 #define VSSR_POT_SW 1
 #define VSSR_POT_EAM 2   /* LAMMPS `pair_style eam`, single-element funcfl (LAMMPSRunSurfCalc: mcmc/calculators/
                             calculators.py:755-811, tests/test_Cu.py, tests/test_Au.py); ntypes must be 1 */
-size_t vssr_classical_smem_bytes(int32_t n_max, int32_t max_nbr);
+/* dynamic shared memory of one CTA (<= 227 KB): Tersoff / SW keep a table of 8 * n_max directed pairs, EAM per-slot
+ * gradients [n_max][max_nbr] */
+size_t vssr_classical_smem_bytes(int32_t kind, int32_t n_max, int32_t max_nbr);
 int vssr_classical_energy_forces(int32_t kind, const double* params, int32_t ntypes,
                                  const double* pos /*[A,3]*/, const int32_t* types /*[A]*/,
                                  const int32_t* atom_ptr, const double* cell /*[B,3,3]*/,

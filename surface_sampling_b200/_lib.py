@@ -53,7 +53,7 @@ SIGNATURES = {
                                       c_void_p, c_void_p]),
     "vssr_painn_relax_edge_stats": (c_int, [c_void_p, c_int, c_int, c_i64, c_void_p, c_int, c_void_p, c_int, c_i64,
                                             c_void_p, c_void_p]),
-    "vssr_classical_smem_bytes": (c_size_t, [c_int, c_int]),
+    "vssr_classical_smem_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vssr_classical_energy_forces": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]),

@@ -5,9 +5,12 @@
 // and Si (SW family) tutorials; functional forms restated in oracle/classical.py, FIRE in
 // oracle/relax.py.
 //
-// Determinism: thread i owns centre atom i.  Forces that centre i exerts on its neighbours are
-// written to i's private slots G[i][slot]; a second phase lets every atom j gather its slots
-// through the reverse-edge map in fixed order.  No atomics anywhere.
+// Determinism: every output has exactly one writer.  Tersoff / SW: the directed pairs (centre i, neighbour j inside
+// the cutoff) are compacted into a shared-memory pair table each step and a THREAD OWNS A PAIR -- it sums, in list
+// order, every term of centre i's energy that pulls on neighbour j (pair term, the triplets where j is the bonded
+// atom, the triplets where j is the third atom) into its private slot pG[pair]; EAM: thread i owns centre i and its
+// slots G[i][slot].  A second phase lets every atom gather the slots that point at it through the reverse-edge map
+// in fixed order.  No atomics anywhere.
 #include <math.h>
 
 #include "common.cuh"
@@ -32,9 +35,23 @@ struct Smem {
   unsigned char* fixed;  // [n_max]
   double* red;    // [4][3]
   double* aux;    // [n_max] EAM: dF/drho of every atom between the two passes
+  // Tersoff / SW: table of the directed pairs inside the cutoff, compacted per centre in skin-list order
+  int* pcnt;             // [n_max] pairs of every centre
+  int* pstart;           // [n_max + 1] first pair of every centre
+  unsigned char* aidx;   // [n_max][max_nbr] skin slot -> index among the centre's pairs (255: outside the cutoff)
+  short* pi;             // [pcap] centre
+  unsigned char* pslot;  // [pcap] skin slot
+  double* pu;            // [pcap][4] unit vector centre -> neighbour, distance
+  double* pa;            // [pcap][2] SW: exp(gamma sigma / (r - a sigma)) and d/dr of its exponent
+  double* pq;            // [pcap][3] energy share, dE/dr of the pair term, Tersoff: fA/2 db/dzeta | SW: 1 = inside cutoff
+  double* pG;            // [pcap][3] gradient of the centre's energy w.r.t. the neighbour's position
+  int pcap;
 };
+constexpr int PAIRS_PER_ATOM = 8;   // pair-table capacity per atom slot of the CTA (an average, not a per-atom limit)
 
-__host__ __device__ inline size_t smem_layout(int n_max, int max_nbr, char* base, Smem* s) {
+__host__ __device__ inline size_t smem_layout(int kind, int n_max, int max_nbr, char* base, Smem* s) {
+  const bool eam = kind == VSSR_POT_EAM;
+  const int pcap = eam ? 0 : PAIRS_PER_ATOM * n_max;
   size_t off = 0;
   auto take = [&](size_t bytes) -> char* {
     char* p = base ? base + off : nullptr;
@@ -45,7 +62,7 @@ __host__ __device__ inline size_t smem_layout(int n_max, int max_nbr, char* base
   double* f = (double*)take((size_t)n_max * 3 * 8);
   double* v = (double*)take((size_t)n_max * 3 * 8);
   double* x0 = (double*)take((size_t)n_max * 3 * 8);
-  double* G = (double*)take((size_t)n_max * max_nbr * 3 * 8);
+  double* G = (double*)take(eam ? (size_t)n_max * max_nbr * 3 * 8 : 0);
   double* eat = (double*)take((size_t)n_max * 8);
   double* own = (double*)take((size_t)n_max * 3 * 8);
   int* type = (int*)take((size_t)n_max * 4);
@@ -55,8 +72,19 @@ __host__ __device__ inline size_t smem_layout(int n_max, int max_nbr, char* base
   unsigned char* rev = (unsigned char*)take((size_t)n_max * max_nbr);
   unsigned char* fixed = (unsigned char*)take((size_t)n_max);
   double* red = (double*)take(4 * 3 * 8);
-  double* aux = (double*)take((size_t)n_max * 8);
+  double* aux = (double*)take(eam ? (size_t)n_max * 8 : 0);
+  int* pcnt = (int*)take(eam ? 0 : (size_t)n_max * 4);
+  int* pstart = (int*)take(eam ? 0 : (size_t)(n_max + 1) * 4);
+  unsigned char* aidx = (unsigned char*)take(eam ? 0 : (size_t)n_max * max_nbr);
+  short* pi = (short*)take((size_t)pcap * 2);
+  unsigned char* pslot = (unsigned char*)take((size_t)pcap);
+  double* pu = (double*)take((size_t)pcap * 4 * 8);
+  double* pa = (double*)take((size_t)pcap * 2 * 8);
+  double* pq = (double*)take((size_t)pcap * 3 * 8);
+  double* pG = (double*)take((size_t)pcap * 3 * 8);
   if (s) {
+    s->pcnt = pcnt; s->pstart = pstart; s->aidx = aidx; s->pi = pi; s->pslot = pslot; s->pu = pu; s->pa = pa; s->pq = pq;
+    s->pG = pG; s->pcap = pcap;
     s->aux = aux;
     s->x = x; s->f = f; s->v = v; s->x0 = x0; s->G = G; s->eat = eat; s->own = own; s->type = type; s->cnt = cnt;
     s->nj = nj; s->ns = ns; s->rev = rev; s->fixed = fixed; s->red = red;
@@ -171,10 +199,19 @@ __device__ __forceinline__ void ters_fc(double r, double R, double D, double& fc
     dfc = -(0.7853981633974483 / D) * cos(a);
   }
 }
-__device__ __forceinline__ void ters_bij(double zeta, const TersP& p, double& b, double& db) {
+// the four regime thresholds of b_ij (LAMMPS pair_tersoff c1..c4) depend on the parameter row only
+__device__ __forceinline__ void ters_bij_consts(double n, double* c) {
+  c[0] = pow(2.0 * n * 1.0e-16, -1.0 / n);
+  c[1] = pow(2.0 * n * 1.0e-8, -1.0 / n);
+  c[2] = 1.0 / c[1];
+  c[3] = 1.0 / c[0];
+}
+__device__ __forceinline__ void ters_bij(double zeta, const TersP& p, const double* __restrict__ bc, double& b, double& db) {
   const double tmp = p.beta * zeta, n = p.n;
-  const double c1 = pow(2.0 * n * 1.0e-16, -1.0 / n), c2 = pow(2.0 * n * 1.0e-8, -1.0 / n);
-  const double c3 = 1.0 / c2, c4 = 1.0 / c1;
+  double cl[4];
+  if (bc) { cl[0] = bc[0]; cl[1] = bc[1]; cl[2] = bc[2]; cl[3] = bc[3]; }
+  else ters_bij_consts(n, cl);
+  const double c1 = cl[0], c2 = cl[1], c3 = cl[2], c4 = cl[3];
   double dbt;  // db/dtmp
   if (tmp > c1) { b = 1.0 / sqrt(tmp); dbt = -0.5 * b / tmp; }
   else if (tmp > c2) {
@@ -214,100 +251,162 @@ __device__ __forceinline__ void ters_zeta_term(const TersP& p, double rij, doubl
   dz_dcos = fc * dg * ex;
 }
 
-constexpr int MAXACT = 16;   // neighbours inside the largest potential cutoff (<= slots inside cutoff+skin)
-
-// compact the skin list of atom i to the slots that are inside rcut right now
-struct Active {
-  int slot[MAXACT];
-  double x[MAXACT], y[MAXACT], z[MAXACT], r[MAXACT];
-  int n;
-};
-__device__ __forceinline__ void gather_active(const Smem& s, const Cell64& ci, int i, int max_nbr, double rcut, Active& a,
-                                              int32_t* status) {
-  a.n = 0;
-  const int cn = s.cnt[i];
-  for (int t = 0; t < cn; ++t) {
-    double x, y, z;
-    edge_vec(s, ci, i, s.nj[i * max_nbr + t], s.ns[i * max_nbr + t], x, y, z);
-    const double r = sqrt(x * x + y * y + z * z);
-    if (r < rcut) {
-      if (a.n < MAXACT) {
-        a.slot[a.n] = t; a.x[a.n] = x; a.y[a.n] = y; a.z[a.n] = z; a.r[a.n] = r;
-        ++a.n;
-      } else {
-        atomicOr(status, VSSR_STATUS_SLOT_OVERFLOW);
-      }
+// ---------------------------------------------------------------------------------- pair table (Tersoff / SW)
+// Directed pairs inside rcut, compacted per centre in skin-list order: count (thread per centre), warp scan, fill.
+__device__ void build_pairs(const Smem& s, const Cell64& ci, int n, int max_nbr, double rcut, int32_t* status) {
+  for (int i = threadIdx.x; i < n; i += NT) {
+    const int cn = s.cnt[i];
+    int c = 0;
+    for (int t = 0; t < cn; ++t) {
+      double x, y, z;
+      edge_vec(s, ci, i, s.nj[i * max_nbr + t], s.ns[i * max_nbr + t], x, y, z);
+      if (sqrt(x * x + y * y + z * z) < rcut) ++c;
     }
+    s.pcnt[i] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int base = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const int c = i < n ? s.pcnt[i] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (i < n) s.pstart[i] = base + incl - c;
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      s.pstart[n] = base;
+      if (base > s.pcap) atomicOr(status, VSSR_STATUS_SLOT_OVERFLOW);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += NT) {
+    const int cn = s.cnt[i], k0 = s.pstart[i];
+    int c = 0;
+    for (int t = 0; t < cn; ++t) {
+      double x, y, z;
+      edge_vec(s, ci, i, s.nj[i * max_nbr + t], s.ns[i * max_nbr + t], x, y, z);
+      const double r = sqrt(x * x + y * y + z * z);
+      unsigned char a = 255;
+      if (r < rcut) {
+        const int k = k0 + c;
+        if (k < s.pcap && c < 255) {
+          const double ir = 1.0 / r;
+          s.pi[k] = (short)i; s.pslot[k] = (unsigned char)t;
+          s.pu[4 * k] = x * ir; s.pu[4 * k + 1] = y * ir; s.pu[4 * k + 2] = z * ir; s.pu[4 * k + 3] = r;
+          a = (unsigned char)c;
+        }
+        ++c;
+      }
+      s.aidx[i * max_nbr + t] = a;
+    }
+  }
+  __syncthreads();
+}
+// pairs of centre i: [k0, k1) clipped to the table
+__device__ __forceinline__ void pair_range(const Smem& s, int i, int& k0, int& k1) {
+  k0 = min(s.pstart[i], s.pcap);
+  k1 = min(s.pstart[i + 1], s.pcap);
+}
+// centre-own gradient and per-atom energy from the centre's pair slots (thread per centre, list order)
+__device__ void pairs_to_centres(const Smem& s, int n) {
+  for (int i = threadIdx.x; i < n; i += NT) {
+    int k0, k1;
+    pair_range(s, i, k0, k1);
+    double gx = 0.0, gy = 0.0, gz = 0.0, e = 0.0;
+    for (int k = k0; k < k1; ++k) {
+      gx -= s.pG[3 * k]; gy -= s.pG[3 * k + 1]; gz -= s.pG[3 * k + 2];
+      e += s.pq[3 * k];
+    }
+    s.own[3 * i] = gx; s.own[3 * i + 1] = gy; s.own[3 * i + 2] = gz;
+    s.eat[i] = e;
   }
 }
 
 __device__ void tersoff_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, const double* __restrict__ params,
-                               int ntypes, double rcut, int32_t* status) {
-  for (int i = threadIdx.x; i < n; i += NT) {
-    const int ti = s.type[i], ci_n = s.cnt[i];
-    double gix = 0.0, giy = 0.0, giz = 0.0, ei = 0.0;
-    double* Gi = s.G + (size_t)i * max_nbr * 3;
-    for (int t = 0; t < ci_n; ++t) { Gi[3 * t] = 0.0; Gi[3 * t + 1] = 0.0; Gi[3 * t + 2] = 0.0; }
-    Active a;
-    gather_active(s, ci, i, max_nbr, rcut, a, status);
-    for (int p = 0; p < a.n; ++p) {
-      const int t = a.slot[p];
-      const int tj = s.type[s.nj[i * max_nbr + t]];
-      const TersP pij = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + tj) * 14);
-      const double jx = a.x[p], jy = a.y[p], jz = a.z[p], rij = a.r[p];
-      if (rij >= pij.R + pij.D) continue;
-      const double irij = 1.0 / rij;
-      const double ux = jx * irij, uy = jy * irij, uz = jz * irij;
+                               const double* __restrict__ bcs, int ntypes, double rcut, int32_t* status) {
+  build_pairs(s, ci, n, max_nbr, rcut, status);
+  const int np = min(s.pstart[n], s.pcap);
+  // pass 1 (thread per pair ij): zeta_ij over the centre's other pairs, bond order, pair energy and its r-derivative
+  for (int k = threadIdx.x; k < np; k += NT) {
+    const int i = s.pi[k], ti = s.type[i];
+    int k0, k1;
+    pair_range(s, i, k0, k1);
+    const int tj = s.type[s.nj[i * max_nbr + s.pslot[k]]];
+    const int row = (ti * ntypes + tj) * ntypes + tj;
+    const TersP pij = load_ters(params + (size_t)row * 14);
+    const double ux = s.pu[4 * k], uy = s.pu[4 * k + 1], uz = s.pu[4 * k + 2], rij = s.pu[4 * k + 3];
+    double e = 0.0, dEdr = 0.0, pref = 0.0;
+    if (rij < pij.R + pij.D) {
       double zeta = 0.0;
-      for (int q = 0; q < a.n; ++q) {
-        if (q == p) continue;
-        const TersP pk = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + s.type[s.nj[i * max_nbr + a.slot[q]]]) * 14);
-        const double rik = a.r[q];
+      for (int q = k0; q < k1; ++q) {
+        if (q == k) continue;
+        const TersP pk = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + s.type[s.nj[i * max_nbr + s.pslot[q]]]) * 14);
+        const double rik = s.pu[4 * q + 3];
         if (rik >= pk.R + pk.D) continue;
-        const double cs = (jx * a.x[q] + jy * a.y[q] + jz * a.z[q]) * irij / rik;
+        const double cs = ux * s.pu[4 * q] + uy * s.pu[4 * q + 1] + uz * s.pu[4 * q + 2];
         double z, a1, a2, a3;
         ters_zeta_term(pk, rij, rik, cs, z, a1, a2, a3);
         zeta += z;
       }
       double fc, dfc, bb, db;
       ters_fc(rij, pij.R, pij.D, fc, dfc);
-      ters_bij(zeta, pij, bb, db);
+      ters_bij(zeta, pij, bcs ? bcs + 4 * row : nullptr, bb, db);
       const double er = pij.A * exp(-pij.lam1 * rij), ea = -pij.B * exp(-pij.lam2 * rij);
       const double fR = fc * er, dfR = er * (dfc - pij.lam1 * fc);
       const double fA = fc * ea, dfA = ea * (dfc - pij.lam2 * fc);
-      ei += 0.5 * (fR + bb * fA);
-      const double dEdr = 0.5 * (dfR + bb * dfA);
-      const double pref = 0.5 * fA * db;
-      double gjx = dEdr * ux, gjy = dEdr * uy, gjz = dEdr * uz;
-      if (pref != 0.0) {
-        for (int q = 0; q < a.n; ++q) {
-          if (q == p) continue;
-          const int u = a.slot[q];
-          const TersP pk = load_ters(params + (size_t)((ti * ntypes + tj) * ntypes + s.type[s.nj[i * max_nbr + u]]) * 14);
-          const double rik = a.r[q];
-          if (rik >= pk.R + pk.D) continue;
-          const double irik = 1.0 / rik;
-          const double wx = a.x[q] * irik, wy = a.y[q] * irik, wz = a.z[q] * irik;
-          const double cs = ux * wx + uy * wy + uz * wz;
+      e = 0.5 * (fR + bb * fA);
+      dEdr = 0.5 * (dfR + bb * dfA);
+      pref = 0.5 * fA * db;
+    }
+    s.pq[3 * k] = e; s.pq[3 * k + 1] = dEdr; s.pq[3 * k + 2] = pref;
+  }
+  __syncthreads();
+  // pass 2 (thread per pair iu): everything of centre i's energy that pulls on neighbour u
+  for (int k = threadIdx.x; k < np; k += NT) {
+    const int i = s.pi[k], ti = s.type[i];
+    int k0, k1;
+    pair_range(s, i, k0, k1);
+    const int tu = s.type[s.nj[i * max_nbr + s.pslot[k]]];
+    const double ux = s.pu[4 * k], uy = s.pu[4 * k + 1], uz = s.pu[4 * k + 2], ru = s.pu[4 * k + 3];
+    const double iru = 1.0 / ru;
+    const double pref_u = s.pq[3 * k + 2];
+    double gx = s.pq[3 * k + 1] * ux, gy = s.pq[3 * k + 1] * uy, gz = s.pq[3 * k + 1] * uz;
+    for (int q = k0; q < k1; ++q) {
+      if (q == k) continue;
+      const double pref_q = s.pq[3 * q + 2];
+      if (pref_u == 0.0 && pref_q == 0.0) continue;
+      const int tq = s.type[s.nj[i * max_nbr + s.pslot[q]]];
+      const double wx = s.pu[4 * q], wy = s.pu[4 * q + 1], wz = s.pu[4 * q + 2], rq = s.pu[4 * q + 3];
+      const double cs = ux * wx + uy * wy + uz * wz;
+      const double tx = (wx - cs * ux) * iru, ty = (wy - cs * uy) * iru, tz = (wz - cs * uz) * iru;   // d cos / d x_u
+      if (pref_u != 0.0) {      // triplet (i; j = u, k = q): u is the bonded atom
+        const TersP pk = load_ters(params + (size_t)((ti * ntypes + tu) * ntypes + tq) * 14);
+        if (rq < pk.R + pk.D) {
           double z, dzj, dzk, dzc;
-          ters_zeta_term(pk, rij, rik, cs, z, dzj, dzk, dzc);
-          const double djx = pref * (dzj * ux + dzc * (wx - cs * ux) * irij);
-          const double djy = pref * (dzj * uy + dzc * (wy - cs * uy) * irij);
-          const double djz = pref * (dzj * uz + dzc * (wz - cs * uz) * irij);
-          const double dkx = pref * (dzk * wx + dzc * (ux - cs * wx) * irik);
-          const double dky = pref * (dzk * wy + dzc * (uy - cs * wy) * irik);
-          const double dkz = pref * (dzk * wz + dzc * (uz - cs * wz) * irik);
-          gjx += djx; gjy += djy; gjz += djz;
-          Gi[3 * u] += dkx; Gi[3 * u + 1] += dky; Gi[3 * u + 2] += dkz;
-          gix -= dkx; giy -= dky; giz -= dkz;
+          ters_zeta_term(pk, ru, rq, cs, z, dzj, dzk, dzc);
+          gx += pref_u * (dzj * ux + dzc * tx); gy += pref_u * (dzj * uy + dzc * ty); gz += pref_u * (dzj * uz + dzc * tz);
         }
       }
-      Gi[3 * t] += gjx; Gi[3 * t + 1] += gjy; Gi[3 * t + 2] += gjz;
-      gix -= gjx; giy -= gjy; giz -= gjz;
+      if (pref_q != 0.0) {      // triplet (i; j = q, k = u): u is the third atom
+        const TersP pk = load_ters(params + (size_t)((ti * ntypes + tq) * ntypes + tu) * 14);
+        if (ru < pk.R + pk.D) {
+          double z, dzj, dzk, dzc;
+          ters_zeta_term(pk, rq, ru, cs, z, dzj, dzk, dzc);
+          gx += pref_q * (dzk * ux + dzc * tx); gy += pref_q * (dzk * uy + dzc * ty); gz += pref_q * (dzk * uz + dzc * tz);
+        }
+      }
     }
-    s.own[3 * i] = gix; s.own[3 * i + 1] = giy; s.own[3 * i + 2] = giz;
-    s.eat[i] = ei;
+    s.pG[3 * k] = gx; s.pG[3 * k + 1] = gy; s.pG[3 * k + 2] = gz;
   }
+  __syncthreads();
+  pairs_to_centres(s, n);
 }
 
 // ---------------------------------------------------------------------------------- SW
@@ -320,79 +419,80 @@ __device__ __forceinline__ SWP load_sw(const double* __restrict__ p) {
   t.p = p[8]; t.q = p[9];
   return t;
 }
+// x^y for the exponents SW parameter files actually use (p = 4, q = 0), general pow otherwise
+__device__ __forceinline__ double sw_pow(double x, double y) {
+  if (y == 0.0) return 1.0;
+  if (y == 4.0) { const double x2 = x * x; return x2 * x2; }
+  return pow(x, y);
+}
 
 __device__ void sw_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, const double* __restrict__ params,
                           int ntypes, double rcut, int32_t* status) {
-  for (int i = threadIdx.x; i < n; i += NT) {
-    const int ti = s.type[i], ci_n = s.cnt[i];
-    double gix = 0.0, giy = 0.0, giz = 0.0, ei = 0.0;
-    double* Gi = s.G + (size_t)i * max_nbr * 3;
-    for (int t = 0; t < ci_n; ++t) { Gi[3 * t] = 0.0; Gi[3 * t + 1] = 0.0; Gi[3 * t + 2] = 0.0; }
-    Active a;
-    gather_active(s, ci, i, max_nbr, rcut, a, status);
-    for (int p = 0; p < a.n; ++p) {
-      const int t = a.slot[p];
-      const int tj = s.type[s.nj[i * max_nbr + t]];
-      const SWP pij = load_sw(params + (size_t)((ti * ntypes + tj) * ntypes + tj) * 10);
-      const double cutij = pij.a * pij.sigma;
-      const double jx = a.x[p], jy = a.y[p], jz = a.z[p], rij = a.r[p];
-      if (rij >= cutij) continue;
+  build_pairs(s, ci, n, max_nbr, rcut, status);
+  const int np = min(s.pstart[n], s.pcap);
+  // pass 1 (thread per pair ij): two-body term (half per direction) and the pair's three-body exponential
+  for (int k = threadIdx.x; k < np; k += NT) {
+    const int i = s.pi[k], ti = s.type[i];
+    const int tj = s.type[s.nj[i * max_nbr + s.pslot[k]]];
+    const SWP pij = load_sw(params + (size_t)((ti * ntypes + tj) * ntypes + tj) * 10);
+    const double cutij = pij.a * pij.sigma, rij = s.pu[4 * k + 3];
+    double e = 0.0, dEdr = 0.0, live = 0.0, ex3 = 0.0, dex3 = 0.0;
+    if (rij < cutij) {
       const double irij = 1.0 / rij;
-      const double ux = jx * irij, uy = jy * irij, uz = jz * irij;
-      {   // two-body (half per direction)
-        const double sr = pij.sigma * irij;
-        const double srp = pow(sr, pij.p), srq = pow(sr, pij.q);
-        const double rc = rij - cutij;
-        const double ex = exp(pij.sigma / rc);
-        const double pre = pij.A * pij.eps;
-        const double poly = pij.B * srp - srq;
-        const double phi = pre * poly * ex;
-        const double dpoly = (-pij.p * pij.B * srp + pij.q * srq) * irij;
-        const double dphi = pre * (dpoly * ex + poly * ex * (-pij.sigma / (rc * rc)));
-        ei += 0.5 * phi;
-        const double g = 0.5 * dphi;
-        Gi[3 * t] += g * ux; Gi[3 * t + 1] += g * uy; Gi[3 * t + 2] += g * uz;
-        gix -= g * ux; giy -= g * uy; giz -= g * uz;
-      }
-      const double gsij = pij.gamma * pij.sigma;
-      const double rcij = rij - cutij;
-      const double exij = exp(gsij / rcij);
-      const double dexij = -gsij / (rcij * rcij);
-      for (int q = p + 1; q < a.n; ++q) {
-        const int u = a.slot[q];
-        const int tk = s.type[s.nj[i * max_nbr + u]];
-        const SWP pik = load_sw(params + (size_t)((ti * ntypes + tk) * ntypes + tk) * 10);
-        const SWP pijk = load_sw(params + (size_t)((ti * ntypes + tj) * ntypes + tk) * 10);
-        const double cutik = pik.a * pik.sigma;
-        const double rik = a.r[q];
-        if (rik >= cutik) continue;
-        const double irik = 1.0 / rik;
-        const double wx = a.x[q] * irik, wy = a.y[q] * irik, wz = a.z[q] * irik;
+      const double sr = pij.sigma * irij;
+      const double srp = sw_pow(sr, pij.p), srq = sw_pow(sr, pij.q);
+      const double rc = rij - cutij;
+      const double ex = exp(pij.sigma / rc);
+      const double pre = pij.A * pij.eps;
+      const double poly = pij.B * srp - srq;
+      const double phi = pre * poly * ex;
+      const double dpoly = (-pij.p * pij.B * srp + pij.q * srq) * irij;
+      const double dphi = pre * (dpoly * ex + poly * ex * (-pij.sigma / (rc * rc)));
+      e = 0.5 * phi;
+      dEdr = 0.5 * dphi;
+      const double gs = pij.gamma * pij.sigma;
+      ex3 = exp(gs / rc);
+      dex3 = -gs / (rc * rc);
+      live = 1.0;
+    }
+    s.pq[3 * k] = e; s.pq[3 * k + 1] = dEdr; s.pq[3 * k + 2] = live;
+    s.pa[2 * k] = ex3; s.pa[2 * k + 1] = dex3;
+  }
+  __syncthreads();
+  // pass 2 (thread per pair iu): pair term + the u-leg of every triplet (i; u, q) of the centre
+  for (int k = threadIdx.x; k < np; k += NT) {
+    double gx = 0.0, gy = 0.0, gz = 0.0, e3 = 0.0;
+    if (s.pq[3 * k + 2] != 0.0) {
+      const int i = s.pi[k], ti = s.type[i];
+      int k0, k1;
+      pair_range(s, i, k0, k1);
+      const int tu = s.type[s.nj[i * max_nbr + s.pslot[k]]];
+      const double ux = s.pu[4 * k], uy = s.pu[4 * k + 1], uz = s.pu[4 * k + 2], iru = 1.0 / s.pu[4 * k + 3];
+      const double exu = s.pa[2 * k], dexu = s.pa[2 * k + 1];
+      gx = s.pq[3 * k + 1] * ux; gy = s.pq[3 * k + 1] * uy; gz = s.pq[3 * k + 1] * uz;
+      for (int q = k0; q < k1; ++q) {
+        if (q == k || s.pq[3 * q + 2] == 0.0) continue;
+        const int tq = s.type[s.nj[i * max_nbr + s.pslot[q]]];
+        // LAMMPS orders a triplet by the neighbour list: (j, k) = (earlier, later) pair of the centre
+        const double* pr = params + (size_t)((ti * ntypes + (k < q ? tu : tq)) * ntypes + (k < q ? tq : tu)) * 10;
+        const double le = pr[3] * pr[0], cos0 = pr[5];
+        const double wx = s.pu[4 * q], wy = s.pu[4 * q + 1], wz = s.pu[4 * q + 2];
         const double cs = ux * wx + uy * wy + uz * wz;
-        const double gsik = pik.gamma * pik.sigma;
-        const double rcik = rik - cutik;
-        const double exik = exp(gsik / rcik);
-        const double dexik = -gsik / (rcik * rcik);
-        const double dc = cs - pijk.cos0;
-        const double le = pijk.lam * pijk.eps;
-        const double ee = exij * exik;
+        const double dc = cs - cos0;
+        const double ee = k < q ? exu * s.pa[2 * q] : s.pa[2 * q] * exu;
         const double h = le * dc * dc * ee;
-        ei += h;
-        const double dh_drij = h * dexij, dh_drik = h * dexik, dh_dcos = 2.0 * le * dc * ee;
-        const double djx = dh_drij * ux + dh_dcos * (wx - cs * ux) * irij;
-        const double djy = dh_drij * uy + dh_dcos * (wy - cs * uy) * irij;
-        const double djz = dh_drij * uz + dh_dcos * (wz - cs * uz) * irij;
-        const double dkx = dh_drik * wx + dh_dcos * (ux - cs * wx) * irik;
-        const double dky = dh_drik * wy + dh_dcos * (uy - cs * wy) * irik;
-        const double dkz = dh_drik * wz + dh_dcos * (uz - cs * wz) * irik;
-        Gi[3 * t] += djx; Gi[3 * t + 1] += djy; Gi[3 * t + 2] += djz;
-        Gi[3 * u] += dkx; Gi[3 * u + 1] += dky; Gi[3 * u + 2] += dkz;
-        gix -= djx + dkx; giy -= djy + dky; giz -= djz + dkz;
+        const double dh_dru = h * dexu, dh_dcos = 2.0 * le * dc * ee;
+        gx += dh_dru * ux + dh_dcos * (wx - cs * ux) * iru;
+        gy += dh_dru * uy + dh_dcos * (wy - cs * uy) * iru;
+        gz += dh_dru * uz + dh_dcos * (wz - cs * uz) * iru;
+        if (k < q) e3 += h;
       }
     }
-    s.own[3 * i] = gix; s.own[3 * i + 1] = giy; s.own[3 * i + 2] = giz;
-    s.eat[i] = ei;
+    s.pG[3 * k] = gx; s.pG[3 * k + 1] = gy; s.pG[3 * k + 2] = gz;
+    s.pq[3 * k] += e3;
   }
+  __syncthreads();
+  pairs_to_centres(s, n);
 }
 
 // ---------------------------------------------------------------------------------- EAM (funcfl, one element)
@@ -474,8 +574,9 @@ __device__ void eam_phase1(const Smem& s, const Cell64& ci, int n, int max_nbr, 
 
 // phase 1 (centre terms) + phase 2 (gather through reverse map) -> s.f = -dE/dx ; returns E (all threads)
 __device__ double eval_forces(int kind, const Smem& s, const Cell64& ci, int n, int max_nbr,
-                              const double* __restrict__ params, int ntypes, double rcut, int32_t* status) {
-  if (kind == VSSR_POT_TERSOFF) tersoff_phase1(s, ci, n, max_nbr, params, ntypes, rcut, status);
+                              const double* __restrict__ params, const double* __restrict__ bcs, int ntypes, double rcut,
+                              int32_t* status) {
+  if (kind == VSSR_POT_TERSOFF) tersoff_phase1(s, ci, n, max_nbr, params, bcs, ntypes, rcut, status);
   else if (kind == VSSR_POT_SW) sw_phase1(s, ci, n, max_nbr, params, ntypes, rcut, status);
   else eam_phase1(s, ci, n, max_nbr, params, rcut);
   __syncthreads();
@@ -486,7 +587,14 @@ __device__ double eval_forces(int kind, const Smem& s, const Cell64& ci, int n, 
       const int i = s.nj[j * max_nbr + t];
       const int r = s.rev[j * max_nbr + t];
       if (r == 255) continue;
-      const double* g = s.G + ((size_t)i * max_nbr + r) * 3;
+      const double* g;
+      if (kind == VSSR_POT_EAM) {
+        g = s.G + ((size_t)i * max_nbr + r) * 3;
+      } else {                        // j's slot in centre i's pair table, if j is inside i's cutoff right now
+        const int a = s.aidx[i * max_nbr + r];
+        if (a == 255) continue;
+        g = s.pG + (size_t)(s.pstart[i] + a) * 3;
+      }
       gx += g[0]; gy += g[1]; gz += g[2];
     }
     s.f[3 * j] = -gx; s.f[3 * j + 1] = -gy; s.f[3 * j + 2] = -gz;
@@ -549,7 +657,7 @@ __global__ void __launch_bounds__(NT) classical_kernel(int kind, const double* _
                                                        double* __restrict__ out_eatom, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) char smem_raw[];
   Smem s;
-  smem_layout(n_max, max_nbr, smem_raw, &s);
+  smem_layout(kind, n_max, max_nbr, smem_raw, &s);
   const int b = blockIdx.x;
   const int a0 = atom_ptr[b], a1 = atom_ptr[b + 1];
   int n = a1 - a0;
@@ -575,11 +683,19 @@ __global__ void __launch_bounds__(NT) classical_kernel(int kind, const double* _
     sprm = sprm_buf;
     __syncthreads();
   }
+  // Tersoff: the regime thresholds of b_ij per parameter row (two pow each), formed once per CTA
+  __shared__ double sbc_buf[27 * 4];
+  const double* bcs = nullptr;
+  if (kind == VSSR_POT_TERSOFF && ntypes <= 3) {
+    for (int q = threadIdx.x; q < ntypes * ntypes * ntypes; q += NT) ters_bij_consts(sprm[q * 14 + 6], sbc_buf + 4 * q);
+    bcs = sbc_buf;
+    __syncthreads();
+  }
   const double rcut = max_cut(kind, sprm, ntypes);
   const double rl = rcut + (RELAX ? skin : 0.0);
   build_list(s, ci, n, max_nbr, rl, status);
 
-  double energy = eval_forces(kind, s, ci, n, max_nbr, sprm, ntypes, rcut, status);
+  double energy = eval_forces(kind, s, ci, n, max_nbr, sprm, bcs, ntypes, rcut, status);
   if (!RELAX) {
     for (int i = threadIdx.x; i < n; i += NT) {
       for (int c = 0; c < 3; ++c) out_forces[3 * (a0 + i) + c] = s.f[3 * i + c];
@@ -658,7 +774,7 @@ __global__ void __launch_bounds__(NT) classical_kernel(int kind, const double* _
     }
     nsteps += 1;
     if (__syncthreads_or(moved)) build_list(s, ci, n, max_nbr, rl, status);
-    energy = eval_forces(kind, s, ci, n, max_nbr, sprm, ntypes, rcut, status);
+    energy = eval_forces(kind, s, ci, n, max_nbr, sprm, bcs, ntypes, rcut, status);
   }
   for (int i = threadIdx.x; i < n; i += NT)
     for (int c = 0; c < 3; ++c) {
@@ -686,8 +802,8 @@ int set_smem(size_t bytes) {
 
 }  // namespace
 
-extern "C" size_t vssr_classical_smem_bytes(int32_t n_max, int32_t max_nbr) {
-  return smem_layout(n_max, max_nbr, nullptr, nullptr);
+extern "C" size_t vssr_classical_smem_bytes(int32_t kind, int32_t n_max, int32_t max_nbr) {
+  return smem_layout(kind, n_max, max_nbr, nullptr, nullptr);
 }
 
 extern "C" int vssr_classical_energy_forces(int32_t kind, const double* params, int32_t ntypes, const double* pos,
@@ -699,7 +815,7 @@ extern "C" int vssr_classical_energy_forces(int32_t kind, const double* params, 
   if (kind != VSSR_POT_TERSOFF && kind != VSSR_POT_SW && kind != VSSR_POT_EAM) return VSSR_ERR_UNSUPPORTED;
   if (kind == VSSR_POT_EAM && ntypes != 1) return VSSR_ERR_UNSUPPORTED;   // funcfl: one element
   if (n_struct <= 0 || n_max <= 0 || n_max > 32767 || max_nbr <= 0 || max_nbr > 254) return VSSR_ERR_ARG;
-  const size_t smem = smem_layout(n_max, max_nbr, nullptr, nullptr);
+  const size_t smem = smem_layout(kind, n_max, max_nbr, nullptr, nullptr);
   if (smem > 227 * 1024) return VSSR_ERR_ARG;
   int rc = set_smem<false>(smem);
   if (rc) return rc;
@@ -719,7 +835,7 @@ extern "C" int vssr_classical_relax(int32_t kind, const double* params, int32_t 
   if (kind == VSSR_POT_EAM && ntypes != 1) return VSSR_ERR_UNSUPPORTED;
   if (n_struct <= 0 || n_max <= 0 || n_max > 32767 || max_nbr <= 0 || max_nbr > 254 || relax_steps < 0 || skin < 0)
     return VSSR_ERR_ARG;
-  const size_t smem = smem_layout(n_max, max_nbr, nullptr, nullptr);
+  const size_t smem = smem_layout(kind, n_max, max_nbr, nullptr, nullptr);
   if (smem > 227 * 1024) return VSSR_ERR_ARG;
   int rc = set_smem<true>(smem);
   if (rc) return rc;

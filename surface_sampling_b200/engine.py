@@ -468,14 +468,15 @@ class ClassicalEngine:
         self.kind, self.ntypes, self.n_max, self.max_nbr, self.skin = kind, ntypes, n_max, max_nbr, skin
         self.device = torch.device(device)
         self.params = torch.from_numpy(np.ascontiguousarray(params, dtype=np.float64)).to(self.device)
-        smem = int(self.lib.vssr_classical_smem_bytes(n_max, max_nbr))
+        smem = int(self.lib.vssr_classical_smem_bytes(kind, n_max, max_nbr))
         if smem > 227 * 1024:
             raise ValueError(f"n_max={n_max}, max_nbr={max_nbr} needs {smem} B shared memory (> 227 KB)")
 
     def _check_status(self, status):
         s = int(status.item())
         if s & 2:
-            raise _lib.VssrError("classical kernel: neighbour slots overflowed (raise max_nbr)")
+            raise _lib.VssrError("classical kernel: neighbour slots overflowed (raise max_nbr; Tersoff / SW also keep at most "
+                                 "8 * n_max atom pairs inside the potential cutoff: raise n_max)")
         if s & 4:
             raise _lib.VssrError("classical kernel: structure larger than n_max")
 

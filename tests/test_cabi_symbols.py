@@ -28,7 +28,7 @@ def test_host_only_queries():
     assert lib.vssr_version() == 100
     assert int(lib.vssr_painn_weight_floats()) == engine.painn_weight_floats()
     assert lib.vssr_painn_workspace_bytes(3, 60, 4000) > 3 * 60 * 128 * 4
-    assert lib.vssr_classical_smem_bytes(64, 24) < 227 * 1024
+    assert lib.vssr_classical_smem_bytes(0, 64, 24) < 227 * 1024
 
 
 def test_weight_packing_roundtrip():
