@@ -200,3 +200,24 @@ def test_eam_cu_calculator_and_toy_mc(golden_values):
         assert [x[0] for x in drv.decisions[k]] == [x[0] for x in o["decisions"]]
         assert np.allclose([x[1] for x in drv.decisions[k]], [x[1] for x in o["decisions"]], rtol=1e-10, atol=1e-9)
         assert np.allclose(res["energy_hist"][k], o["energy_hist"], rtol=1e-10, atol=1e-9)
+
+
+def test_pair_table_overflow_is_reported(structures):
+    """Tersoff / SW keep the directed pairs inside the potential cutoff in a shared-memory table of 8 * n_max entries.
+    The Si slab compressed by 5 % pulls the second shell inside the SW cutoff (12.5 pairs per atom, 1250 in all): with
+    n_max = 100 that does not fit and the kernel must say so through the status word (VssrError), never return numbers
+    from a truncated table; with n_max = 160 (1280 entries) it runs and matches the oracle."""
+    from surface_sampling_b200 import _lib, engine
+    base = structures["Si_111_5x5"]
+    dense = dict(base, positions=base["positions"] * 0.95, cell=np.asarray(base["cell"]) * 0.95)
+    n = len(base["numbers"])
+    assert n == 100
+    types = [np.zeros(n, np.int32)]
+    tight = engine.ClassicalEngine(engine.POT_SW, engine.sw_param_table(), 1, n_max=n, max_nbr=24)
+    with pytest.raises(_lib.VssrError):
+        tight.energy_forces(_batch([dense], types))
+    roomy = engine.ClassicalEngine(engine.POT_SW, engine.sw_param_table(), 1, n_max=160, max_nbr=24)
+    r = roomy.energy_forces(_batch([dense], types))
+    e0, f0 = ocl.energy_forces(ocl.sw_energy, dense["positions"], dense["cell"], dense["pbc"], ocl.SWParams())
+    assert abs(r["energy"].cpu().numpy()[0] - e0) < 1e-9 * abs(e0)
+    assert np.abs(r["forces"].cpu().numpy() - f0).max() < 1e-7
