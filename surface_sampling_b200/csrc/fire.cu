@@ -350,9 +350,11 @@ struct GraphPool {
     return VSSR_OK;
   }
 };
-GraphPool& graph_pool() {
-  static thread_local GraphPool pool;
-  return pool;
+GraphPool& graph_pool() {       // per thread AND per device: the capture stream lives on one device
+  static thread_local GraphPool pools[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return pools[dev & 63];
 }
 }  // namespace
 
