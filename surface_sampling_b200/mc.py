@@ -70,7 +70,11 @@ class ChainState:
     def snapshot(self):
         return (list(self.numbers), list(self.positions), list(self.ads_group), self.occ.copy(), dict(self.results))
 
-    def restore(self, snap):
+    def restore(self, snap, adopt=False):
+        """adopt=True takes over the snapshot's containers instead of copying them (the caller drops the snapshot)."""
+        if adopt:
+            self.numbers, self.positions, self.ads_group, self.occ, self.results = snap
+            return
         self.numbers, self.positions, self.ads_group, self.occ, self.results = (
             list(snap[0]), list(snap[1]), list(snap[2]), snap[3].copy(), dict(snap[4]))
 
@@ -141,7 +145,8 @@ class ChainState:
 
     def remove_atom(self, site_idx, start_ads):
         idx = int(self.occ[site_idx])
-        assert np.count_nonzero(self.occ == idx) == 1, "no sites found" if not np.any(self.occ == idx) else "more than 1 site found"
+        hits = int((self.occ == idx).sum())
+        assert hits == 1, "no sites found" if hits == 0 else "more than 1 site found"
         n = len(start_ads)
         if n > 1 and hill_formula(start_ads) not in ATOM_GROUPS:
             raise ValueError(f"Unknown group name: {hill_formula(start_ads)}")
@@ -150,9 +155,10 @@ class ChainState:
         del self.ads_group[idx:idx + n]
         # slab.py:372-395 shifts every index >= idx down by n and clamps negatives to 0.  A group id is the index of
         # its first atom, so only entries behind the removed block can be >= idx, and idx >= n0 > n keeps them positive.
-        occ = self.occ.copy()
-        occ[occ >= idx] -= n
-        occ[occ < 0] = 0
+        occ = self.occ
+        occ = np.where(occ >= idx, occ - n, occ)      # (a fresh array: snapshots keep theirs)
+        if n >= idx:                                  # never with idx >= n0 > n; kept for the reference's clamp
+            occ[occ < 0] = 0
         occ[site_idx] = 0
         self.occ = occ
         ag = self.ads_group
@@ -179,11 +185,22 @@ class ChainState:
     def propose_switch(self):
         """SwitchProposal.get_action -> get_complementary_idx with uniform weights (slab.py:168-232).
         Note the reference's groupby-into-dict keeps only the LAST run of each symbol; replicated."""
-        occ = self.occ.tolist()
-        filled = [x for x, o in enumerate(occ) if o != 0]
         numbers = self.numbers
-        curr = {k: list(g) for k, g in itertools.groupby(filled, key=lambda x: SYMBOLS[numbers[occ[x]]])}
-        empty = [x for x, o in enumerate(occ) if o == 0]
+        # {symbol: sites of its LAST run} in first-appearance order of the symbols -- what the reference's
+        # {k: list(g) for k, g in groupby(filled, key=symbol)} builds (a repeated key keeps its slot, takes the new
+        # run) -- in one pass over the sites
+        curr, empty, last, run = {}, [], None, None
+        for x, o in enumerate(self.occ.tolist()):
+            if o == 0:
+                empty.append(x)
+                continue
+            sym = SYMBOLS[numbers[o]]
+            if sym == last:
+                run.append(x)
+            else:
+                run = [x]
+                curr[sym] = run
+                last = sym
         if empty:
             curr["None"] = empty
         t1, t2 = self.py_rng.sample(list(curr.keys()), 2)
@@ -305,17 +322,22 @@ class MultiChainMC:
         self.temp = 1.0
         self.n_relaxed = 0
         self.decisions = [[] for _ in seeds]        # per chain: (accept, curr, prev, u)
+        self._fixed_masks = {}
 
     # -- hot path call ------------------------------------------------------------------------
     # relax_fn may return out[C,8] directly, or a handle with .result() -> out[C,8] when the engine call is
     # asynchronous (the relaxation is enqueued on the GPU and only result() waits for the 8 scalars per chain)
     def _launch(self, chains):
         pos, num, fix = [], [], []
+        masks = self._fixed_masks
         for c in chains:
             p, z = c.arrays()
             pos.append(p)
             num.append(z)
-            fix.append(np.concatenate([self.fixed0, np.zeros(len(z) - len(self.fixed0), dtype=bool)]))
+            m = masks.get(len(z))
+            if m is None:       # the frozen mask depends on the atom count only (adsorbates are appended, never frozen)
+                m = masks[len(z)] = np.concatenate([self.fixed0, np.zeros(len(z) - len(self.fixed0), dtype=bool)])
+            fix.append(m)
         fns = [self.surface_energy_fn[c.index] for c in chains] if self._se_per_chain else None
         if self.energy_memo is not None:
             return self._launch_memo(pos, num, fix), num, fns
@@ -418,9 +440,8 @@ class MultiChainMC:
                 c.results["surface_energy"] = curr[k]
             else:
                 snap = snaps[k]
-                res = dict(snap[4])
-                res["surface_energy"] = prev[k]
-                c.restore((snap[0], snap[1], snap[2], snap[3], res))
+                snap[4]["surface_energy"] = prev[k]
+                c.restore(snap, adopt=True)      # the ticket's snapshot is not used again
             self.decisions[idx[k]].append((acc, curr[k], prev[k], u))
             accepts.append(acc)
         return accepts
