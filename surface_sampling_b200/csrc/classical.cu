@@ -798,11 +798,15 @@ __global__ void __launch_bounds__(NT, 2) classical_kernel(int kind, const double
 
 template <bool RELAX>
 int set_smem(size_t bytes) {
-  static size_t configured = 0;
-  if (bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(classical_kernel<RELAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  static size_t configured[64] = {};   // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  size_t& c = configured[dev & 63];
+  if (bytes > c) {
+    e = cudaFuncSetAttribute(classical_kernel<RELAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    configured = bytes;
+    c = bytes;
   }
   return 0;
 }
