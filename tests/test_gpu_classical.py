@@ -221,3 +221,36 @@ def test_pair_table_overflow_is_reported(structures):
     e0, f0 = ocl.energy_forces(ocl.sw_energy, dense["positions"], dense["cell"], dense["pbc"], ocl.SWParams())
     assert abs(r["energy"].cpu().numpy()[0] - e0) < 1e-9 * abs(e0)
     assert np.abs(r["forces"].cpu().numpy() - f0).max() < 1e-7
+
+
+@pytest.mark.parametrize("kind", ["tersoff", "sw"])
+def test_edge_cases_isolated_atoms_and_size_limit(structures, potentials, kind):
+    """Ragged batch: an isolated atom (no pair inside the cutoff), a dimer outside the cutoff, a bonded dimer and a normal
+    slab in one launch -- zero energy and force where nothing interacts, the slab unchanged by its neighbours in the
+    batch; a structure larger than n_max is reported, not truncated silently."""
+    from surface_sampling_b200 import _lib, engine
+    if kind == "tersoff":
+        eng = engine.ClassicalEngine(engine.POT_TERSOFF, engine.tersoff_param_table(potentials["GaN.tersoff"], ["Ga", "N"]), 2,
+                                     n_max=64, max_nbr=32)
+        base, z, d_bond = structures["GaN_0001_3x3"], 31, 2.4
+        tab = {31: 0, 7: 1}
+    else:
+        eng = engine.ClassicalEngine(engine.POT_SW, engine.sw_param_table(), 1, n_max=128, max_nbr=32)
+        base, z, d_bond = structures["Si_111_5x5"], 14, 2.35
+        tab = {14: 0}
+    box = np.eye(3) * 30.0
+    pbc = np.array([True, True, True])
+    mk = lambda pts: {"positions": np.array(pts, float), "numbers": np.full(len(pts), z), "cell": box, "pbc": pbc}
+    structs = [mk([[1, 1, 1]]), mk([[1, 1, 1], [9, 1, 1]]), mk([[1, 1, 1], [1 + d_bond, 1, 1]]), base]
+    types = [np.array([tab[int(q)] for q in s["numbers"]], np.int32) for s in structs]
+    b = _batch(structs, types)
+    r = eng.energy_forces(b)
+    e = r["energy"].cpu().numpy()
+    f = b.split_host(r["forces"].cpu().numpy())
+    assert e[0] == 0.0 and e[1] == 0.0 and not f[0].any() and not f[1].any()
+    assert e[2] != 0.0 and np.abs(f[2][0] + f[2][1]).max() < 1e-12 and abs(f[2][0][0]) > 1e-3 and not f[2][:, 1:].any()
+    alone = eng.energy_forces(_batch([base], [types[3]]))
+    assert alone["energy"].cpu().numpy()[0] == e[3] and np.array_equal(alone["forces"].cpu().numpy(), f[3])
+    small = engine.ClassicalEngine(eng.kind, eng.params.cpu().numpy(), eng.ntypes, n_max=len(base["numbers"]) - 1, max_nbr=32)
+    with pytest.raises(_lib.VssrError):
+        small.energy_forces(_batch([base], [types[3]]))
