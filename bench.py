@@ -725,8 +725,9 @@ def classical_roofline(breakdown, a_prof, evals, peaks, name=None, proposals=0):
             "hbm_if_streamed": {"achieved_gbs": streamed, "peak_gbs": hbm, "frac": streamed / hbm,
                                 "note": "SURVEY.md 8d: 53 B per atom-evaluation; the kernel keeps the relaxation in shared "
                                         "memory, so this only shows that it is not bandwidth-bound"},
-            "note": "one 128-thread CTA per chain, whole relaxation (<= 100 FIRE steps, converged chains stop early) inside "
-                    "the SM: bound by FP64 issue latency at 4 warps per CTA, not by the pipe's throughput"}
+            "note": "one 256-thread CTA per chain (thread per directed atom pair), whole relaxation (<= 100 dependent FIRE "
+                    "steps, converged chains stop early) inside the SM: latency-bound per chain, the chain count is the "
+                    "parallelism (see `saturation`)"}
     f = ROOT / "profiles" / "round2_classical_fp64.json"
     if f.exists() and name:
         d = json.loads(f.read_text()).get(name)
