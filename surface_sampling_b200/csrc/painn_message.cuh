@@ -164,6 +164,7 @@ __device__ __forceinline__ void row_table_slice(RowTable& rt, const float* __res
         e_lo += __popc(__ballot_sync(0xffffffffu, j < lo));
         e_hi += __popc(__ballot_sync(0xffffffffu, j < hi));
       }
+      __syncwarp();     // every lane has read the slot (orders the reads above against the write below)
       if (lane == 0 && t < nt) { rt.e0[t] = e0[u] + e_lo; rt.ne[t] = e_hi - e_lo; }
     }
   }
