@@ -64,11 +64,19 @@ def test_overflowing_boltzmann_factor_accepts():
     assert drv.step() == [True]
 
 
+def _free_port() -> str:
+    """A port the kernel just handed out: back-to-back runs of the suite must not trip over a socket in TIME_WAIT."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return str(sk.getsockname()[1])
+
+
 @pytest.mark.timeout(120)
 def test_sharded_statistics_gather_gloo_world2(tmp_path):
     """Chains shard across ranks with no data-path collective; only per-sweep scalars are gathered."""
     script = ROOT / "tests" / "_gloo_worker.py"
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", PYTHONPATH=str(ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=_free_port(), PYTHONPATH=str(ROOT))
     procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", str(tmp_path)], env=env) for r in range(2)]
     assert all(p.wait(timeout=100) == 0 for p in procs)
     got = np.load(tmp_path / "gathered.npy")
@@ -95,7 +103,7 @@ def test_pourbaix_grid_shards_over_ranks_gloo_world2(tmp_path):
     (parallel.shard_grid); every unit carries its own grand-potential scalar; only per-sweep scalars are gathered.
     Two gloo ranks reproduce the single-process run unit by unit."""
     script = ROOT / "tests" / "_gloo_worker.py"
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29733", PYTHONPATH=str(ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=_free_port(), PYTHONPATH=str(ROOT))
     procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", str(tmp_path), "grid"], env=env) for r in range(2)]
     assert all(p.wait(timeout=160) == 0 for p in procs)
     got = np.load(tmp_path / "gathered.npy")
